@@ -1,0 +1,195 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference classes (dev container only).
+
+    python oracle/make_golden.py
+
+Every array written here is an output (or an input) of the reference's own code
+(/root/reference: GymEnvModel, RolloutWorker, simple_evolution, simple_genetic, openai_es, Adam)
+driven through the duck-typed env shims of oracle/pyref.py.  np.argsort is pinned to
+kind="stable" while evaluate() runs.  The fixtures are committed; this
+script is committed so they can be regenerated.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+
+from oracle import pyref, ref_bridge  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def flat_of(model):
+    return np.concatenate([p.ravel() for p in model.get_param_list()]).astype(np.float32)
+
+
+def set_flat(model, flat, obs, act, gru):
+    model.apply_param(pyref.flat_to_list(flat, obs, act, gru))
+
+
+class TracingCartPole(pyref.CartPoleShim):
+    """CartPoleShim that records (state after step, action) for every step."""
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.log = []
+
+    def reset(self):
+        self.log.append(("reset",))
+        return super().reset()
+
+    def step(self, action):
+        out = super().step(action)
+        self.log.append((int(action["0"]), tuple(self.state)))
+        return out
+
+
+def golden_policy(ref, gru, n_models, n_steps, seed):
+    rng = np.random.RandomState(seed)
+    obs_dim, act = 4, 2
+    D = pyref.param_count(obs_dim, act, gru)
+    W = (rng.normal(0, 2.0 if not gru else 0.7, size=(n_models, D))).astype(np.float32)
+    O = rng.uniform(-1, 1, size=(n_models, n_steps, obs_dim)) * np.array([2.4, 3.0, 0.21, 3.0])
+    A = np.zeros((n_models, n_steps), dtype=np.int64)
+    Z = np.zeros((n_models, n_steps, act), dtype=np.float32)
+    for i in range(n_models):
+        model = ref.GymEnvModel(obs_dim, act, True, gru)
+        set_flat(model, W[i], obs_dim, act, gru)
+        cap = []
+        hook = model.fc2.register_forward_hook(lambda m, inp, out: cap.append(out.detach().numpy().ravel().copy()))
+        model.reset()
+        for t in range(n_steps):
+            A[i, t] = int(model(O[i, t][np.newaxis, ...]))
+            Z[i, t] = cap[-1]
+        hook.remove()
+    return dict(W=W, obs=O, actions=A, logits=Z, gru=np.int32(gru))
+
+
+def golden_rollout(ref, gru, pomdp, P, E, seed, sigma, n_trace):
+    """Reference RolloutWorker + GymEnvModel over the CartPole shim with a fixed [E,4] table of
+    initial states shared by every offspring (pool semantics)."""
+    rng = np.random.RandomState(seed)
+    obs_dim, act = 4, 2
+    D = pyref.param_count(obs_dim, act, gru)
+    init = rng.uniform(-0.05, 0.05, size=(E, 4))
+    W = rng.normal(0, sigma, size=(P, D)).astype(np.float32)
+    W[0] = 0.0
+    fitness = np.zeros(P)
+    logs = []
+    for i in range(P):
+        model = ref.GymEnvModel(obs_dim, act, True, gru)
+        set_flat(model, W[i], obs_dim, act, gru)
+        env = TracingCartPole(max_step=500, pomdp=pomdp, init_states=init)
+        fitness[i] = ref.RolloutWorker((env, {"0": model}, E))
+        ep0 = []
+        for rec in env.log[1:]:
+            if rec[0] == "reset":
+                break
+            ep0.append(rec)
+        logs.append(ep0)
+    # trace the offspring whose first episode is longest (first 200 steps of episode 0)
+    trace_ids = np.argsort([-len(l) for l in logs], kind="stable")[:n_trace].astype(np.int32)
+    traces = np.full((n_trace, 200, 4), np.nan)
+    tr_actions = np.full((n_trace, 200), -1, dtype=np.int32)
+    for j, i in enumerate(trace_ids):
+        for t, rec in enumerate(logs[i][:200]):
+            tr_actions[j, t] = rec[0]
+            traces[j, t] = rec[1]
+    return dict(W=W, init=init, fitness=fitness, trace_ids=trace_ids, traces=traces, trace_actions=tr_actions,
+                gru=np.int32(gru), pomdp=np.int32(pomdp), E=np.int32(E), max_step=np.int32(500))
+
+
+def reward_vectors(P, rng):
+    """Three synthetic reward vectors: tie-free floats, CartPole-like tie-heavy k/5, mixed."""
+    r0 = rng.uniform(8, 500, size=P)
+    r1 = rng.randint(40, 60, size=P) / 5.0
+    r1[rng.randint(0, P, size=max(2, P // 4))] = 500.0
+    r2 = np.round(rng.uniform(8, 30, size=P))
+    return [r0, r1, r2]
+
+
+def golden_strategy(ref, name, seed):
+    obs_dim, act, gru = 4, 2, False
+    D = pyref.param_count(obs_dim, act, gru)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    if name == "simple_evolution":
+        cfg = dict(init_sigma=2.0, sigma_decay=0.99, elite_num=5, offspring_num=24)
+        strat = ref.simple_evolution(cfg["init_sigma"], cfg["sigma_decay"], cfg["elite_num"], cfg["offspring_num"])
+    elif name == "simple_genetic":
+        cfg = dict(init_sigma=1.0, sigma_decay=0.98, elite_num=4, offspring_num=26)
+        strat = ref.simple_genetic(cfg["init_sigma"], cfg["sigma_decay"], cfg["elite_num"], cfg["offspring_num"])
+    else:
+        cfg = dict(init_sigma=0.2, sigma_decay=0.999, learning_rate=0.1, offspring_num=40)
+        strat = ref.openai_es(cfg["init_sigma"], cfg["sigma_decay"], cfg["learning_rate"], cfg["offspring_num"])
+    net = ref.GymEnvModel(obs_dim, act, True, gru)
+    net.zero_init()
+    group = strat.init_offspring(net, ["0"])
+    out = {"cfg_" + k: np.float64(v) for k, v in cfg.items()}
+    rng = np.random.RandomState(seed + 1)
+    P = len(group)
+    rews = reward_vectors(P, rng)
+    out["P"] = np.int32(P)
+    for g, rewards in enumerate(rews):
+        pop = np.stack([flat_of(off["0"]) for off in group])
+        out["pop_%d" % g] = pop
+        out["rewards_%d" % g] = rewards
+        out["sigma_before_%d" % g] = np.float64(strat.curr_sigma)
+        if name == "openai_es":
+            out["eps_%d" % g] = np.stack([flat_of(e) for e in strat.epsilons])
+            out["mu_before_%d" % g] = flat_of(strat.mu_model)
+        sink = []
+        with ref_bridge.stable_argsort(ref.strategies), ref_bridge.capture_locals("evaluate", sink):
+            group, best, sigma = strat.evaluate(list(rewards))
+        loc = sink[-1]
+        out["best_%d" % g] = np.float64(best)
+        out["sigma_after_%d" % g] = np.float64(sigma)
+        if name == "openai_es":
+            out["order_%d" % g] = np.asarray(loc["offspring_rank_id"], dtype=np.int64)
+            out["shaped_%d" % g] = np.asarray(loc["reward_array"], dtype=np.float64)
+            out["update_factor_%d" % g] = np.float64(loc["update_factor"])
+            out["grad_%d" % g] = np.concatenate([p.ravel() for p in loc["grad_param_list"]]).astype(np.float32)
+            out["mu_after_%d" % g] = flat_of(strat.mu_model)
+            out["adam_m_%d" % g] = np.concatenate([p.ravel() for p in strat.optimizer.m]).astype(np.float32)
+            out["adam_v_%d" % g] = np.concatenate([p.ravel() for p in strat.optimizer.v]).astype(np.float32)
+            out["adam_t_%d" % g] = np.int64(strat.optimizer.t)
+        else:
+            out["elite_ids_%d" % g] = np.asarray(loc["elite_ids"], dtype=np.int64)
+            if name == "simple_evolution":
+                out["mu_after_%d" % g] = flat_of(strat.mu_model)
+            else:
+                out["elites_after_%d" % g] = np.stack([flat_of(m) for m in strat.elite_models])
+    out["pop_final"] = np.stack([flat_of(off["0"]) for off in group])
+    # unpinned argsort on the tie-free vector must agree with the pinned order
+    out["order_unpinned_0"] = np.flip(np.argsort(np.array(list(rews[0])))).astype(np.int64)
+    return out
+
+
+def main():
+    ref = ref_bridge.load()
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(1)
+    jobs = {
+        "policy_mlp": lambda: golden_policy(ref, False, 48, 32, 11),
+        "policy_gru": lambda: golden_policy(ref, True, 12, 40, 12),
+        "rollout_cartpole_mlp": lambda: golden_rollout(ref, False, False, 256, 5, 21, 2.0, 6),
+        "rollout_cartpole_gru_pomdp": lambda: golden_rollout(ref, True, True, 24, 3, 22, 0.7, 3),
+        "strategy_simple_evolution": lambda: golden_strategy(ref, "simple_evolution", 31),
+        "strategy_simple_genetic": lambda: golden_strategy(ref, "simple_genetic", 32),
+        "strategy_openai_es": lambda: golden_strategy(ref, "openai_es", 33),
+    }
+    only = sys.argv[1:]
+    for name, fn in jobs.items():
+        if only and name not in only:
+            continue
+        data = fn()
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **data)
+        print("wrote", path, {k: getattr(v, "shape", None) for k, v in data.items() if hasattr(v, "shape") and v.ndim > 0})
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,213 @@
+"""ctypes binding of the CPU bit-twin oracle (oracle/ses_twin.c).
+
+TEST INFRASTRUCTURE ONLY -- importable from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs; never from simple-es_b200/.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libses_twin.so")
+
+
+def build(force=False):
+    """Compile the twin with the committed Makefile (gcc only, seconds)."""
+    srcs = [os.path.join(_HERE, f) for f in ("ses_twin.c", "ses_twin_mpe.c", "Makefile")]
+    if not force and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs):
+        return _SO
+    subprocess.check_call(["make", "-s", "-C", _HERE], env={**os.environ, "CC": "/usr/bin/gcc"})
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        _lib = C.CDLL(_SO)
+        _lib.tw_rollout_cartpole.restype = C.c_int64
+        if hasattr(_lib, "tw_rollout_mpe"):
+            _lib.tw_rollout_mpe.restype = C.c_double
+    return _lib
+
+
+def _p(a, t=None):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+# ---------------------------------------------------------------------------- math hooks
+def philox(ctr, key):
+    ctr = np.ascontiguousarray(ctr, dtype=np.uint32)
+    key = np.ascontiguousarray(key, dtype=np.uint32)
+    out = np.zeros(4, dtype=np.uint32)
+    lib().tw_philox(_p(ctr), _p(key), _p(out))
+    return out
+
+
+def tanhf(x):
+    x = _f32(x); y = np.empty_like(x)
+    lib().tw_tanhf_v(_p(x), _p(y), C.c_int64(x.size))
+    return y
+
+
+def sigmf(x):
+    x = _f32(x); y = np.empty_like(x)
+    lib().tw_sigmf_v(_p(x), _p(y), C.c_int64(x.size))
+    return y
+
+
+def lnf(x):
+    x = _f32(x); y = np.empty_like(x)
+    lib().tw_lnf_v(_p(x), _p(y), C.c_int64(x.size))
+    return y
+
+
+def sincos2pif(x):
+    x = _f32(x); s = np.empty_like(x); c = np.empty_like(x)
+    lib().tw_sincos2pif_v(_p(x), _p(s), _p(c), C.c_int64(x.size))
+    return s, c
+
+
+def sincos(x):
+    x = _f64(x); s = np.empty_like(x); c = np.empty_like(x)
+    lib().tw_sincos_v(_p(x), _p(s), _p(c), C.c_int64(x.size))
+    return s, c
+
+
+def normals(seed, gen, idx, D):
+    out = np.empty(D, dtype=np.float32)
+    lib().tw_normals(C.c_uint32(seed), C.c_uint32(gen), C.c_uint32(idx), C.c_int(D), _p(out))
+    return out
+
+
+def param_count(obs, act, gru):
+    return int(lib().tw_param_count(C.c_int(obs), C.c_int(act), C.c_int(int(gru))))
+
+
+# ---------------------------------------------------------------------------- population
+def layout(strategy, P, offspring_num=None, elite_num=None):
+    """(group, n_head) of the population index layout."""
+    if strategy == "simple_evolution":
+        return P, 2
+    if strategy == "openai_es":
+        return P, 1
+    if strategy == "simple_genetic":
+        return offspring_num // elite_num, 1
+    raise ValueError(strategy)
+
+
+def materialize(parents, sigma, seed, gen, group, n_head, ids):
+    parents = _f32(parents)
+    if parents.ndim == 1:
+        parents = parents[None]
+    D = parents.shape[1]
+    ids = np.ascontiguousarray(ids, dtype=np.int32)
+    out = np.empty((ids.size, D), dtype=np.float32)
+    lib().tw_materialize(_p(parents), C.c_int(D), C.c_float(sigma), C.c_uint32(seed), C.c_uint32(gen),
+                         C.c_int(group), C.c_int(n_head), _p(ids), C.c_int(ids.size), _p(out))
+    return out
+
+
+def policy_step(w, obs, act, gru, o, h=None):
+    """One forward pass; returns (action, logits, new_h)."""
+    w = _f32(w); o = _f32(o)
+    hh = np.zeros(32, dtype=np.float32) if h is None else _f32(h).copy()
+    logits = np.zeros(act, dtype=np.float32)
+    a = lib().tw_policy_step(_p(w), C.c_int(obs), C.c_int(act), C.c_int(int(gru)), _p(o), _p(hh), _p(logits))
+    return int(a), logits, hh
+
+
+def cartpole_step(state, action):
+    st = _f64(state).copy()
+    d = lib().tw_cartpole_step_x(_p(st), C.c_int(int(action)))
+    return st, bool(d)
+
+
+def cartpole_init(seed, init_mode, gen, idx, e):
+    st = np.empty(4, dtype=np.float64)
+    lib().tw_cartpole_init(C.c_uint32(seed), C.c_int(init_mode), C.c_uint32(gen), C.c_uint32(idx), C.c_uint32(e), _p(st))
+    return st
+
+
+def rollout_cartpole(w, gru=False, pomdp=False, E=5, max_step=500, init=None, seed=0, init_mode=0, gen=0, idx=0,
+                     trace_steps=0):
+    """One offspring.  Returns (total_steps, trace[trace_steps,4], actions[trace_steps])."""
+    w = _f32(w)
+    init_a = None if init is None else _f64(init)
+    trace = np.full((max(trace_steps, 1), 4), np.nan, dtype=np.float64)
+    acts = np.full(max(trace_steps, 1), -1, dtype=np.int32)
+    t = lib().tw_rollout_cartpole(_p(w), C.c_int(int(gru)), C.c_int(int(pomdp)), C.c_int(E), C.c_int(max_step),
+                                  _p(init_a), C.c_uint32(seed), C.c_int(init_mode), C.c_uint32(gen), C.c_uint32(idx),
+                                  _p(trace), _p(acts), C.c_int(trace_steps))
+    return int(t), trace[:trace_steps], acts[:trace_steps]
+
+
+def population_cartpole(parents, gru=False, pomdp=False, sigma=0.0, seed=0, gen=0, group=1, n_head=1, id0=0, n=1,
+                        E=5, max_step=500, W_override=None, init=None, init_mode=0, nthreads=1):
+    """Fitness (float64) and total steps (int64) of offspring [id0, id0+n)."""
+    parents = _f32(parents)
+    Wo = None if W_override is None else _f32(W_override)
+    init_a = None if init is None else _f64(init)
+    fit = np.empty(n, dtype=np.float64)
+    steps = np.empty(n, dtype=np.int64)
+    lib().tw_population_cartpole(_p(parents), C.c_int(int(gru)), C.c_int(int(pomdp)), C.c_float(sigma),
+                                 C.c_uint32(seed), C.c_uint32(gen), C.c_int(group), C.c_int(n_head), C.c_int(id0),
+                                 C.c_int(n), C.c_int(E), C.c_int(max_step), _p(Wo), _p(init_a), C.c_int(init_mode),
+                                 _p(fit), _p(steps), C.c_int(nthreads))
+    return fit, steps
+
+
+# ---------------------------------------------------------------------------- K2 / K3
+def rank_desc(fitness):
+    f = _f64(fitness)
+    order = np.empty(f.size, dtype=np.int32)
+    lib().tw_rank_desc(_p(f), C.c_int(f.size), _p(order))
+    return order
+
+
+def centered_rank(order):
+    order = np.ascontiguousarray(order, dtype=np.int32)
+    shaped = np.empty(order.size, dtype=np.float64)
+    lib().tw_centered_rank(_p(order), C.c_int(order.size), _p(shaped))
+    return shaped
+
+
+def grad_openai(shaped, D, seed, gen, group, n_head, update_factor, eps=None):
+    shaped = _f64(shaped)
+    e = None if eps is None else _f32(eps)
+    g = np.empty(D, dtype=np.float32)
+    lib().tw_grad_openai(_p(shaped), C.c_int(shaped.size), C.c_int(D), C.c_uint32(seed), C.c_uint32(gen),
+                         C.c_int(group), C.c_int(n_head), _p(e), C.c_double(update_factor), _p(g))
+    return g
+
+
+def adam(theta, m, v, g, a, beta1=0.99, beta2=0.999, epsilon=1e-8):
+    """In-place on copies; returns (theta, m, v)."""
+    theta = _f32(theta).copy(); m = _f32(m).copy(); v = _f32(v).copy(); g = _f32(g)
+    lib().tw_adam(_p(theta), _p(m), _p(v), _p(g), C.c_int(theta.size), C.c_double(a), C.c_double(beta1),
+                  C.c_double(beta2), C.c_double(epsilon))
+    return theta, m, v
+
+
+def elite_mean(elites):
+    elites = _f32(elites)
+    k, D = elites.shape
+    mu = np.empty(D, dtype=np.float32)
+    lib().tw_elite_mean(_p(elites), C.c_int(k), C.c_int(D), _p(mu))
+    return mu

@@ -1,0 +1,118 @@
+"""Rank / top-k / centered ranks / gradient / Adam / elite mean of the bit-twin and of the
+flat-vector strategy ports against vectors produced by the reference's own strategy classes
+(tests/golden/strategy_*.npz, np.argsort pinned stable -- SURVEY.md quirk Q6)."""
+import numpy as np
+import pytest
+
+from oracle import pyref
+
+D = 226
+
+
+def test_rank_desc_matches_reference_order(twin, golden):
+    g = golden("strategy_openai_es")
+    for gen in range(3):
+        order = twin.rank_desc(g["rewards_%d" % gen])
+        assert np.array_equal(order, g["order_%d" % gen])                 # bit-exact indices
+    assert np.array_equal(twin.rank_desc(g["rewards_0"]), g["order_unpinned_0"])   # tie-free: any argsort agrees
+
+
+@pytest.mark.parametrize("name", ["strategy_simple_evolution", "strategy_simple_genetic"])
+def test_topk_matches_reference_elites(twin, golden, name):
+    g = golden(name)
+    k = int(g["cfg_elite_num"])
+    for gen in range(3):
+        assert np.array_equal(twin.rank_desc(g["rewards_%d" % gen])[:k], g["elite_ids_%d" % gen])
+
+
+def test_rank_tie_rule_large(twin):
+    rng = np.random.default_rng(0)
+    r = rng.integers(40, 2500, 100_000) / 5.0
+    want = np.flip(np.argsort(r, kind="stable"))
+    assert np.array_equal(twin.rank_desc(r), want)
+
+
+def test_centered_ranks_match_reference(twin, golden):
+    g = golden("strategy_openai_es")
+    for gen in range(3):
+        shaped = twin.centered_rank(g["order_%d" % gen].astype(np.int32))
+        np.testing.assert_allclose(shaped, g["shaped_%d" % gen], rtol=1e-12, atol=1e-15)
+
+
+def test_openai_gradient_and_adam_match_reference(twin, golden):
+    """Materialised-noise (verification) path: the twin consumes the reference's own epsilon
+    arrays.  From generation 1 on those hold mu+eps (quirk Q1) -> atol scaled by |mu|."""
+    g = golden("strategy_openai_es")
+    P = int(g["P"])
+    lr = float(g["cfg_learning_rate"])
+    theta = np.zeros(D, np.float32); m = np.zeros(D, np.float32); v = np.zeros(D, np.float32)
+    for gen in range(3):
+        sigma = float(g["sigma_before_%d" % gen])
+        uf = -(lr / (P * sigma))
+        assert uf == float(g["update_factor_%d" % gen])
+        mu = g["mu_before_%d" % gen]
+        np.testing.assert_array_equal(theta, mu) if gen == 0 else None
+        eps_ref = g["eps_%d" % gen]                       # = f32(mu + eps), eps_ref[0] = mu
+        shaped = g["shaped_%d" % gen]
+        grad_q1 = twin.grad_openai(shaped, D, 0, gen, P, 1, uf, eps=eps_ref)          # what the reference sums
+        np.testing.assert_allclose(grad_q1, g["grad_%d" % gen], rtol=1e-4, atol=1e-7)
+        eps_true = (eps_ref.astype(np.float64) - mu.astype(np.float64)).astype(np.float32)
+        grad = twin.grad_openai(shaped, D, 0, gen, P, 1, uf, eps=eps_true)            # what the engine sums
+        np.testing.assert_allclose(grad, g["grad_%d" % gen], rtol=1e-4, atol=1e-6 * max(1.0, np.abs(mu).max()))
+        a = lr * np.sqrt(1 - 0.999 ** (gen + 1)) / (1 - 0.99 ** (gen + 1))
+        theta, m, v = twin.adam(g["mu_before_%d" % gen], m, v, g["grad_%d" % gen], a)
+        assert np.array_equal(m, g["adam_m_%d" % gen]) and np.array_equal(v, g["adam_v_%d" % gen])
+        assert np.array_equal(theta, g["mu_after_%d" % gen])                          # bit-exact Adam
+        # end to end from the engine's gradient: rtol 1e-4 on the updated mu (north_star)
+        th2, _, _ = twin.adam(g["mu_before_%d" % gen], g["adam_m_%d" % (gen - 1)] if gen else np.zeros(D, np.float32),
+                              g["adam_v_%d" % (gen - 1)] if gen else np.zeros(D, np.float32), grad, a)
+        np.testing.assert_allclose(th2, g["mu_after_%d" % gen], rtol=1e-4, atol=1e-6)
+
+
+def test_elite_mean_bit_exact(twin, golden):
+    g = golden("strategy_simple_evolution")
+    for gen in range(3):
+        ids = g["elite_ids_%d" % gen]
+        mu = twin.elite_mean(g["pop_%d" % gen][ids])
+        assert np.array_equal(mu, g["mu_after_%d" % gen])
+        nxt = g["pop_%d" % (gen + 1)] if gen < 2 else g["pop_final"]
+        assert np.array_equal(nxt[0], mu) and np.array_equal(nxt[1], mu)              # quirk Q2
+
+
+def test_genetic_elite_carry_over(twin, golden):
+    g = golden("strategy_simple_genetic")
+    k, n = int(g["cfg_elite_num"]), int(g["cfg_offspring_num"])
+    grp = n // k
+    assert int(g["P"]) == k * grp
+    for gen in range(3):
+        ids = g["elite_ids_%d" % gen]
+        elites = g["pop_%d" % gen][ids]
+        assert np.array_equal(elites, g["elites_after_%d" % gen])
+        nxt = g["pop_%d" % (gen + 1)] if gen < 2 else g["pop_final"]
+        for e in range(k):
+            assert np.array_equal(nxt[e * grp], elites[e])                             # first of each group unperturbed
+
+
+@pytest.mark.parametrize("name", ["simple_evolution", "simple_genetic", "openai_es"])
+def test_strategy_port_replays_reference(golden, name):
+    """oracle/pyref.StrategyPort (what the CPU baseline runs on the GPU box) reproduces the
+    reference's populations bit for bit from the same numpy seed."""
+    g = golden("strategy_" + name)
+    seed = {"simple_evolution": 31, "simple_genetic": 32, "openai_es": 33}[name]
+    cfg = dict(name=name, init_sigma=float(g["cfg_init_sigma"]), sigma_decay=float(g["cfg_sigma_decay"]),
+               offspring_num=int(g["cfg_offspring_num"]))
+    if "cfg_elite_num" in g:
+        cfg["elite_num"] = int(g["cfg_elite_num"])
+    if "cfg_learning_rate" in g:
+        cfg["learning_rate"] = float(g["cfg_learning_rate"])
+    np.random.seed(seed)
+    s = pyref.StrategyPort(cfg, D)
+    pop = s.generate()
+    for gen in range(3):
+        assert np.array_equal(pop, g["pop_%d" % gen])
+        pop, best, sigma = s.evaluate(g["rewards_%d" % gen])
+        assert best == float(g["best_%d" % gen]) and sigma == float(g["sigma_after_%d" % gen])
+        if name == "openai_es":
+            np.testing.assert_allclose(s.mu, g["mu_after_%d" % gen], rtol=1e-6, atol=1e-7)
+    if name != "openai_es":
+        assert np.array_equal(pop, g["pop_final"])
