@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 population-rollout engine.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json metric: "env-steps/sec/GPU, CartPole-v1 pop=65536 ...; ES generations/sec"):
+CartPole-v1, 32-hidden MLP policy (D = 226), openai_es (centered ranks + Adam), population 65536
+sharded over N GPUs (strong scaling), eval_ep_num 5, max_step 500, seed 0, mu = 0 at generation 0
+(conf/cartpole_openai.yaml).  A "step" is one ES generation: K1 rollout of the rank's slice ->
+fitness all-gather (N > 1) -> K2 rank/shape -> K3 gradient + Adam.  `value` counts env steps that were
+actually simulated (sum of episode lengths), not P*E*500.
+
+Prints ONE JSON line on rank 0 (see DESIGN.md section 8 for every key).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+P_DEFAULT = 65536
+E_DEFAULT = 5
+D = 226
+FLOP_PER_STEP = 418          # 192 FMA + 34 bias adds per env step (CartPole MLP)
+STRATEGY = dict(name="openai_es", init_sigma=0.2, sigma_decay=0.9999, learning_rate=0.1)
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks (B200_PROFILING.md "clocks DURING the timed region")
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU legs (oracle; allowed importers of oracle/: tests, smoke, and these two functions)
+# ----------------------------------------------------------------------------------------------
+def cpu_reference_generation(n_offspring, cores, gen_seed, eval_ep_num=E_DEFAULT):
+    """One generation of the reference's CPU path (port: oracle/pyref.py -- torch-CPU policy per
+    offspring, Python CartPole, a fresh mp.Pool(cores), strategy.evaluate) on a gen-0 population
+    sample of n_offspring.  Returns (env_steps, seconds)."""
+    import numpy as np
+    import torch
+    from oracle import pyref
+    torch.set_num_threads(1)
+    np.random.seed(gen_seed)
+    init = np.random.RandomState(0).uniform(-0.05, 0.05, size=(eval_ep_num, 4))
+    env = pyref.CartPoleShim(max_step=500, init_states=init)
+    cfg = dict(STRATEGY, offspring_num=n_offspring)
+    t0 = time.perf_counter()
+    rec = pyref.es_loop_port(env, (4, 2, False), cfg, 1, cores, eval_ep_num, seed=gen_seed)
+    return rec[0]["env_steps"], time.perf_counter() - t0
+
+
+def cpu_baseline_block(cores):
+    """Bounded CPU baseline reported beside the GPU number (rank 0, N = 1)."""
+    n = max(64, min(4096, 48 * cores))
+    steps, dt = cpu_reference_generation(n, cores, 12345)
+    out = {"value": steps / dt, "unit": "env-steps/s", "cores": cores, "kind": "port",
+           "sample": "1 generation of the reference CPU path (oracle/pyref.py port: torch-CPU policy, Python CartPole, "
+                     "mp.Pool(%d), evaluate) on %d gen-0 offspring x %d episodes = %d env steps in %.1f s"
+                     % (cores, n, E_DEFAULT, steps, dt)}
+    try:  # a much stronger CPU number for context: the C bit-twin on every host thread
+        import numpy as np
+        from oracle import twin
+        n2 = 8192
+        t0 = time.perf_counter()
+        _, ts = twin.population_cartpole(np.zeros((1, D), np.float32), sigma=2.0, seed=0, gen=0, group=P_DEFAULT, n_head=1,
+                                         n=n2, E=E_DEFAULT, nthreads=cores)
+        dt2 = time.perf_counter() - t0
+        out["c_twin"] = {"value": float(ts.sum()) / dt2, "unit": "env-steps/s", "cores": cores,
+                         "sample": "%d gen-0 offspring (sigma 2) x %d episodes, oracle/ses_twin.c, %d pthreads" % (n2, E_DEFAULT, cores)}
+    except Exception as exc:  # pragma: no cover
+        out["c_twin"] = {"error": str(exc)}
+    return out
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path, timed on the host cores."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    n = max(64, min(2048, 24 * cores))
+    for w in range(args.warmup):
+        cpu_reference_generation(max(16, cores), cores, 100 + w)
+    tot_steps, tot_t = 0, 0.0
+    for k in range(args.steps):
+        s, dt = cpu_reference_generation(n, cores, 1000 + k)
+        tot_steps += s; tot_t += dt
+    v = tot_steps / tot_t
+    sample = ("each step = 1 generation of the reference CPU path (oracle/pyref.py port, mp.Pool(%d)) on %d gen-0 "
+              "offspring x %d episodes (bounded sample of the 65536 population)" % (cores, n, E_DEFAULT))
+    line = {
+        "impl": "reference", "metric": "env-steps/sec", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, args.steps),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 policy / f64 physics",
+        "data": "synthetic", "config": workload_config(args, 1),
+        "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, world):
+    return {"workload": "CartPole-v1 MLP(4-32-2, D=226) openai_es pop=%d eval_ep_num=%d max_step=500 "
+                        "(BASELINE configs[2]; conf/cartpole_openai.yaml)" % (args.pop, E_DEFAULT),
+            "population": args.pop, "eval_ep_num": E_DEFAULT, "strategy": STRATEGY, "parallelism": "pop-shard x%d" % world,
+            "init_states": "shared [E] table (reference mp.Pool semantics)",
+            "l2": "flushed between timed generations (256 MiB write); the hot path itself reads 904 B of parameters per generation"}
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from simple_es_b200 import dist as sdist
+    from simple_es_b200.loop import B200Loop
+
+    rank, world = sdist.init_from_env()
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    config = {"env": {"name": "CartPole-v1", "max_step": 500, "pomdp": False},
+              "network": {"name": "gym_model", "num_state": 4, "num_action": 2, "discrete_action": True, "gru": False},
+              "strategy": dict(STRATEGY, offspring_num=args.pop), "engine": {"name": "b200"}}
+    loop = B200Loop(config, args.steps + args.warmup, 1, E_DEFAULT, log=False, save_model_period=0, seed=0, device=local, quiet=True)
+    s = loop.strategy
+    eng = s.engine
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        s.step()
+    barrier()
+    steps_before = int(s.total_env_steps.item())
+    launches_before = eng.launches
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    wall0 = time.perf_counter()
+    rollout_steps = []
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)                      # L2 flush, outside the timed events
+        ev[k][0].record()
+        # one generation, with an extra event after K1 so that the dominant kernel is timed alone
+        e = s.engine
+        e.rollout(s.generation, s.sigma, s.parents, fitness=s.fitness, steps=s.steps)
+        ev[k][1].record()
+        sdist.exchange_fitness(s.fitness, s.lo, s.hi)
+        s.total_env_steps += s.steps[s.lo:s.hi].sum()
+        e.rank_desc(s.fitness, shaped=True, order=s.order, shaped_out=s.shaped)
+        s.t += 1
+        e.update_openai(s.generation, s.sigma, s.lr, s.t, s.shaped, s.parents.view(-1), s.m, s.v)
+        s.sigma *= s.decay; s.curr_sigma = s.sigma; s.generation += 1
+        ev[k][2].record()
+        rollout_steps.append(s.steps[s.lo:s.hi].sum())
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if rank == 0 else None
+    gen_ms = sum(ev[k][0].elapsed_time(ev[k][2]) for k in range(args.steps))
+    k1_ms = sum(ev[k][0].elapsed_time(ev[k][1]) for k in range(args.steps))
+    local_steps = int(s.total_env_steps.item()) - steps_before
+    k1_local_steps = int(sum(int(x.item()) for x in rollout_steps))
+    best = float(s.best_reward().item())
+    launches = eng.launches - launches_before
+    t = torch.tensor([gen_ms, k1_ms], dtype=torch.float64, device=dev)
+    n = torch.tensor([local_steps], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(n, op=dist.ReduceOp.SUM)
+    gen_ms, k1_ms = float(t[0]), float(t[1])
+    total_steps = int(n[0])
+
+    # ---------------- e2e: the same generations through the host-buffer C-ABI call (N = 1 path on each rank's own full copy)
+    e2e = None
+    if rank == 0:
+        import numpy as np
+        from simple_es_b200.engine import RolloutEngine
+        P = args.pop
+        eng2 = RolloutEngine("CartPole-v1", 4, 2, False, False, 500, E_DEFAULT, P, P, 1, 1, seed=0, device=local)
+        pin = lambda n_, dt: torch.empty(n_, dtype=dt).pin_memory().numpy()
+        mu, m, v = pin(D, torch.float32), pin(D, torch.float32), pin(D, torch.float32)
+        fit = pin(P, torch.float64)
+        mu[:] = 0; m[:] = 0; v[:] = 0
+        sigma = STRATEGY["init_sigma"]
+        for g in range(args.warmup):
+            eng2.generation_openai_host(g, sigma, STRATEGY["learning_rate"], g + 1, mu, m, v, fit)
+            sigma *= STRATEGY["sigma_decay"]
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        tot = 0
+        for g in range(args.warmup, args.warmup + args.steps):
+            tot += eng2.generation_openai_host(g, sigma, STRATEGY["learning_rate"], g + 1, mu, m, v, fit)
+            sigma *= STRATEGY["sigma_decay"]
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        e2e = {"value": tot / dt, "unit": "env-steps/s", "h2d_bytes_per_step": 3 * D * 4, "d2h_bytes_per_step": P * 8 + 3 * D * 4 + 8,
+               "api": "ses_generation_openai_host (C ABI, pinned host buffers, synchronous)", "n_gpus": 1, "env_steps": tot,
+               "generations_per_sec": args.steps / dt}
+        eng2.close()
+
+    if rank != 0:
+        return 0
+    peak_tf = measure_fp32_peak(local)
+    achieved_tf = k1_local_steps * FLOP_PER_STEP / (k1_ms * 1e-3) / 1e12 if k1_ms > 0 else 0.0
+    value = total_steps / (gen_ms * 1e-3)
+    line = {
+        "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": gen_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32 policy / f64 physics", "data": "synthetic",
+        "config": workload_config(args, world),
+        "per_gpu": value / world, "generations_per_sec": args.steps / (gen_ms * 1e-3), "env_steps": total_steps,
+        "best_reward_last_gen": best, "wall_s": wall,
+        "roofline": {"bound": "fp32_pipe", "kernel": "k_rollout_cartpole_mlp", "achieved": achieved_tf, "peak": peak_tf,
+                     "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
+                     "peak_source": "measured live: dependent-free FFMA microbenchmark on this GPU (MEASURED_PEAKS.json has only HBM and bf16-tensor peaks)",
+                     "algorithmic": "%d FP32 FLOP per env step (SURVEY 8d) x %d env steps of rank 0 / %.3f ms in K1" % (FLOP_PER_STEP, k1_local_steps, k1_ms),
+                     "k1_share_of_step": k1_ms / gen_ms if gen_ms else None},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+    }
+    if world == 1 and not args.no_cpu:
+        try:
+            line["cpu_baseline"] = cpu_baseline_block(os.cpu_count() or 1)
+        except Exception as exc:  # pragma: no cover
+            line["cpu_baseline"] = {"error": str(exc)}
+    print(json.dumps(line))
+    return 0
+
+
+def measure_fp32_peak(device):
+    """FFMA microbenchmark (library test hook) -> TFLOP/s; None if the hook is missing."""
+    try:
+        import ctypes as C
+        from simple_es_b200 import _lib
+        lib = _lib.load()
+        out = C.c_double(0.0)
+        _lib.check(lib.ses_measure_fp32_peak(int(device), C.byref(out)))
+        return out.value
+    except Exception:
+        return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pop", type=int, default=P_DEFAULT)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

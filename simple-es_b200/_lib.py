@@ -1,0 +1,80 @@
+"""ctypes binding of libses_b200.so (C ABI: include/ses_b200.h)."""
+import ctypes as C
+import os
+import subprocess
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+LIB_PATH = os.path.join(_PKG, "libses_b200.so")
+SOURCES = [os.path.join(_PKG, "csrc", f) for f in (
+    "ses_abi.cu", "ses_common.cuh", "rollout_cartpole_mlp.cuh", "rollout_cartpole_gru.cuh", "rollout_mpe.cuh",
+    "rank.cuh", "update.cuh")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-fmad=false",           # numerical contract: FMAs only where written
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+class ses_config(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "env", "obs_dim", "act_dim", "gru", "pomdp", "n_agents", "max_step", "eval_ep_num", "population", "group",
+        "n_head", "n_parents")] + [("seed", C.c_uint32)] + [(n, C.c_int32) for n in (
+            "init_mode", "id_begin", "id_end", "device")] + [("reserved", C.c_int32 * 7)]
+
+
+# every symbol include/ses_b200.h declares: name -> (restype, argtypes)
+_vp, _i32, _i64, _u32, _f32, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_float, C.c_double
+SYMBOLS = {
+    "ses_abi_version": (C.c_int, []),
+    "ses_last_error": (C.c_char_p, []),
+    "ses_param_count": (C.c_int, [_i32, _i32, _i32]),
+    "ses_create": (C.c_int, [C.POINTER(ses_config), C.POINTER(_vp)]),
+    "ses_destroy": (C.c_int, [_vp]),
+    "ses_rollout": (C.c_int, [_vp, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "ses_rank_desc": (C.c_int, [_vp, _vp, _i32, _i32, _f64, _vp, _vp, _vp]),
+    "ses_update_openai": (C.c_int, [_vp, _u32, _vp, _vp, _f64, _f64, _f64, _f64, _f64, _vp, _vp, _vp, _vp, _vp]),
+    "ses_materialize": (C.c_int, [_vp, _u32, _f32, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "ses_update_elite_mean": (C.c_int, [_vp, _u32, _f32, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "ses_generation_openai_host": (C.c_int, [_vp, _u32, _f32, _f64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ses_test_math": (C.c_int, [_i32, _vp, _vp, _i64, _vp]),
+    "ses_test_normals": (C.c_int, [_vp, _u32, _i32, _vp, _vp]),
+    "ses_measure_fp32_peak": (C.c_int, [_i32, C.POINTER(C.c_double)]),
+    "ses_launch_count": (_i64, [_vp]),
+}
+
+
+def build_library(force=False, verbose=False):
+    """Compile the CUDA library for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    if not force and os.path.exists(LIB_PATH) and all(
+            os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in SOURCES):
+        return LIB_PATH
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, SOURCES[0]]
+    subprocess.check_call(cmd, cwd=_ROOT)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load():
+    """Load libses_b200.so; no fallback -- a missing library is an error."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "simple-es_b200: %s is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). The engine has no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)          # AttributeError if the ABI is incomplete
+        fn.restype = res
+        fn.argtypes = args
+    if lib.ses_abi_version() != 1:
+        raise RuntimeError("simple-es_b200: ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError("simple-es_b200: " + load().ses_last_error().decode())

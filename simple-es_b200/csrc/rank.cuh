@@ -1,0 +1,152 @@
+// rank.cuh -- K2: descending rank of the fitness vector, centered-rank shaping.
+//
+// Replaces np.flip(np.argsort(np.array(rewards))) (offspring_strategies.py:112,234,380) and the
+// centered-rank loop + standardisation (offspring_strategies.py:392-398).
+//
+// Tie order is pinned: descending fitness, ties by DESCENDING index, which
+// equals np.flip(np.argsort(r, kind="stable")).  Implementation: the input is presented in
+// reverse index order with keys that ascend when fitness descends, then sorted with a STABLE
+// least-significant-digit radix sort (8-bit digits; 8 passes for a full float64 key, ceil(k/8)
+// when the caller bounds the key to k bits, e.g. CartPole's integer step totals).
+// HBM-trivial (<= 12 MB at P = 2^20); what matters is launch count and stability.
+#pragma once
+#include "ses_common.cuh"
+
+namespace ses {
+
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_ITEMS = 16;                            // chunks of 32 per warp
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;      // 4096 keys per CTA
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int SORT_WSEG = 32 * SORT_ITEMS;                // 512 consecutive keys per warp
+
+// position p holds offspring i = n-1-p; key ascends when fitness descends
+__global__ void k_sort_init(const double *__restrict__ fitness, int n, int key_bits, double key_scale,
+                            unsigned long long *__restrict__ keys, int *__restrict__ vals)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int i = n - 1 - p;
+    const double f = fitness[i];
+    unsigned long long k;
+    if (key_bits == 0) {
+        const unsigned long long b = (unsigned long long)__double_as_longlong(f);
+        const unsigned long long asc = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+        k = ~asc;
+    } else {
+        const unsigned long long v = (unsigned long long)__double2ll_rn(__dmul_rn(f, key_scale));
+        k = ((1ull << key_bits) - 1ull) - v;
+    }
+    keys[p] = k;
+    vals[p] = i;
+}
+
+// per-CTA digit histogram -> hist[cta][256]; digit totals -> tot[256] (zeroed by the host)
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(const unsigned long long *__restrict__ keys, int n, int shift,
+                                                            int *__restrict__ hist, int *__restrict__ tot)
+{
+    __shared__ int h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const int base = blockIdx.x * SORT_TILE;
+#pragma unroll 4
+    for (int it = 0; it < SORT_ITEMS; ++it) {
+        const int p = base + it * SORT_THREADS + threadIdx.x;
+        if (p < n) atomicAdd(&h[(int)((keys[p] >> shift) & 255ull)], 1);
+    }
+    __syncthreads();
+    const int c = h[threadIdx.x];
+    hist[blockIdx.x * 256 + threadIdx.x] = c;
+    if (c) atomicAdd(&tot[threadIdx.x], c);
+}
+
+// stable scatter of one tile: CTA c owns keys [c*4096, ...), warp w the 512 consecutive keys
+// [c*4096 + w*512, ...) in 16 chunks of 32 (so "earlier position" == lower (warp, chunk, lane)).
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const unsigned long long *__restrict__ keys_in,
+                                                               const int *__restrict__ vals_in, int n, int shift,
+                                                               const int *__restrict__ hist, const int *__restrict__ tot,
+                                                               unsigned long long *__restrict__ keys_out,
+                                                               int *__restrict__ vals_out)
+{
+    __shared__ int digit_base[256];
+    __shared__ int whist[SORT_WARPS][256];
+    __shared__ int scan_tmp[256];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lt = lanemask_lt();
+
+    // (a) global base of digit d for this CTA: sum_{d'<d} tot[d'] + sum_{c<cta} hist[c][d]
+    {
+        const int t = tot[tid];
+        scan_tmp[tid] = t;
+        __syncthreads();
+        for (int off = 1; off < 256; off <<= 1) {             // Hillis-Steele inclusive scan
+            int v = tid >= off ? scan_tmp[tid - off] : 0;
+            __syncthreads();
+            scan_tmp[tid] += v;
+            __syncthreads();
+        }
+        int b = scan_tmp[tid] - t;
+        for (int c = 0; c < (int)blockIdx.x; ++c) b += hist[c * 256 + tid];
+        digit_base[tid] = b;
+    }
+    for (int i = tid; i < SORT_WARPS * 256; i += SORT_THREADS) (&whist[0][0])[i] = 0;
+    __syncthreads();
+
+    // (b) load this warp's segment, count digits
+    unsigned long long key[SORT_ITEMS];
+    int val[SORT_ITEMS];
+    const int seg = blockIdx.x * SORT_TILE + w * SORT_WSEG;
+#pragma unroll
+    for (int it = 0; it < SORT_ITEMS; ++it) {
+        const int p = seg + it * 32 + lane;
+        const bool ok = p < n;
+        key[it] = ok ? keys_in[p] : 0ull;
+        val[it] = ok ? vals_in[p] : -1;
+        const int d = ok ? (int)((key[it] >> shift) & 255ull) : (256 + lane);
+        const unsigned peers = __match_any_sync(FULL, d);
+        if (ok && lane == __ffs(peers) - 1) whist[w][d] += __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    // (c) exclusive scan over warps per digit, seeded with the digit's global base
+    {
+        int run = digit_base[tid];
+#pragma unroll
+        for (int ww = 0; ww < SORT_WARPS; ++ww) {
+            const int t = whist[ww][tid];
+            whist[ww][tid] = run;
+            run += t;
+        }
+    }
+    __syncthreads();
+    // (d) second walk: stable positions
+#pragma unroll
+    for (int it = 0; it < SORT_ITEMS; ++it) {
+        const bool ok = val[it] >= 0;
+        const int d = ok ? (int)((key[it] >> shift) & 255ull) : (256 + lane);
+        const unsigned peers = __match_any_sync(FULL, d);
+        const int leader = __ffs(peers) - 1;
+        int b = 0;
+        if (ok && lane == leader) { b = whist[w][d]; whist[w][d] = b + __popc(peers); }
+        b = __shfl_sync(FULL, b, leader);
+        if (ok) {
+            const int pos = b + __popc(peers & lt);
+            keys_out[pos] = key[it];
+            vals_out[pos] = val[it];
+        }
+        __syncwarp();
+    }
+}
+
+// centered ranks, standardised with the closed-form mean (0) and population std of the table
+// {i/(P-1) - 0.5} (offspring_strategies.py:392-398).
+__global__ void k_shape_centered(const int *__restrict__ order, int n, double stdv, double *__restrict__ shaped)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const double v = __dsub_rn(__ddiv_rn((double)(n - 1 - r), (double)(n - 1)), 0.5);
+    shaped[order[r]] = __ddiv_rn(v, stdv);
+}
+
+}  // namespace ses

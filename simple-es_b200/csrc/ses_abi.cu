@@ -1,0 +1,487 @@
+// ses_abi.cu -- the C ABI of include/ses_b200.h over the sm_100a kernels in this directory.
+// Host side only does argument checking, scratch management and launches; there is no CPU
+// implementation of any entry point (no fallback): without a device every call fails.
+#include "../../include/ses_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "rank.cuh"
+#include "rollout_cartpole_mlp.cuh"
+#include "rollout_cartpole_gru.cuh"
+#include "rollout_mpe.cuh"
+#include "ses_common.cuh"
+#include "update.cuh"
+
+using namespace ses;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return -1;
+}
+
+#define CU(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e__ = (call);                                                                      \
+        if (e__ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char *ses_last_error(void) { return g_err; }
+extern "C" int ses_abi_version(void) { return SES_ABI_VERSION; }
+extern "C" int ses_param_count(int32_t obs, int32_t act, int32_t gru) { return param_count(obs, act, gru); }
+
+// ------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------
+struct ses_handle {
+    ses_config cfg;
+    int D, NQ, DP;
+    int state_dim;
+    int num_sms;
+    int eff_max_step;
+    // scratch (device)
+    int *work_counter = nullptr;
+    unsigned long long *keys[2] = {nullptr, nullptr};
+    int *vals_scratch = nullptr;
+    int *hist = nullptr;
+    int *tot = nullptr;            // [8][256]
+    double *part0 = nullptr, *part1 = nullptr;
+    int nb0 = 0, nb1 = 0, n_tiles = 0;
+    // scratch for the host-buffer generation path
+    float *h_parents = nullptr, *h_m = nullptr, *h_v = nullptr;
+    double *h_fitness = nullptr, *h_shaped = nullptr;
+    long long *h_steps = nullptr;
+    int *h_order = nullptr;
+    unsigned long long *h_total = nullptr;
+    // rollout launch configuration
+    int slots = 8;
+    int ctas_per_sm = 0;
+    int64_t launches = 0;
+};
+
+static cudaStream_t S(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+static int env_int(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+extern "C" int ses_create(const ses_config *cfg, ses_handle **out)
+{
+    if (!cfg || !out) return fail("ses_create: null argument");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail("ses_create: no CUDA device (%s); this engine has no CPU fallback", cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail("ses_create: device %d out of range (%d devices)", cfg->device, ndev);
+    if (cfg->env != SES_ENV_CARTPOLE && cfg->env != SES_ENV_SIMPLE_SPREAD) return fail("ses_create: unknown env %d", cfg->env);
+    if (cfg->env == SES_ENV_CARTPOLE && (cfg->obs_dim != 4 || cfg->act_dim != 2))
+        return fail("ses_create: CartPole-v1 needs num_state=4, num_action=2 (got %d, %d)", cfg->obs_dim, cfg->act_dim);
+    if (cfg->env == SES_ENV_SIMPLE_SPREAD) {
+        if (cfg->n_agents < 2 || cfg->n_agents > 3) return fail("ses_create: simple_spread supports N=2 or N=3 agents (got %d)", cfg->n_agents);
+        if (cfg->obs_dim != 6 * cfg->n_agents || cfg->act_dim != 5)
+            return fail("ses_create: simple_spread N=%d needs num_state=%d, num_action=5", cfg->n_agents, 6 * cfg->n_agents);
+        if (cfg->gru) return fail("ses_create: simple_spread GRU policy is not implemented in the GPU engine");
+    }
+    if (cfg->eval_ep_num < 1 || cfg->eval_ep_num > 32) return fail("ses_create: eval_ep_num must be in [1, 32] (got %d)", cfg->eval_ep_num);
+    if (cfg->population < 2) return fail("ses_create: population must be >= 2");
+    if (cfg->group < 1 || cfg->n_head < 0 || cfg->n_parents < 1) return fail("ses_create: bad population layout");
+    if (cfg->id_begin < 0 || cfg->id_end > cfg->population || cfg->id_begin > cfg->id_end) return fail("ses_create: bad slice [%d, %d)", cfg->id_begin, cfg->id_end);
+    if ((cfg->population - 1) / cfg->group >= cfg->n_parents) return fail("ses_create: layout needs %d parents, table has %d", (cfg->population - 1) / cfg->group + 1, cfg->n_parents);
+
+    CU(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major < 10) return fail("ses_create: device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
+
+    ses_handle *h = new ses_handle();
+    h->cfg = *cfg;
+    h->D = param_count(cfg->obs_dim, cfg->act_dim, cfg->gru);
+    h->NQ = (h->D + 3) / 4;
+    h->DP = h->NQ * 4;
+    h->state_dim = cfg->env == SES_ENV_CARTPOLE ? 4 : 4 * cfg->n_agents;
+    h->num_sms = prop.multiProcessorCount;
+    // gym registers CartPole-v1 with max_episode_steps=500 (TimeLimit); the wrapper's own max_step
+    // (gym_wrapper.py:37-39) can only shorten it.  simple_spread: max_cycles=25.
+    const int env_cap = cfg->env == SES_ENV_CARTPOLE ? 500 : 25;
+    h->eff_max_step = cfg->max_step > 0 ? (cfg->max_step < env_cap ? cfg->max_step : env_cap) : env_cap;
+    h->slots = env_int("SES_ROLLOUT_SLOTS", 8);
+    h->ctas_per_sm = env_int("SES_ROLLOUT_CTAS_PER_SM", 0);
+
+    const int P = cfg->population;
+    h->n_tiles = (P + SORT_TILE - 1) / SORT_TILE;
+    h->nb0 = (P + GB0 - 1) / GB0;
+    h->nb1 = (h->nb0 + GB1 - 1) / GB1;
+    CU(cudaMalloc(&h->work_counter, sizeof(int)));
+    CU(cudaMalloc(&h->keys[0], sizeof(unsigned long long) * P));
+    CU(cudaMalloc(&h->keys[1], sizeof(unsigned long long) * P));
+    CU(cudaMalloc(&h->vals_scratch, sizeof(int) * P));
+    CU(cudaMalloc(&h->hist, sizeof(int) * h->n_tiles * 256));
+    CU(cudaMalloc(&h->tot, sizeof(int) * 8 * 256));
+    CU(cudaMalloc(&h->part0, sizeof(double) * (size_t)h->nb0 * h->DP));
+    CU(cudaMalloc(&h->part1, sizeof(double) * (size_t)h->nb1 * h->DP));
+    *out = h;
+    return 0;
+}
+
+extern "C" int ses_destroy(ses_handle *h)
+{
+    if (!h) return 0;
+    cudaSetDevice(h->cfg.device);
+    cudaFree(h->work_counter);
+    cudaFree(h->keys[0]); cudaFree(h->keys[1]);
+    cudaFree(h->vals_scratch); cudaFree(h->hist); cudaFree(h->tot);
+    cudaFree(h->part0); cudaFree(h->part1);
+    cudaFree(h->h_parents); cudaFree(h->h_m); cudaFree(h->h_v);
+    cudaFree(h->h_fitness); cudaFree(h->h_shaped); cudaFree(h->h_steps); cudaFree(h->h_order); cudaFree(h->h_total);
+    delete h;
+    return 0;
+}
+
+extern "C" int64_t ses_launch_count(ses_handle *h) { return h ? h->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// K1
+// ------------------------------------------------------------------------------------------------
+template <typename Kernel>
+static int launch_persistent(ses_handle *h, Kernel kernel, int threads, size_t smem, int units_per_cta, int n_units,
+                             const RolloutParams &rp, cudaStream_t st)
+{
+    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    if (per_sm < 1) return fail("rollout kernel does not fit on an SM (smem %zu B)", smem);
+    if (h->ctas_per_sm > 0 && h->ctas_per_sm < per_sm) per_sm = h->ctas_per_sm;
+    int grid = per_sm * h->num_sms;
+    const int need = (n_units + units_per_cta - 1) / units_per_cta;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    kernel<<<grid, threads, smem, st>>>(rp);
+    CU(cudaGetLastError());
+    h->launches += 1;
+    return 0;
+}
+
+extern "C" int ses_rollout(ses_handle *h, uint32_t generation, float sigma, const float *parents_dev,
+                           const float *w_override_dev, const double *init_states_dev, double *fitness_dev,
+                           int64_t *steps_dev, double *trace_dev, int32_t *trace_actions_dev, int32_t n_trace,
+                           void *stream)
+{
+    if (!h) return fail("ses_rollout: null handle");
+    if (!fitness_dev || !steps_dev) return fail("ses_rollout: fitness_dev and steps_dev are required");
+    if (!parents_dev && !w_override_dev) return fail("ses_rollout: need parents_dev or w_override_dev");
+    if (n_trace > 0 && (!trace_dev || !trace_actions_dev)) return fail("ses_rollout: n_trace > 0 needs trace buffers");
+    const ses_config &c = h->cfg;
+    const int n_local = c.id_end - c.id_begin;
+    if (n_local == 0) return 0;
+    if (n_trace > n_local) n_trace = n_local;
+    CU(cudaSetDevice(c.device));
+    cudaStream_t st = S(stream);
+    CU(cudaMemsetAsync(h->work_counter, 0, sizeof(int), st));
+
+    RolloutParams rp;
+    rp.parents = parents_dev; rp.w_override = w_override_dev; rp.init_states = init_states_dev;
+    rp.fitness = fitness_dev; rp.steps = reinterpret_cast<long long *>(steps_dev);
+    rp.trace = trace_dev; rp.trace_actions = trace_actions_dev; rp.work_counter = h->work_counter;
+    rp.sigma = sigma; rp.seed = c.seed; rp.gen = generation;
+    rp.layout.group = c.group; rp.layout.n_head = c.n_head;
+    rp.id_begin = c.id_begin; rp.id_end = c.id_end;
+    rp.E = c.eval_ep_num; rp.max_step = h->eff_max_step; rp.pomdp = c.pomdp; rp.init_mode = c.init_mode;
+    rp.n_trace = n_trace; rp.slots_cap = 0; rp.n_agents = c.n_agents;
+
+    if (c.env == SES_ENV_CARTPOLE && !c.gru) {
+        constexpr int WARPS = 4;
+        auto go = [&](auto kern, int Sl) -> int {
+            const size_t smem = (size_t)WARPS * (Sl == 8 ? sizeof(CartpoleWarpSmem<8>) : sizeof(CartpoleWarpSmem<16>));
+            // spread small populations over more warps: cap the slots a warp may hold
+            int per_sm = 0;
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
+            if (h->ctas_per_sm > 0 && h->ctas_per_sm < per_sm) per_sm = h->ctas_per_sm;
+            const long long total_warps = (long long)per_sm * h->num_sms * WARPS;
+            int cap = (int)((n_local + total_warps - 1) / total_warps);
+            rp.slots_cap = cap < 1 ? 1 : (cap > Sl ? Sl : cap);
+            return launch_persistent(h, kern, WARPS * 32, smem, WARPS * rp.slots_cap, n_local, rp, st);
+        };
+        const bool tr = n_trace > 0;
+        if (h->slots == 16) return tr ? go(k_rollout_cartpole_mlp<16, WARPS, true>, 16) : go(k_rollout_cartpole_mlp<16, WARPS, false>, 16);
+        return tr ? go(k_rollout_cartpole_mlp<8, WARPS, true>, 8) : go(k_rollout_cartpole_mlp<8, WARPS, false>, 8);
+    }
+    if (c.env == SES_ENV_CARTPOLE && c.gru) return launch_rollout_cartpole_gru(h->num_sms, h->ctas_per_sm, rp, n_trace > 0, st, &h->launches, g_err, sizeof(g_err));
+    return launch_rollout_mpe(h->num_sms, h->ctas_per_sm, rp, n_trace > 0, st, &h->launches, g_err, sizeof(g_err));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2
+// ------------------------------------------------------------------------------------------------
+extern "C" int ses_rank_desc(ses_handle *h, const double *fitness_dev, int32_t n, int32_t key_bits, double key_scale,
+                             int32_t *order_dev, double *shaped_dev, void *stream)
+{
+    if (!h) return fail("ses_rank_desc: null handle");
+    if (!fitness_dev || !order_dev) return fail("ses_rank_desc: null buffer");
+    if (n < 1 || n > h->cfg.population) return fail("ses_rank_desc: n=%d outside (0, population=%d]", n, h->cfg.population);
+    if (key_bits < 0 || key_bits > 62) return fail("ses_rank_desc: key_bits must be in [0, 62]");
+    CU(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = S(stream);
+    const int passes = key_bits == 0 ? 8 : (key_bits + 7) / 8;
+    const int tiles = (n + SORT_TILE - 1) / SORT_TILE;
+    // ping-pong so that the last pass lands in order_dev
+    int *vals[2];
+    vals[0] = (passes % 2 == 0) ? order_dev : h->vals_scratch;
+    vals[1] = (passes % 2 == 0) ? h->vals_scratch : order_dev;
+    CU(cudaMemsetAsync(h->tot, 0, sizeof(int) * 8 * 256, st));
+    k_sort_init<<<(n + 255) / 256, 256, 0, st>>>(fitness_dev, n, key_bits, key_scale, h->keys[0], vals[0]);
+    h->launches += 1;
+    for (int ps = 0; ps < passes; ++ps) {
+        const int a = ps & 1, b = a ^ 1;
+        k_sort_hist<<<tiles, SORT_THREADS, 0, st>>>(h->keys[a], n, 8 * ps, h->hist, h->tot + 256 * ps);
+        k_sort_scatter<<<tiles, SORT_THREADS, 0, st>>>(h->keys[a], vals[a], n, 8 * ps, h->hist, h->tot + 256 * ps, h->keys[b], vals[b]);
+        h->launches += 2;
+    }
+    if (shaped_dev) {
+        if (n < 2) return fail("ses_rank_desc: centered ranks need n >= 2");
+        const double stdv = sqrt((double)(n + 1) / (12.0 * (double)(n - 1)));
+        k_shape_centered<<<(n + 255) / 256, 256, 0, st>>>(order_dev, n, stdv, shaped_dev);
+        h->launches += 1;
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3
+// ------------------------------------------------------------------------------------------------
+extern "C" int ses_update_openai(ses_handle *h, uint32_t generation, const double *shaped_dev,
+                                 const float *eps_override_dev, double update_factor, double adam_a, double beta1,
+                                 double beta2, double adam_eps, float *mu_dev, float *m_dev, float *v_dev,
+                                 float *grad_out_dev, void *stream)
+{
+    if (!h) return fail("ses_update_openai: null handle");
+    if (!shaped_dev || !mu_dev || !m_dev || !v_dev) return fail("ses_update_openai: null buffer");
+    CU(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = S(stream);
+    const int P = h->cfg.population;
+    Layout lay{h->cfg.group, h->cfg.n_head};
+    const int t0 = h->nb0 * h->NQ;
+    k_grad_level0<<<(t0 + 255) / 256, 256, 0, st>>>(shaped_dev, P, h->D, h->NQ, h->cfg.seed, generation, lay, eps_override_dev, h->part0, h->nb0);
+    const int t1 = h->nb1 * h->DP;
+    k_grad_level1<<<(t1 + 255) / 256, 256, 0, st>>>(h->part0, h->nb0, h->DP, h->part1, h->nb1);
+    k_grad_final_adam<<<(h->D + 255) / 256, 256, 0, st>>>(h->part1, h->nb1, h->DP, h->D, (float)update_factor, adam_a, (float)beta1,
+                                                         (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)adam_eps,
+                                                         mu_dev, m_dev, v_dev, grad_out_dev);
+    h->launches += 3;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ses_materialize(ses_handle *h, uint32_t generation, float sigma, const float *parents_dev,
+                               const float *w_override_dev, const int32_t *ids_dev, int32_t n, float *out_dev, void *stream)
+{
+    if (!h) return fail("ses_materialize: null handle");
+    if ((!parents_dev && !w_override_dev) || !ids_dev || !out_dev) return fail("ses_materialize: null buffer");
+    if (n < 1) return 0;
+    CU(cudaSetDevice(h->cfg.device));
+    Layout lay{h->cfg.group, h->cfg.n_head};
+    const int t = n * h->NQ;
+    k_materialize<<<(t + 255) / 256, 256, 0, S(stream)>>>(parents_dev, w_override_dev, h->cfg.id_begin, h->D, h->NQ, sigma, h->cfg.seed,
+                                                          generation, lay, ids_dev, n, out_dev);
+    h->launches += 1;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ses_update_elite_mean(ses_handle *h, uint32_t generation, float sigma, const float *parents_dev,
+                                     const float *w_override_dev, const int32_t *order_dev, int32_t k, float *mu_out_dev,
+                                     void *stream)
+{
+    if (!h) return fail("ses_update_elite_mean: null handle");
+    if ((!parents_dev && !w_override_dev) || !order_dev || !mu_out_dev) return fail("ses_update_elite_mean: null buffer");
+    if (k < 1 || k > h->cfg.population) return fail("ses_update_elite_mean: k=%d out of range", k);
+    CU(cudaSetDevice(h->cfg.device));
+    Layout lay{h->cfg.group, h->cfg.n_head};
+    k_elite_mean<<<(h->NQ + 63) / 64, 64, 0, S(stream)>>>(parents_dev, w_override_dev, h->cfg.id_begin, h->D, h->NQ, sigma, h->cfg.seed,
+                                                          generation, lay, order_dev, k, mu_out_dev);
+    h->launches += 1;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// whole openai_es generation with host buffers (bench.py e2e)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_sum_steps(const long long *__restrict__ steps, int n, unsigned long long *__restrict__ total)
+{
+    long long s = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += steps[i];
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(total, (unsigned long long)s);
+}
+
+extern "C" int ses_generation_openai_host(ses_handle *h, uint32_t generation, float sigma, double learning_rate,
+                                          int64_t adam_t, float *mu_host, float *m_host, float *v_host,
+                                          double *fitness_host, int64_t *total_steps_host, void *stream)
+{
+    if (!h) return fail("ses_generation_openai_host: null handle");
+    const ses_config &c = h->cfg;
+    const int P = c.population;
+    if (c.id_begin != 0 || c.id_end != P) return fail("ses_generation_openai_host: needs a single-slice handle");
+    if (c.n_parents != 1) return fail("ses_generation_openai_host: openai_es has one parent (mu)");
+    if (!mu_host || !m_host || !v_host || !fitness_host || !total_steps_host) return fail("ses_generation_openai_host: null buffer");
+    CU(cudaSetDevice(c.device));
+    cudaStream_t st = S(stream);
+    if (!h->h_parents) {
+        CU(cudaMalloc(&h->h_parents, sizeof(float) * h->D));
+        CU(cudaMalloc(&h->h_m, sizeof(float) * h->D));
+        CU(cudaMalloc(&h->h_v, sizeof(float) * h->D));
+        CU(cudaMalloc(&h->h_fitness, sizeof(double) * P));
+        CU(cudaMalloc(&h->h_shaped, sizeof(double) * P));
+        CU(cudaMalloc(&h->h_steps, sizeof(long long) * P));
+        CU(cudaMalloc(&h->h_order, sizeof(int) * P));
+        CU(cudaMalloc(&h->h_total, sizeof(unsigned long long)));
+    }
+    const size_t db = sizeof(float) * h->D;
+    CU(cudaMemcpyAsync(h->h_parents, mu_host, db, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(h->h_m, m_host, db, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(h->h_v, v_host, db, cudaMemcpyHostToDevice, st));
+    if (ses_rollout(h, generation, sigma, h->h_parents, nullptr, nullptr, h->h_fitness, reinterpret_cast<int64_t *>(h->h_steps), nullptr,
+                    nullptr, 0, stream))
+        return -1;
+    int key_bits = 0;
+    double key_scale = 1.0;
+    if (c.env == SES_ENV_CARTPOLE) {          // fitness = steps / E with integer steps <= E * max_step
+        const long long vmax = (long long)c.eval_ep_num * h->eff_max_step;
+        while ((1ll << key_bits) <= vmax) ++key_bits;
+        key_scale = (double)c.eval_ep_num;
+    }
+    if (ses_rank_desc(h, h->h_fitness, P, key_bits, key_scale, h->h_order, h->h_shaped, stream)) return -1;
+    const double beta1 = 0.99, beta2 = 0.999;  // optimizers.py:31
+    const double a = learning_rate * sqrt(1.0 - pow(beta2, (double)adam_t)) / (1.0 - pow(beta1, (double)adam_t));
+    const double uf = -(learning_rate / ((double)P * (double)sigma));
+    if (ses_update_openai(h, generation, h->h_shaped, nullptr, uf, a, beta1, beta2, 1e-8, h->h_parents, h->h_m, h->h_v, nullptr, stream))
+        return -1;
+    CU(cudaMemsetAsync(h->h_total, 0, sizeof(unsigned long long), st));
+    k_sum_steps<<<64, 256, 0, st>>>(h->h_steps, P, h->h_total);
+    h->launches += 1;
+    CU(cudaMemcpyAsync(fitness_host, h->h_fitness, sizeof(double) * P, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(mu_host, h->h_parents, db, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(m_host, h->h_m, db, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(v_host, h->h_v, db, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(total_steps_host, h->h_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// test hooks
+// ------------------------------------------------------------------------------------------------
+__global__ void k_test_math(int kind, const void *in, void *out, long long n)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (kind <= 4) {
+        const float x = static_cast<const float *>(in)[i];
+        float y = 0.0f, s, c;
+        switch (kind) {
+        case 0: y = tanh32(x); break;
+        case 1: y = sigm32(x); break;
+        case 2: y = ln32(x); break;
+        case 3: sincos2pi32(x, s, c); y = s; break;
+        default: sincos2pi32(x, s, c); y = c; break;
+        }
+        static_cast<float *>(out)[i] = y;
+    } else {
+        const double x = static_cast<const double *>(in)[i];
+        static_cast<double *>(out)[i] = kind == 5 ? sin64(x) : cos64(x);
+    }
+}
+
+extern "C" int ses_test_math(int32_t kind, const void *in_dev, void *out_dev, int64_t n, void *stream)
+{
+    if (kind < 0 || kind > 6) return fail("ses_test_math: unknown kind %d", kind);
+    if (n < 1) return 0;
+    k_test_math<<<(unsigned)((n + 255) / 256), 256, 0, S(stream)>>>(kind, in_dev, out_dev, (long long)n);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+__global__ void k_test_normals(uint32_t seed, uint32_t gen, uint32_t id, int D, float *out)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (4 * q >= D) return;
+    const float4 n = normal4(seed, (uint32_t)q, id, gen);
+    const int d = 4 * q;
+    out[d] = n.x;
+    if (d + 1 < D) out[d + 1] = n.y;
+    if (d + 2 < D) out[d + 2] = n.z;
+    if (d + 3 < D) out[d + 3] = n.w;
+}
+
+extern "C" int ses_test_normals(ses_handle *h, uint32_t generation, int32_t id, float *out_dev, void *stream)
+{
+    if (!h || !out_dev) return fail("ses_test_normals: null argument");
+    CU(cudaSetDevice(h->cfg.device));
+    k_test_normals<<<(h->NQ + 63) / 64, 64, 0, S(stream)>>>(h->cfg.seed, generation, (uint32_t)id, h->D, out_dev);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP32 pipe peak: dependent-free FFMA streams, the denominator of K1's roofline (bench.py)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_ffma_peak(float *out, int iters, float a, float b)
+{
+    float x0 = threadIdx.x, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+        }
+    }
+    const float s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 123.456f) out[0] = s;
+}
+
+extern "C" int ses_measure_fp32_peak(int32_t device, double *tflops_out)
+{
+    if (!tflops_out) return fail("ses_measure_fp32_peak: null argument");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    float *out = nullptr;
+    CU(cudaMalloc(&out, sizeof(float)));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    const int grid = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CU(cudaEventRecord(e0));
+        k_ffma_peak<<<grid, threads>>>(out, iters, 0.999f, 0.001f);
+        CU(cudaEventRecord(e1));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        const double fl = (double)grid * threads * (double)iters * 64.0 * 2.0;
+        const double tf = fl / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    *tflops_out = best;
+    return 0;
+}

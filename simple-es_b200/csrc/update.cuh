@@ -1,0 +1,150 @@
+// update.cuh -- K3: strategy updates that re-derive the noise instead of storing it.
+//
+//   openai_es : g = sum_j eps_j F_j, scale, Adam      (offspring_strategies.py:401-416, optimizers.py:13-57)
+//   evolution : mu = mean of the k best offspring      (offspring_strategies.py:241-250)
+//   genetic   : elite table = weights of the k best    (offspring_strategies.py:114-116)
+//
+// The reduction tree of the gradient is fixed so that every rank and the
+// CPU oracle produce the same bits: float64 accumulation,
+//   level 0: blocks of 32 consecutive offspring, sequential fma in offspring order
+//   level 1: groups of 64 consecutive block partials, sequential add
+//   level 2: sequential add over groups, one rounding to float32, scale, Adam.
+#pragma once
+#include "ses_common.cuh"
+
+namespace ses {
+
+constexpr int GB0 = 32;
+constexpr int GB1 = 64;
+
+// level 0: thread <-> (block b, quad q); grid covers nb0*NQ threads.  part0[b][4*NQ] float64.
+__global__ void __launch_bounds__(256) k_grad_level0(const double *__restrict__ shaped, int P, int D, int NQ, uint32_t seed,
+                                                     uint32_t gen, Layout layout, const float *__restrict__ eps_override,
+                                                     double *__restrict__ part0, int nb0)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nb0 * NQ) return;
+    const int b = t / NQ, q = t - b * NQ;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    const int j1 = min(P, (b + 1) * GB0);
+    for (int j = b * GB0; j < j1; ++j) {
+        float4 e;
+        if (eps_override) {
+            const float *row = eps_override + (size_t)j * D;
+            const int d = 4 * q;
+            e.x = d + 0 < D ? row[d + 0] : 0.0f;
+            e.y = d + 1 < D ? row[d + 1] : 0.0f;
+            e.z = d + 2 < D ? row[d + 2] : 0.0f;
+            e.w = d + 3 < D ? row[d + 3] : 0.0f;
+        } else {
+            if (!layout.perturbed(j)) continue;               // eps == 0 (offspring_strategies.py:302-308)
+            e = normal4(seed, (uint32_t)q, (uint32_t)j, gen);
+        }
+        const double f = shaped[j];
+        a0 = fma((double)e.x, f, a0);
+        a1 = fma((double)e.y, f, a1);
+        a2 = fma((double)e.z, f, a2);
+        a3 = fma((double)e.w, f, a3);
+    }
+    double *o = part0 + ((size_t)b * NQ + q) * 4;
+    o[0] = a0; o[1] = a1; o[2] = a2; o[3] = a3;
+}
+
+// level 1: thread <-> (group g, padded parameter d)
+__global__ void __launch_bounds__(256) k_grad_level1(const double *__restrict__ part0, int nb0, int DP, double *__restrict__ part1,
+                                                     int nb1)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nb1 * DP) return;
+    const int g = t / DP, d = t - g * DP;
+    double s = 0.0;
+    const int b1 = min(nb0, (g + 1) * GB1);
+    for (int b = g * GB1; b < b1; ++b) s = __dadd_rn(s, part0[(size_t)b * DP + d]);
+    part1[(size_t)g * DP + d] = s;
+}
+
+// level 2 + scale + Adam with the dtypes numpy>=2 gives the reference (m, v float32 with separately
+// rounded products, step float64, theta rounded once to float32).
+__global__ void __launch_bounds__(256) k_grad_final_adam(const double *__restrict__ part1, int nb1, int DP, int D, float update_factor,
+                                                         double a, float b1, float ob1, float b2, float ob2, float ep,
+                                                         float *__restrict__ mu, float *__restrict__ m, float *__restrict__ v,
+                                                         float *__restrict__ grad_out)
+{
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= D) return;
+    double s = 0.0;
+    for (int g = 0; g < nb1; ++g) s = __dadd_rn(s, part1[(size_t)g * DP + d]);
+    const float gr = __fmul_rn((float)s, update_factor);        // offspring_strategies.py:413-414
+    if (grad_out) grad_out[d] = gr;
+    const float mn = __fadd_rn(__fmul_rn(b1, m[d]), __fmul_rn(ob1, gr));                 // optimizers.py:48-49
+    const float vn = __fadd_rn(__fmul_rn(b2, v[d]), __fmul_rn(ob2, __fmul_rn(gr, gr)));  // optimizers.py:50-53
+    m[d] = mn;
+    v[d] = vn;
+    const double step = __ddiv_rn(__dmul_rn(-a, (double)mn), (double)__fadd_rn(__fsqrt_rn(vn), ep));  // :56
+    mu[d] = (float)__dadd_rn((double)mu[d], step);              // optimizers.py:22-24
+}
+
+// weights of selected offspring: out[j][D] = parent(ids[j]) + sigma * eps(gen, ids[j])
+__global__ void __launch_bounds__(256) k_materialize(const float *__restrict__ parents, const float *__restrict__ w_override,
+                                                     int id_begin, int D, int NQ, float sigma, uint32_t seed, uint32_t gen,
+                                                     Layout layout, const int *__restrict__ ids, int n, float *__restrict__ out)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * NQ) return;
+    const int j = t / NQ, q = t - j * NQ;
+    const int id = ids[j];
+    float4 w;
+    if (w_override) {
+        const float *row = w_override + (size_t)(id - id_begin) * D;
+        const int d = 4 * q;
+        w.x = d + 0 < D ? row[d + 0] : 0.0f;
+        w.y = d + 1 < D ? row[d + 1] : 0.0f;
+        w.z = d + 2 < D ? row[d + 2] : 0.0f;
+        w.w = d + 3 < D ? row[d + 3] : 0.0f;
+    } else {
+        w = offspring_quad(parents + (size_t)layout.parent(id) * D, D, q, layout.perturbed(id), sigma, seed, (uint32_t)id, gen);
+    }
+    float *o = out + (size_t)j * D + 4 * q;
+    const int d = 4 * q;
+    if (d + 0 < D) o[0] = w.x;
+    if (d + 1 < D) o[1] = w.y;
+    if (d + 2 < D) o[2] = w.z;
+    if (d + 3 < D) o[3] = w.w;
+}
+
+// simple_evolution: float32 running sum of the k best in rank order, then / k
+__global__ void __launch_bounds__(64) k_elite_mean(const float *__restrict__ parents, const float *__restrict__ w_override, int id_begin,
+                                                   int D, int NQ, float sigma, uint32_t seed, uint32_t gen, Layout layout,
+                                                   const int *__restrict__ order, int k, float *__restrict__ mu_out)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= NQ) return;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = 0; e < k; ++e) {
+        const int id = order[e];
+        float4 w;
+        if (w_override) {
+            const float *row = w_override + (size_t)(id - id_begin) * D;
+            const int d = 4 * q;
+            w.x = d + 0 < D ? row[d + 0] : 0.0f;
+            w.y = d + 1 < D ? row[d + 1] : 0.0f;
+            w.z = d + 2 < D ? row[d + 2] : 0.0f;
+            w.w = d + 3 < D ? row[d + 3] : 0.0f;
+        } else {
+            w = offspring_quad(parents + (size_t)layout.parent(id) * D, D, q, layout.perturbed(id), sigma, seed, (uint32_t)id, gen);
+        }
+        if (e == 0) acc = w;
+        else {
+            acc.x = __fadd_rn(acc.x, w.x); acc.y = __fadd_rn(acc.y, w.y);
+            acc.z = __fadd_rn(acc.z, w.z); acc.w = __fadd_rn(acc.w, w.w);
+        }
+    }
+    const float kf = (float)k;
+    const int d = 4 * q;
+    if (d + 0 < D) mu_out[d + 0] = __fdiv_rn(acc.x, kf);
+    if (d + 1 < D) mu_out[d + 1] = __fdiv_rn(acc.y, kf);
+    if (d + 2 < D) mu_out[d + 2] = __fdiv_rn(acc.z, kf);
+    if (d + 3 < D) mu_out[d + 3] = __fdiv_rn(acc.w, kf);
+}
+
+}  // namespace ses

@@ -1,0 +1,222 @@
+"""RolloutEngine: torch-tensor front end of the C ABI (include/ses_b200.h).
+
+torch is plumbing only: it owns device memory and the CUDA stream; every computation is one of the
+library's own sm_100a kernels.  Replaces, inside one generation of the reference loop
+(learning_strategies/evolution/loop.py:61-84):
+  * ``p.map(RolloutWorker, arguments)``           -> :meth:`RolloutEngine.rollout`
+  * ``np.flip(np.argsort(rewards))`` + shaping     -> :meth:`RolloutEngine.rank_desc`
+  * the strategy updates of ``evaluate``          -> :meth:`update_openai`, :meth:`elite_mean`,
+                                                     :meth:`materialize`
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+
+ENV_IDS = {"CartPole-v1": 0, "simple_spread": 1}
+CARTPOLE_TIME_LIMIT = 500       # gym registers CartPole-v1 with max_episode_steps=500
+SPREAD_MAX_CYCLES = 25          # simple_spread_v2 default max_cycles
+
+
+def population_layout(strategy, offspring_num, elite_num=None):
+    """(P, group, n_head, n_parents) of a strategy (offspring_strategies.py:48-61,165-176,299-328)."""
+    n = int(offspring_num)
+    if strategy == "simple_evolution":
+        return n + 1, n + 1, 2, 1            # [mu, elite0 (== mu), n-1 perturbed]
+    if strategy == "openai_es":
+        return n, n, 1, 1                    # [mu, n-1 perturbed]
+    if strategy == "simple_genetic":
+        k = int(elite_num)
+        g = n // k
+        if g < 1:
+            raise ValueError("simple_genetic needs offspring_num >= elite_num")
+        return k * g, g, 1, k                # per elite: [elite, g-1 perturbed]
+    raise ValueError("unknown strategy %r" % (strategy,))
+
+
+def shard_bounds(P, rank, world):
+    """Contiguous offspring-id range of `rank`; remainder to the low ranks."""
+    base, rem = divmod(P, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+class RolloutEngine:
+    """One engine instance == one ses_handle == one GPU's slice of the population."""
+
+    def __init__(self, env_name, obs_dim, act_dim, gru, pomdp, max_step, eval_ep_num, population, group, n_head,
+                 n_parents, seed=0, init_mode="shared", n_agents=2, id_begin=0, id_end=None, device=0):
+        if env_name not in ENV_IDS:
+            raise ValueError(
+                "env %r is not supported by the B200 engine (CartPole-v1 and simple_spread only; Box2D, PyBullet and "
+                "Unity environments stay on the reference CPU path)" % (env_name,))
+        if not torch.cuda.is_available():
+            raise RuntimeError("simple-es_b200: no CUDA device; the engine has no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", device)
+        self.P = int(population)
+        self.id_begin = int(id_begin)
+        self.id_end = self.P if id_end is None else int(id_end)
+        self.E = int(eval_ep_num)
+        self.env_name = env_name
+        self.n_agents = int(n_agents) if env_name == "simple_spread" else 1
+        ms = 0 if max_step in (None, "None") else int(max_step)
+        cap = CARTPOLE_TIME_LIMIT if env_name == "CartPole-v1" else SPREAD_MAX_CYCLES
+        self.max_step = min(ms, cap) if ms > 0 else cap
+        self.state_dim = 4 if env_name == "CartPole-v1" else 4 * self.n_agents
+        self.D = self.lib.ses_param_count(obs_dim, act_dim, int(bool(gru)))
+        self.cfg = _lib.ses_config(
+            env=ENV_IDS[env_name], obs_dim=obs_dim, act_dim=act_dim, gru=int(bool(gru)), pomdp=int(bool(pomdp)),
+            n_agents=self.n_agents, max_step=ms, eval_ep_num=self.E, population=self.P, group=int(group),
+            n_head=int(n_head), n_parents=int(n_parents), seed=int(seed) & 0xFFFFFFFF,
+            init_mode={"shared": 0, "fresh": 1}[init_mode], id_begin=self.id_begin, id_end=self.id_end, device=device)
+        h = C.c_void_p()
+        _lib.check(self.lib.ses_create(C.byref(self.cfg), C.byref(h)))
+        self._h = h
+        # integer-key fast path of K2: CartPole fitness*E is an integer < 2^key_bits
+        if env_name == "CartPole-v1":
+            self.key_bits = int(self.E * self.max_step).bit_length()
+            self.key_scale = float(self.E)
+        else:
+            self.key_bits, self.key_scale = 0, 1.0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.ses_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------ helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _chk(self, t, dtype, numel=None, name="tensor"):
+        if t is None:
+            return None
+        if not (t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+            raise ValueError("%s must be a contiguous CUDA tensor of dtype %s" % (name, dtype))
+        if numel is not None and t.numel() != numel:
+            raise ValueError("%s has %d elements, expected %d" % (name, t.numel(), numel))
+        return t
+
+    @property
+    def n_local(self):
+        return self.id_end - self.id_begin
+
+    @property
+    def launches(self):
+        return int(self.lib.ses_launch_count(self._h))
+
+    # ------------------------------------------------------------------------------ K1
+    def rollout(self, generation, sigma, parents, fitness=None, steps=None, w_override=None, init_states=None,
+                n_trace=0):
+        """Roll out this engine's slice.  Returns (fitness[P] f64, steps[P] i64[, trace, trace_actions]);
+        only [id_begin, id_end) is written."""
+        dev = self.device
+        parents = self._chk(parents, torch.float32, name="parents")
+        w_override = self._chk(w_override, torch.float32, self.n_local * self.D, "w_override")
+        init_states = self._chk(init_states, torch.float64, self.E * self.state_dim, "init_states")
+        if fitness is None:
+            fitness = torch.zeros(self.P, dtype=torch.float64, device=dev)
+        if steps is None:
+            steps = torch.zeros(self.P, dtype=torch.int64, device=dev)
+        self._chk(fitness, torch.float64, self.P, "fitness")
+        self._chk(steps, torch.int64, self.P, "steps")
+        trace = actions = None
+        if n_trace > 0:
+            n_trace = min(n_trace, self.n_local)
+            trace = torch.full((n_trace, 200, self.state_dim), float("nan"), dtype=torch.float64, device=dev)
+            actions = torch.full((n_trace, 200, self.n_agents), -1, dtype=torch.int32, device=dev)
+        _lib.check(self.lib.ses_rollout(self._h, int(generation), float(sigma), _ptr(parents), _ptr(w_override),
+                                        _ptr(init_states), _ptr(fitness), _ptr(steps), _ptr(trace), _ptr(actions),
+                                        int(n_trace), self._stream()))
+        if n_trace > 0:
+            return fitness, steps, trace, actions
+        return fitness, steps
+
+    # ------------------------------------------------------------------------------ K2
+    def rank_desc(self, fitness, shaped=False, order=None, shaped_out=None, full_key=False):
+        """order[r] = offspring with rank r (0 = best; ties by descending index); optional centered ranks."""
+        n = fitness.numel()
+        self._chk(fitness, torch.float64, name="fitness")
+        if order is None:
+            order = torch.empty(n, dtype=torch.int32, device=self.device)
+        if shaped and shaped_out is None:
+            shaped_out = torch.empty(n, dtype=torch.float64, device=self.device)
+        kb, ks = (0, 1.0) if full_key else (self.key_bits, self.key_scale)
+        _lib.check(self.lib.ses_rank_desc(self._h, _ptr(fitness), n, kb, ks, _ptr(order),
+                                          _ptr(shaped_out) if shaped else None, self._stream()))
+        return (order, shaped_out) if shaped else order
+
+    # ------------------------------------------------------------------------------ K3
+    @staticmethod
+    def adam_a(lr, t, beta1=0.99, beta2=0.999):
+        """optimizers.py:43-47 (float64)."""
+        return lr * math.sqrt(1 - beta2 ** t) / (1 - beta1 ** t)
+
+    def update_openai(self, generation, sigma, lr, t, shaped, mu, m, v, eps_override=None, grad_out=None,
+                      beta1=0.99, beta2=0.999, eps=1e-8):
+        """In-place openai_es step on (mu, m, v); `t` is Adam's step count AFTER the increment."""
+        for name, x in (("mu", mu), ("m", m), ("v", v)):
+            self._chk(x, torch.float32, self.D, name)
+        self._chk(shaped, torch.float64, self.P, "shaped")
+        eps_override = self._chk(eps_override, torch.float32, self.P * self.D, "eps_override")
+        uf = -1.0 * (lr / (self.P * sigma))              # offspring_strategies.py:406-408
+        _lib.check(self.lib.ses_update_openai(self._h, int(generation), _ptr(shaped), _ptr(eps_override), uf,
+                                              self.adam_a(lr, t, beta1, beta2), beta1, beta2, eps, _ptr(mu), _ptr(m),
+                                              _ptr(v), _ptr(grad_out), self._stream()))
+
+    def materialize(self, generation, sigma, parents, ids, w_override=None, out=None):
+        ids = self._chk(ids, torch.int32, name="ids")
+        n = ids.numel()
+        if out is None:
+            out = torch.empty((n, self.D), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.ses_materialize(self._h, int(generation), float(sigma), _ptr(parents), _ptr(w_override),
+                                            _ptr(ids), n, _ptr(out), self._stream()))
+        return out
+
+    def elite_mean(self, generation, sigma, parents, order, k, w_override=None, out=None):
+        if out is None:
+            out = torch.empty(self.D, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.ses_update_elite_mean(self._h, int(generation), float(sigma), _ptr(parents),
+                                                  _ptr(w_override), _ptr(order), int(k), _ptr(out), self._stream()))
+        return out
+
+    # ------------------------------------------------------------------------------ host-buffer generation
+    def generation_openai_host(self, generation, sigma, lr, t, mu, m, v, fitness):
+        """Whole openai_es generation on HOST numpy buffers (pinned recommended); updates mu/m/v/fitness in
+        place and returns the number of env steps simulated.  Synchronous."""
+        total = np.zeros(1, dtype=np.int64)
+        for a, dt in ((mu, np.float32), (m, np.float32), (v, np.float32), (fitness, np.float64)):
+            assert isinstance(a, np.ndarray) and a.dtype == dt and a.flags.c_contiguous
+        _lib.check(self.lib.ses_generation_openai_host(
+            self._h, int(generation), float(sigma), float(lr), int(t), C.c_void_p(mu.ctypes.data),
+            C.c_void_p(m.ctypes.data), C.c_void_p(v.ctypes.data), C.c_void_p(fitness.ctypes.data),
+            C.c_void_p(total.ctypes.data), self._stream()))
+        return int(total[0])
+
+    # ------------------------------------------------------------------------------ test hooks
+    def test_math(self, kind, x):
+        kinds = {"tanh": 0, "sigmoid": 1, "ln": 2, "sin2pi": 3, "cos2pi": 4, "sin64": 5, "cos64": 6}
+        out = torch.empty_like(x)
+        _lib.check(self.lib.ses_test_math(kinds[kind], _ptr(x), _ptr(out), x.numel(), self._stream()))
+        return out
+
+    def test_normals(self, generation, idx):
+        out = torch.empty(self.D, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.ses_test_normals(self._h, int(generation), int(idx), _ptr(out), self._stream()))
+        return out

@@ -1,0 +1,100 @@
+"""B200Loop: the generation loop of the reference (learning_strategies/evolution/loop.py:14-104)
+with the per-offspring multiprocessing fan-out replaced by the GPU engine.
+
+Observable behaviour kept from ESLoop: constructor signature (plus the split config), the per
+generation print line (loop.py:89-91), wandb keys (loop.py:94-99), and
+``logs/<env.name>/<%Y%m%d%H%M%S>/saved_models/ep_<n>.pt`` holding the elite's
+GymEnvModel-compatible state_dict every ``save_model_period`` generations (loop.py:40-47,101-104).
+"""
+import os
+import time
+from abc import ABCMeta, abstractmethod
+from collections import deque
+from datetime import datetime
+
+import torch
+
+from . import checkpoint
+from . import dist as sdist
+from .strategies import STRATEGIES
+
+
+class BaseESLoop(metaclass=ABCMeta):
+    """Same two-method contract as the reference's BaseESLoop (learning_strategies/evolution/abstracts.py:5-12)."""
+
+    @abstractmethod
+    def __init__(self):
+        pass
+
+    @abstractmethod
+    def run(self):
+        pass
+
+
+class B200Loop(BaseESLoop):
+    def __init__(self, config, generation_num, process_num, eval_ep_num, log=False, save_model_period=10,
+                 seed=0, device=None, save_dir=None, quiet=False):
+        super().__init__()
+        self.config = config
+        env_cfg, net_cfg, strat_cfg = config["env"], config["network"], config["strategy"]
+        self.engine_cfg = dict(config.get("engine") or {})
+        if net_cfg.get("name") != "gym_model":
+            raise ValueError("the B200 engine implements the reference's only network, gym_model (builder.py:17-24)")
+        if not net_cfg.get("discrete_action", True):
+            raise ValueError("continuous-action heads run only on Box2D/PyBullet envs, which stay on the reference CPU path")
+        if strat_cfg["name"] not in STRATEGIES:
+            raise ValueError("unknown strategy %r" % strat_cfg["name"])
+        self.rank, self.world = sdist.init_from_env()
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", 0))
+        torch.cuda.set_device(device)
+        self.process_num = process_num                    # accepted for CLI compatibility; the GPU replaces the pool
+        self.generation_num = generation_num
+        self.eval_ep_num = eval_ep_num
+        self.log = log
+        self.save_model_period = save_model_period
+        self.quiet = quiet
+        self.ep5_rewards = deque(maxlen=5)
+        self.env_name = env_cfg["name"]
+        self.net_cfg = net_cfg
+        self.strategy = STRATEGIES[strat_cfg["name"]](strat_cfg, env_cfg, net_cfg, eval_ep_num, seed, device, self.engine_cfg)
+        self.history = []
+
+        self.save_dir = save_dir
+        if self.rank == 0 and self.save_model_period and self.save_model_period > 0:
+            if self.save_dir is None:
+                self.save_dir = f"logs/{self.env_name}/{datetime.now().strftime('%Y%m%d%H%M%S')}"
+            os.makedirs(self.save_dir + "/saved_models/", exist_ok=True)
+        self._wandb = None
+        if self.log and self.rank == 0:
+            import wandb
+            wandb.init(project=self.env_name, config=config)
+            self._wandb = wandb
+
+    def elite_state_dict(self):
+        n = self.net_cfg
+        return checkpoint.flat_to_state_dict(self.strategy.elite_flat(), int(n["num_state"]), int(n["num_action"]), bool(n["gru"]))
+
+    def run(self):
+        s = self.strategy
+        ep_num = 0
+        for _ in range(self.generation_num):
+            start = time.time()
+            ep_num += 1
+            s.step()
+            best_reward = float(s.best_reward().item())      # the one device->host sync of a generation
+            consumed = time.time() - start
+            curr_sigma = s.curr_sigma
+            self.history.append((ep_num, best_reward, curr_sigma, consumed))
+            if self.rank == 0 and not self.quiet:
+                # rollout and evaluate are one stream-ordered GPU pass; their split is not observable from
+                # the host without extra syncs, so both reference fields report the generation time.
+                print(f"episode: {ep_num}, Best reward: {best_reward:.2f}, sigma: {curr_sigma:.3f}, "
+                      f"time: {consumed:.2f}, rollout_t: {consumed:.2f}, eval_t: {0.0:.2f}")
+            if self._wandb is not None:
+                self.ep5_rewards.append(best_reward)
+                self._wandb.log({"ep5_mean_reward": sum(self.ep5_rewards) / len(self.ep5_rewards),
+                                 "curr_sigma": curr_sigma})
+            if self.rank == 0 and self.save_model_period and self.save_model_period > 0 and ep_num % self.save_model_period == 0:
+                torch.save(self.elite_state_dict(), self.save_dir + "/saved_models" + f"/ep_{ep_num}.pt")
+        return self.history

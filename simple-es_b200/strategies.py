@@ -1,0 +1,126 @@
+"""Device-resident strategy state for the three offspring strategies.
+
+Each class keeps what the reference strategy keeps (learning_strategies/evolution/offspring_strategies.py)
+-- mu / elite table, sigma, Adam moments -- as a few small CUDA tensors, and never materialises the
+population: offspring i of generation g is (parent(i), sigma, Philox(seed, g, i)).  `step()` is one
+generation: K1 rollout of this rank's slice, fitness exchange, K2 rank, K3 update -- the GPU form of
+``results = p.map(RolloutWorker, ...); strategy.evaluate(results)`` (loop.py:66-84).
+"""
+import torch
+
+from . import dist as sdist
+from .engine import RolloutEngine, population_layout, shard_bounds
+
+
+class _Base:
+    name = None
+
+    def __init__(self, strategy_cfg, env_cfg, network_cfg, eval_ep_num, seed, device, engine_cfg):
+        rank, ws = sdist.world()
+        self.cfg = strategy_cfg
+        self.sigma = float(strategy_cfg["init_sigma"])           # sigma the CURRENT population was drawn with
+        self.curr_sigma = self.sigma                              # what the reference reports (post-decay)
+        self.decay = float(strategy_cfg["sigma_decay"])
+        self.n = int(strategy_cfg["offspring_num"])
+        self.k = int(strategy_cfg.get("elite_num", 1))
+        self.P, group, n_head, n_par = population_layout(self.name, self.n, self.k)
+        self.lo, self.hi = shard_bounds(self.P, rank, ws)
+        name = env_cfg["name"]
+        self.engine = RolloutEngine(
+            name, int(network_cfg["num_state"]), int(network_cfg["num_action"]), bool(network_cfg["gru"]),
+            bool(env_cfg.get("pomdp", False)), env_cfg.get("max_step"), eval_ep_num, self.P, group, n_head, n_par,
+            seed=seed, init_mode=engine_cfg.get("init_states", "shared"), n_agents=int(engine_cfg.get("n_agents", 2)),
+            id_begin=self.lo, id_end=self.hi, device=device)
+        self.D = self.engine.D
+        dev = self.engine.device
+        self.parents = torch.zeros(n_par, self.D, dtype=torch.float32, device=dev)   # network.zero_init() (loop.py:31)
+        self.fitness = torch.zeros(self.P, dtype=torch.float64, device=dev)
+        self.steps = torch.zeros(self.P, dtype=torch.int64, device=dev)
+        self.order = torch.empty(self.P, dtype=torch.int32, device=dev)
+        self.generation = 0
+        self.total_env_steps = torch.zeros((), dtype=torch.int64, device=dev)
+
+    def _rollout_and_rank(self, shaped=False):
+        e = self.engine
+        e.rollout(self.generation, self.sigma, self.parents, fitness=self.fitness, steps=self.steps)
+        sdist.exchange_fitness(self.fitness, self.lo, self.hi)
+        self.total_env_steps += self.steps[self.lo:self.hi].sum()
+        return e.rank_desc(self.fitness, shaped=shaped, order=self.order)
+
+    def best_reward(self):
+        """max(rewards) (offspring_strategies.py:113,235,381) -- a 0-d device tensor."""
+        return self.fitness[self.order[0].long()]
+
+    def elite_flat(self):
+        raise NotImplementedError
+
+    def step(self):
+        raise NotImplementedError
+
+
+class OpenAIES(_Base):
+    """offspring_strategies.py:270-434 + optimizers.py:30-57."""
+    name = "openai_es"
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.lr = float(self.cfg["learning_rate"])
+        dev = self.engine.device
+        self.m = torch.zeros(self.D, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(self.D, dtype=torch.float32, device=dev)
+        self.t = 0
+        self.shaped = torch.empty(self.P, dtype=torch.float64, device=dev)
+
+    def step(self):
+        e = self.engine
+        e.rollout(self.generation, self.sigma, self.parents, fitness=self.fitness, steps=self.steps)
+        sdist.exchange_fitness(self.fitness, self.lo, self.hi)
+        self.total_env_steps += self.steps[self.lo:self.hi].sum()
+        e.rank_desc(self.fitness, shaped=True, order=self.order, shaped_out=self.shaped)
+        self.t += 1
+        e.update_openai(self.generation, self.sigma, self.lr, self.t, self.shaped, self.parents.view(-1), self.m, self.v)
+        self.sigma *= self.decay                                  # :418, after update_factor used the old sigma
+        self.curr_sigma = self.sigma
+        self.generation += 1
+
+    def elite_flat(self):
+        return self.parents[0]                                    # get_elite_model() is mu_model (:330-331)
+
+
+class SimpleEvolution(_Base):
+    """offspring_strategies.py:137-267 (quirk Q2: the stored elite is the mean)."""
+    name = "simple_evolution"
+
+    def step(self):
+        e = self.engine
+        self._rollout_and_rank()
+        new_mu = e.elite_mean(self.generation, self.sigma, self.parents, self.order, self.k)
+        self.parents[0].copy_(new_mu)
+        self.sigma *= self.decay                                  # :251, BEFORE regenerating
+        self.curr_sigma = self.sigma
+        self.generation += 1
+
+    def elite_flat(self):
+        return self.parents[0]                                    # elite_models[0] was overwritten by the mean (Q2)
+
+
+class SimpleGenetic(_Base):
+    """offspring_strategies.py:11-134."""
+    name = "simple_genetic"
+
+    def step(self):
+        e = self.engine
+        self._rollout_and_rank()
+        elites = e.materialize(self.generation, self.sigma, self.parents, self.order[:self.k].contiguous())
+        self.parents.copy_(elites)
+        # the next population is regenerated with the CURRENT sigma, then sigma decays (:117-124):
+        # population g+1 was drawn with the sigma reported after generation g-1.
+        self.sigma = self.curr_sigma
+        self.curr_sigma = self.curr_sigma * self.decay
+        self.generation += 1
+
+    def elite_flat(self):
+        return self.parents[0]                                    # elite_models[0] (:64-65)
+
+
+STRATEGIES = {c.name: c for c in (OpenAIES, SimpleEvolution, SimpleGenetic)}

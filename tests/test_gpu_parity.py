@@ -1,0 +1,284 @@
+"""GPU parity: the sm_100a kernels, called through the C ABI (simple_es_b200.engine -> ctypes ->
+libses_b200.so), against the CPU bit-twin oracle on the same seeded inputs and against the
+reference-generated golden fixtures.  Integer / index results and everything under the numerical
+contract must be bit-exact; comparisons with the reference's torch/numpy path carry the
+tolerances the north_star states (written next to each assert)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+D = 226
+
+
+def _engine(**kw):
+    from simple_es_b200.engine import RolloutEngine
+    args = dict(env_name="CartPole-v1", obs_dim=4, act_dim=2, gru=False, pomdp=False, max_step=500, eval_ep_num=5,
+                population=1024, group=1024, n_head=1, n_parents=1, seed=0, init_mode="shared")
+    args.update(kw)
+    return RolloutEngine(**args)
+
+
+def _cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# ------------------------------------------------------------------------------------- contract
+def test_math_contract_bit_exact(twin):
+    eng = _engine()
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-10, 10, 1_000_000), rng.normal(0, 1, 1_000_000), [0.0, -0.0, 50, -50]]).astype(np.float32)
+    assert np.array_equal(eng.test_math("tanh", _cuda(x)).cpu().numpy(), twin.tanhf(x))
+    assert np.array_equal(eng.test_math("sigmoid", _cuda(x)).cpu().numpy(), twin.sigmf(x))
+    u = ((rng.integers(0, 2 ** 24, 1_000_000) + 0.5) * 2.0 ** -24).astype(np.float32)
+    assert np.array_equal(eng.test_math("ln", _cuda(u)).cpu().numpy(), twin.lnf(u))
+    v = (rng.integers(0, 2 ** 24, 1_000_000) * 2.0 ** -24).astype(np.float32)
+    s, c = twin.sincos2pif(v)
+    assert np.array_equal(eng.test_math("sin2pi", _cuda(v)).cpu().numpy(), s)
+    assert np.array_equal(eng.test_math("cos2pi", _cuda(v)).cpu().numpy(), c)
+    th = rng.uniform(-0.5, 0.5, 1_000_000)
+    s, c = twin.sincos(th)
+    assert np.array_equal(eng.test_math("sin64", _cuda(th)).cpu().numpy(), s)
+    assert np.array_equal(eng.test_math("cos64", _cuda(th)).cpu().numpy(), c)
+
+
+def test_philox_normals_bit_exact(twin):
+    eng = _engine(seed=1234)
+    for gen, idx in [(0, 0), (0, 1), (3, 77), (1000, 65535), (2 ** 31, 2 ** 20 - 1)]:
+        got = eng.test_normals(gen, idx).cpu().numpy()
+        assert np.array_equal(got, twin.normals(1234, gen, idx, D))
+
+
+@pytest.mark.parametrize("strategy,n,k", [("simple_evolution", 96, 10), ("openai_es", 128, None), ("simple_genetic", 100, 8)])
+def test_materialize_layouts_bit_exact(twin, strategy, n, k):
+    from simple_es_b200.engine import population_layout
+    P, group, n_head, n_par = population_layout(strategy, n, k)
+    eng = _engine(population=P, group=group, n_head=n_head, n_parents=n_par, seed=5)
+    rng = np.random.default_rng(1)
+    parents = rng.normal(0, 1, (n_par, D)).astype(np.float32)
+    ids = np.arange(P, dtype=np.int32)
+    got = eng.materialize(7, 0.37, _cuda(parents), _cuda(ids)).cpu().numpy()
+    want = twin.materialize(parents, 0.37, 5, 7, group, n_head, ids)
+    assert np.array_equal(got, want)
+    heads = [i for i in range(P) if i % group < n_head]
+    assert all(np.array_equal(got[i], parents[i // group]) for i in heads)
+
+
+# ------------------------------------------------------------------------------------- K1
+@pytest.mark.parametrize("init_mode,pomdp,E", [("shared", False, 5), ("fresh", False, 3), ("shared", True, 5), ("shared", False, 1)])
+def test_rollout_philox_bit_exact(twin, init_mode, pomdp, E):
+    P = 3000
+    eng = _engine(population=P, group=P, n_head=1, eval_ep_num=E, pomdp=pomdp, init_mode=init_mode, seed=11)
+    mu = np.zeros((1, D), np.float32)
+    fit, steps = eng.rollout(2, 2.0, _cuda(mu))
+    tf, ts = twin.population_cartpole(mu, pomdp=pomdp, sigma=2.0, seed=11, gen=2, group=P, n_head=1, n=P, E=E,
+                                      init_mode=0 if init_mode == "shared" else 1, nthreads=8)
+    assert np.array_equal(steps.cpu().numpy(), ts)          # integer returns: bit-exact
+    assert np.array_equal(fit.cpu().numpy(), tf)
+    assert ts.max() > 3 * ts.min()                          # the case really has ragged episode lengths
+
+
+def test_rollout_trained_parent_long_episodes(twin):
+    """A parent that balances the pole (bang-bang on theta + theta_dot) with small sigma: most
+    episodes hit the 500-step limit, exercising long trajectories and the truncation rule."""
+    P, E = 1024, 5
+    mu = np.zeros((1, D), np.float32)
+    w1 = mu[0, :128].reshape(32, 4); w2 = mu[0, 160:224].reshape(2, 32)
+    w1[0] = [0.0, 0.5, 10.0, 3.0]                           # h0 = tanh(.5 xdot + 10 theta + 3 thetadot)
+    w2[1, 0] = 5.0; w2[0, 0] = -5.0
+    eng = _engine(population=P, group=P, n_head=1, eval_ep_num=E, seed=3)
+    fit, steps = eng.rollout(0, 0.05, _cuda(mu))
+    tf, ts = twin.population_cartpole(mu, sigma=0.05, seed=3, gen=0, group=P, n_head=1, n=P, E=E, nthreads=8)
+    assert np.array_equal(steps.cpu().numpy(), ts)
+    assert (ts == 500 * E).mean() > 0.5
+
+
+def test_rollout_verification_mode_matches_reference(twin, golden):
+    """The engine consumes the reference's own weight arrays and initial states (north_star
+    verification mode).  Golden = reference RolloutWorker + GymEnvModel (torch CPU)."""
+    g = golden("rollout_cartpole_mlp")
+    W, init = g["W"], g["init"]
+    tid = [int(i) for i in g["trace_ids"]]
+    perm = np.array(tid + [i for i in range(W.shape[0]) if i not in tid])
+    P = W.shape[0]
+    eng = _engine(population=P, group=P, n_head=1, eval_ep_num=int(g["E"]))
+    fit, steps, trace, actions = eng.rollout(0, 0.0, None, w_override=_cuda(W[perm]), init_states=_cuda(init), n_trace=len(tid))
+    fit = fit.cpu().numpy()
+    # returns: exact for >= 99.9 % of offspring (near-tie action flips vs torch are allowed for the rest)
+    assert (fit == g["fitness"][perm]).mean() >= 0.999
+    np.testing.assert_allclose(fit, g["fitness"][perm], rtol=1e-4) if (fit == g["fitness"][perm]).all() else None
+    trace = trace.cpu().numpy(); actions = actions.cpu().numpy()[:, :, 0]
+    for j in range(len(tid)):
+        ref = g["traces"][j]
+        n = int(np.isfinite(ref[:, 0]).sum())
+        assert np.array_equal(actions[j, :n], g["trace_actions"][j, :n])
+        assert np.abs(trace[j, :n] - ref[:n]).max() <= 1e-9      # north_star: 1e-9 over the first 200 steps
+        # against the bit-twin the trace is exact
+        _, ttr, tac = twin.rollout_cartpole(W[perm][j], E=int(g["E"]), init=init, trace_steps=200)
+        m = int(np.isfinite(ttr[:, 0]).sum())
+        assert np.array_equal(trace[j, :m], ttr[:m]) and np.array_equal(actions[j, :m], tac[:m])
+
+
+def test_rollout_edge_cases(twin):
+    mu = np.zeros((1, D), np.float32)
+    # max_step = 1: every episode is truncated after one step
+    eng = _engine(population=64, group=64, max_step=1, eval_ep_num=4)
+    fit, steps = eng.rollout(0, 1.0, _cuda(mu))
+    assert np.all(steps.cpu().numpy() == 4) and np.all(fit.cpu().numpy() == 1.0)
+    # the smallest population, the largest E
+    eng = _engine(population=2, group=2, eval_ep_num=32, seed=9)
+    fit, steps = eng.rollout(5, 2.0, _cuda(mu))
+    tf, ts = twin.population_cartpole(mu, sigma=2.0, seed=9, gen=5, group=2, n_head=1, n=2, E=32)
+    assert np.array_equal(steps.cpu().numpy(), ts)
+    # empty slice: nothing written
+    eng = _engine(population=64, group=64, id_begin=10, id_end=10)
+    fit, steps = eng.rollout(0, 1.0, _cuda(mu))
+    assert np.all(steps.cpu().numpy() == 0)
+    # ragged slice writes only its own range
+    eng = _engine(population=64, group=64, id_begin=5, id_end=38, seed=2)
+    fit, steps = eng.rollout(1, 2.0, _cuda(mu))
+    tf, ts = twin.population_cartpole(mu, sigma=2.0, seed=2, gen=1, group=64, n_head=1, id0=5, n=33)
+    s = steps.cpu().numpy()
+    assert np.array_equal(s[5:38], ts) and np.all(s[:5] == 0) and np.all(s[38:] == 0)
+
+
+def test_rollout_full_size_properties():
+    """BASELINE config 3 size (P = 65536): size-independent properties."""
+    P, E = 65536, 5
+    mu = _cuda(np.zeros((1, D), np.float32))
+    eng = _engine(population=P, group=P, n_head=1, eval_ep_num=E, seed=0)
+    fit, steps = eng.rollout(0, 2.0, mu)
+    fit2, steps2 = eng.rollout(0, 2.0, mu)
+    assert torch.equal(steps, steps2) and torch.equal(fit, fit2)                 # deterministic, schedule independent
+    s = steps.cpu().numpy(); f = fit.cpu().numpy()
+    assert s.min() >= E * 8 and s.max() <= E * 500 and np.array_equal(f, s / E)
+    # sharding: two half-population handles reproduce the unsharded result (no data-path collective)
+    a = _engine(population=P, group=P, n_head=1, eval_ep_num=E, seed=0, id_begin=0, id_end=P // 2 + 3)
+    b = _engine(population=P, group=P, n_head=1, eval_ep_num=E, seed=0, id_begin=P // 2 + 3, id_end=P)
+    fa, sa = a.rollout(0, 2.0, mu)
+    fb, sb = b.rollout(0, 2.0, mu, fitness=fa, steps=sa)
+    assert torch.equal(sb, steps)
+    # offspring 0 is the unperturbed all-zero parent -> action 0 forever
+    assert 8 * E <= s[0] <= 12 * E
+    # a different generation gives different noise
+    _, steps3 = eng.rollout(1, 2.0, mu)
+    assert not torch.equal(steps3, steps)
+
+
+# ------------------------------------------------------------------------------------- K2
+@pytest.mark.parametrize("n", [2, 97, 4097, 65536, 1 << 20])
+def test_rank_desc_bit_exact(n):
+    eng = _engine(population=max(n, 2), group=max(n, 2))
+    rng = np.random.default_rng(n)
+    for kind in ("float", "ties", "cartpole"):
+        if kind == "float":
+            r = rng.normal(0, 100, n)
+        elif kind == "ties":
+            r = np.round(rng.normal(0, 3, n))                      # negative values and many ties
+        else:
+            r = rng.integers(40, 2501, n) / 5.0
+        want = np.flip(np.argsort(r, kind="stable")).astype(np.int32)
+        got = eng.rank_desc(_cuda(r), full_key=True).cpu().numpy()
+        assert np.array_equal(got, want), kind
+        if kind == "cartpole":                                     # integer-key fast path
+            got = eng.rank_desc(_cuda(r)).cpu().numpy()
+            assert np.array_equal(got, want)
+
+
+def test_rank_and_shaping_match_reference(twin, golden):
+    g = golden("strategy_openai_es")
+    P = int(g["P"])
+    eng = _engine(population=P, group=P)
+    for gen in range(3):
+        order, shaped = eng.rank_desc(_cuda(g["rewards_%d" % gen]), shaped=True, full_key=True)
+        assert np.array_equal(order.cpu().numpy(), g["order_%d" % gen])            # bit-exact indices
+        assert np.array_equal(shaped.cpu().numpy(), twin.centered_rank(g["order_%d" % gen].astype(np.int32)))
+        np.testing.assert_allclose(shaped.cpu().numpy(), g["shaped_%d" % gen], rtol=1e-12, atol=1e-15)
+    for name in ("strategy_simple_evolution", "strategy_simple_genetic"):
+        g = golden(name)
+        P, k = int(g["P"]), int(g["cfg_elite_num"])
+        eng = _engine(population=P, group=P)
+        for gen in range(3):
+            order = eng.rank_desc(_cuda(g["rewards_%d" % gen]), full_key=True).cpu().numpy()
+            assert np.array_equal(order[:k], g["elite_ids_%d" % gen])              # top-k parents bit-exact
+
+
+# ------------------------------------------------------------------------------------- K3
+def test_update_openai_regenerated_noise_bit_exact(twin):
+    P = 4096 + 37
+    eng = _engine(population=P, group=P, n_head=1, seed=21)
+    rng = np.random.default_rng(2)
+    order = rng.permutation(P).astype(np.int32)
+    shaped = twin.centered_rank(order)
+    mu = rng.normal(0, 1, D).astype(np.float32); m = rng.normal(0, .01, D).astype(np.float32)
+    v = np.abs(rng.normal(0, .01, D)).astype(np.float32)
+    lr, sigma, t, gen = 0.1, 0.2, 4, 9
+    mu_d, m_d, v_d = _cuda(mu), _cuda(m), _cuda(v)
+    grad_d = torch.empty(D, dtype=torch.float32, device="cuda")
+    eng.update_openai(gen, sigma, lr, t, _cuda(shaped), mu_d, m_d, v_d, grad_out=grad_d)
+    g = twin.grad_openai(shaped, D, 21, gen, P, 1, -(lr / (P * sigma)))
+    assert np.array_equal(grad_d.cpu().numpy(), g)
+    th, mm, vv = twin.adam(mu, m, v, g, eng.adam_a(lr, t))
+    assert np.array_equal(mu_d.cpu().numpy(), th) and np.array_equal(m_d.cpu().numpy(), mm) and np.array_equal(v_d.cpu().numpy(), vv)
+
+
+def test_update_openai_matches_reference_with_its_noise(golden):
+    """Verification mode: the kernel consumes the reference's own epsilon arrays (which hold
+    mu+eps from generation 1 on, quirk Q1) and must land on the reference's mu / Adam state."""
+    g = golden("strategy_openai_es")
+    P, lr = int(g["P"]), float(g["cfg_learning_rate"])
+    eng = _engine(population=P, group=P, n_head=1)
+    m_d = torch.zeros(D, dtype=torch.float32, device="cuda"); v_d = torch.zeros_like(m_d)
+    for gen in range(3):
+        sigma = float(g["sigma_before_%d" % gen])
+        mu_d = _cuda(g["mu_before_%d" % gen])
+        grad_d = torch.empty(D, dtype=torch.float32, device="cuda")
+        eng.update_openai(gen, sigma, lr, gen + 1, _cuda(g["shaped_%d" % gen]), mu_d, m_d, v_d,
+                          eps_override=_cuda(g["eps_%d" % gen]), grad_out=grad_d)
+        np.testing.assert_allclose(grad_d.cpu().numpy(), g["grad_%d" % gen], rtol=1e-4, atol=1e-7)
+        np.testing.assert_allclose(mu_d.cpu().numpy(), g["mu_after_%d" % gen], rtol=1e-4, atol=1e-6)   # north_star rtol
+        np.testing.assert_allclose(m_d.cpu().numpy(), g["adam_m_%d" % gen], rtol=1e-4, atol=1e-9)
+        np.testing.assert_allclose(v_d.cpu().numpy(), g["adam_v_%d" % gen], rtol=2e-4, atol=1e-12)
+
+
+def test_elite_mean_and_genetic_carry_over(twin, golden):
+    g = golden("strategy_simple_evolution")
+    P, k = int(g["P"]), int(g["cfg_elite_num"])
+    eng = _engine(population=P, group=P, n_head=2)
+    for gen in range(3):                                           # verification mode: reference populations
+        order = eng.rank_desc(_cuda(g["rewards_%d" % gen]), full_key=True)
+        mu = eng.elite_mean(gen, 0.0, None, order, k, w_override=_cuda(g["pop_%d" % gen]))
+        assert np.array_equal(mu.cpu().numpy(), g["mu_after_%d" % gen])              # bit-exact vs the reference
+    # Philox mode vs the twin
+    rng = np.random.default_rng(4)
+    parent = rng.normal(0, 1, (1, D)).astype(np.float32)
+    eng = _engine(population=97, group=97, n_head=2, seed=8)
+    order = rng.permutation(97).astype(np.int32)
+    mu = eng.elite_mean(3, 1.5, _cuda(parent), _cuda(order), 10).cpu().numpy()
+    assert np.array_equal(mu, twin.elite_mean(twin.materialize(parent, 1.5, 8, 3, 97, 2, order[:10])))
+    g = golden("strategy_simple_genetic")
+    P, k = int(g["P"]), int(g["cfg_elite_num"])
+    eng = _engine(population=P, group=P // k, n_head=1, n_parents=k)
+    for gen in range(3):
+        order = eng.rank_desc(_cuda(g["rewards_%d" % gen]), full_key=True)
+        el = eng.materialize(gen, 0.0, None, order[:k].contiguous(), w_override=_cuda(g["pop_%d" % gen]))
+        assert np.array_equal(el.cpu().numpy(), g["elites_after_%d" % gen])
+
+
+def test_generation_openai_host_matches_twin_composition(twin):
+    P, E, lr, sigma, seed = 2048, 5, 0.1, 0.5, 17
+    eng = _engine(population=P, group=P, n_head=1, eval_ep_num=E, seed=seed)
+    mu = np.zeros(D, np.float32); m = np.zeros(D, np.float32); v = np.zeros(D, np.float32)
+    fit = np.zeros(P, np.float64)
+    tmu, tm, tv = mu.copy(), m.copy(), v.copy()
+    for gen in range(3):
+        total = eng.generation_openai_host(gen, sigma, lr, gen + 1, mu, m, v, fit)
+        tf, ts = twin.population_cartpole(tmu[None], sigma=sigma, seed=seed, gen=gen, group=P, n_head=1, n=P, E=E, nthreads=8)
+        assert total == ts.sum() and np.array_equal(fit, tf)
+        shaped = twin.centered_rank(twin.rank_desc(tf))
+        g = twin.grad_openai(shaped, D, seed, gen, P, 1, -(lr / (P * sigma)))
+        tmu, tm, tv = twin.adam(tmu, tm, tv, g, eng.adam_a(lr, gen + 1))
+        assert np.array_equal(mu, tmu) and np.array_equal(m, tm) and np.array_equal(v, tv)
+        sigma *= 0.999
