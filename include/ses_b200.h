@@ -126,9 +126,11 @@ int ses_generation_openai_host(ses_handle *h, uint32_t generation, float sigma, 
 
 /* Test hook: the numerical-contract functions on the device, elementwise.
  * kind: 0 tanh32, 1 sigmoid32, 2 ln32, 3 sin2pi32, 4 cos2pi32 (in/out f32);
- *       5 sin64, 6 cos64 (in/out f64).  Test hook: standard normals for (generation, id): 7. */
+ *       5 sin64, 6 cos64 (in/out f64); 7 tanh32 with the division fast path written out (what K1 runs). */
 int ses_test_math(int32_t kind, const void *in_dev, void *out_dev, int64_t n, void *stream);
 int ses_test_normals(ses_handle *h, uint32_t generation, int32_t id, float *out_dev /* [D] */, void *stream);
+/* counts float32 inputs x in [lo, hi] (and -x) for which K1's fast-path tanh differs from the contract's tanh32 */
+int ses_test_tanh_fast_exhaustive(float lo, float hi, uint64_t *mismatches_host);
 
 /* Measurement hook: FP32 (non-tensor) FFMA peak of `device` in TFLOP/s from a dependent-free FFMA
  * microbenchmark -- the denominator of the rollout kernel's roofline in bench.py. */

@@ -37,6 +37,7 @@ SYMBOLS = {
     "ses_generation_openai_host": (C.c_int, [_vp, _u32, _f32, _f64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ses_test_math": (C.c_int, [_i32, _vp, _vp, _i64, _vp]),
     "ses_test_normals": (C.c_int, [_vp, _u32, _i32, _vp, _vp]),
+    "ses_test_tanh_fast_exhaustive": (C.c_int, [_f32, _f32, C.POINTER(C.c_uint64)]),
     "ses_measure_fp32_peak": (C.c_int, [_i32, C.POINTER(C.c_double)]),
     "ses_launch_count": (_i64, [_vp]),
 }

@@ -27,7 +27,7 @@ __global__ void k_sort_init(const double *__restrict__ fitness, int n, int key_b
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     const int i = n - 1 - p;
-    const double f = fitness[i];
+    const double f = __dadd_rn(fitness[i], 0.0);   // -0.0 -> +0.0: numpy compares them equal
     unsigned long long k;
     if (key_bits == 0) {
         const unsigned long long b = (unsigned long long)__double_as_longlong(f);

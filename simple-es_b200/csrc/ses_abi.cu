@@ -68,7 +68,8 @@ struct ses_handle {
     int *h_order = nullptr;
     unsigned long long *h_total = nullptr;
     // rollout launch configuration
-    int slots = 8;
+    int cta_warps = 4;
+    int lanes_used_override = 0;
     int ctas_per_sm = 0;
     int64_t launches = 0;
 };
@@ -120,7 +121,8 @@ extern "C" int ses_create(const ses_config *cfg, ses_handle **out)
     // (gym_wrapper.py:37-39) can only shorten it.  simple_spread: max_cycles=25.
     const int env_cap = cfg->env == SES_ENV_CARTPOLE ? 500 : 25;
     h->eff_max_step = cfg->max_step > 0 ? (cfg->max_step < env_cap ? cfg->max_step : env_cap) : env_cap;
-    h->slots = env_int("SES_ROLLOUT_SLOTS", 8);
+    h->cta_warps = env_int("SES_ROLLOUT_CTA_WARPS", 4);
+    h->lanes_used_override = env_int("SES_ROLLOUT_LANES", 0);
     h->ctas_per_sm = env_int("SES_ROLLOUT_CTAS_PER_SM", 0);
 
     const int P = cfg->population;
@@ -202,25 +204,27 @@ extern "C" int ses_rollout(ses_handle *h, uint32_t generation, float sigma, cons
     rp.layout.group = c.group; rp.layout.n_head = c.n_head;
     rp.id_begin = c.id_begin; rp.id_end = c.id_end;
     rp.E = c.eval_ep_num; rp.max_step = h->eff_max_step; rp.pomdp = c.pomdp; rp.init_mode = c.init_mode;
-    rp.n_trace = n_trace; rp.slots_cap = 0; rp.n_agents = c.n_agents;
+    rp.n_trace = n_trace; rp.slots_cap = 0; rp.lanes_used = 32; rp.n_agents = c.n_agents;
+
+    // lanes of a warp that take episodes: a multiple of E so that slots start and finish together
+    rp.lanes_used = c.eval_ep_num >= 32 ? 32 : c.eval_ep_num * (32 / c.eval_ep_num);
+    if (h->lanes_used_override > 0) rp.lanes_used = h->lanes_used_override < 32 ? h->lanes_used_override : 32;
 
     if (c.env == SES_ENV_CARTPOLE && !c.gru) {
-        constexpr int WARPS = 4;
-        auto go = [&](auto kern, int Sl) -> int {
-            const size_t smem = (size_t)WARPS * (Sl == 8 ? sizeof(CartpoleWarpSmem<8>) : sizeof(CartpoleWarpSmem<16>));
-            // spread small populations over more warps: cap the slots a warp may hold
-            int per_sm = 0;
-            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
-            if (h->ctas_per_sm > 0 && h->ctas_per_sm < per_sm) per_sm = h->ctas_per_sm;
-            const long long total_warps = (long long)per_sm * h->num_sms * WARPS;
-            int cap = (int)((n_local + total_warps - 1) / total_warps);
-            rp.slots_cap = cap < 1 ? 1 : (cap > Sl ? Sl : cap);
-            return launch_persistent(h, kern, WARPS * 32, smem, WARPS * rp.slots_cap, n_local, rp, st);
-        };
+        constexpr int SL = 8;
+        rp.slots_cap = SL;
+        // as few warps as give every episode a lane at once; all resident warps when there is more work than that
+        const long long n_episodes = (long long)n_local * c.eval_ep_num;
         const bool tr = n_trace > 0;
-        if (h->slots == 16) return tr ? go(k_rollout_cartpole_mlp<16, WARPS, true>, 16) : go(k_rollout_cartpole_mlp<16, WARPS, false>, 16);
-        return tr ? go(k_rollout_cartpole_mlp<8, WARPS, true>, 8) : go(k_rollout_cartpole_mlp<8, WARPS, false>, 8);
+        if (h->cta_warps == 1) {
+            const int need_warps = (int)((n_episodes + rp.lanes_used - 1) / rp.lanes_used);
+            return tr ? launch_persistent(h, k_rollout_cartpole_mlp<SL, 1, true>, 32, sizeof(CartpoleWarpSmem<SL>), 1, need_warps, rp, st)
+                      : launch_persistent(h, k_rollout_cartpole_mlp<SL, 1, false>, 32, sizeof(CartpoleWarpSmem<SL>), 1, need_warps, rp, st);
+        }
+        constexpr int WARPS = 4;
+        const int need_warps = (int)((n_episodes + rp.lanes_used - 1) / rp.lanes_used);
+        return tr ? launch_persistent(h, k_rollout_cartpole_mlp<SL, WARPS, true>, WARPS * 32, WARPS * sizeof(CartpoleWarpSmem<SL>), WARPS, need_warps, rp, st)
+                  : launch_persistent(h, k_rollout_cartpole_mlp<SL, WARPS, false>, WARPS * 32, WARPS * sizeof(CartpoleWarpSmem<SL>), WARPS, need_warps, rp, st);
     }
     if (c.env == SES_ENV_CARTPOLE && c.gru) return launch_rollout_cartpole_gru(h->num_sms, h->ctas_per_sm, rp, n_trace > 0, st, &h->launches, g_err, sizeof(g_err));
     return launch_rollout_mpe(h->num_sms, h->ctas_per_sm, rp, n_trace > 0, st, &h->launches, g_err, sizeof(g_err));
@@ -393,7 +397,7 @@ __global__ void k_test_math(int kind, const void *in, void *out, long long n)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    if (kind <= 4) {
+    if (kind <= 4 || kind == 7) {
         const float x = static_cast<const float *>(in)[i];
         float y = 0.0f, s, c;
         switch (kind) {
@@ -401,6 +405,7 @@ __global__ void k_test_math(int kind, const void *in, void *out, long long n)
         case 1: y = sigm32(x); break;
         case 2: y = ln32(x); break;
         case 3: sincos2pi32(x, s, c); y = s; break;
+        case 7: y = tanh32_fast(x); break;
         default: sincos2pi32(x, s, c); y = c; break;
         }
         static_cast<float *>(out)[i] = y;
@@ -412,7 +417,7 @@ __global__ void k_test_math(int kind, const void *in, void *out, long long n)
 
 extern "C" int ses_test_math(int32_t kind, const void *in_dev, void *out_dev, int64_t n, void *stream)
 {
-    if (kind < 0 || kind > 6) return fail("ses_test_math: unknown kind %d", kind);
+    if (kind < 0 || kind > 7) return fail("ses_test_math: unknown kind %d", kind);
     if (n < 1) return 0;
     k_test_math<<<(unsigned)((n + 255) / 256), 256, 0, S(stream)>>>(kind, in_dev, out_dev, (long long)n);
     CU(cudaGetLastError());
@@ -483,5 +488,37 @@ extern "C" int ses_measure_fp32_peak(int32_t device, double *tflops_out)
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
     *tflops_out = best;
+    return 0;
+}
+
+// every float32 bit pattern b in [lo_bits, hi_bits]: tanh32_fast(x) must equal tanh32(x) bit for bit
+__global__ void k_tanh_fast_exhaustive(uint32_t lo_bits, uint32_t hi_bits, unsigned long long *mismatches)
+{
+    unsigned long long bad = 0;
+    const unsigned long long n = (unsigned long long)hi_bits - lo_bits + 1ull;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const float x = __uint_as_float(lo_bits + (uint32_t)i);
+        const uint32_t a = __float_as_uint(tanh32_fast(x)), b = __float_as_uint(tanh32(x));
+        const uint32_t an = __float_as_uint(tanh32_fast(-x)), bn = __float_as_uint(tanh32(-x));
+        // +0 and -0 compare equal (the only inputs that can differ in the sign of a zero result are x = +-0)
+        bad += ((a != b) && ((a | b) << 1) != 0) + ((an != bn) && ((an | bn) << 1) != 0);
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+extern "C" int ses_test_tanh_fast_exhaustive(float lo, float hi, uint64_t *mismatches_host)
+{
+    if (!mismatches_host || !(lo >= 0.0f) || !(hi >= lo)) return fail("ses_test_tanh_fast_exhaustive: bad arguments");
+    unsigned long long *d = nullptr;
+    CU(cudaMalloc(&d, sizeof(unsigned long long)));
+    CU(cudaMemset(d, 0, sizeof(unsigned long long)));
+    uint32_t lb, hb;
+    memcpy(&lb, &lo, 4); memcpy(&hb, &hi, 4);
+    k_tanh_fast_exhaustive<<<148 * 16, 256>>>(lb, hb, d);
+    CU(cudaGetLastError());
+    unsigned long long r = 0;
+    CU(cudaMemcpy(&r, d, sizeof(r), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    *mismatches_host = r;
     return 0;
 }

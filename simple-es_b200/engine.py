@@ -211,10 +211,16 @@ class RolloutEngine:
 
     # ------------------------------------------------------------------------------ test hooks
     def test_math(self, kind, x):
-        kinds = {"tanh": 0, "sigmoid": 1, "ln": 2, "sin2pi": 3, "cos2pi": 4, "sin64": 5, "cos64": 6}
+        kinds = {"tanh": 0, "sigmoid": 1, "ln": 2, "sin2pi": 3, "cos2pi": 4, "sin64": 5, "cos64": 6, "tanh_fast": 7}
         out = torch.empty_like(x)
         _lib.check(self.lib.ses_test_math(kinds[kind], _ptr(x), _ptr(out), x.numel(), self._stream()))
         return out
+
+    def test_tanh_fast_exhaustive(self, lo=0.0, hi=10.0):
+        """Number of float32 inputs in [lo, hi] (and their negatives) where K1's fast-path tanh != the contract's."""
+        bad = C.c_uint64(0)
+        _lib.check(self.lib.ses_test_tanh_fast_exhaustive(float(lo), float(hi), C.byref(bad)))
+        return int(bad.value)
 
     def test_normals(self, generation, idx):
         out = torch.empty(self.D, dtype=torch.float32, device=self.device)
