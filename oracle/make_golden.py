@@ -102,6 +102,51 @@ def golden_rollout(ref, gru, pomdp, P, E, seed, sigma, n_trace):
                 gru=np.int32(gru), pomdp=np.int32(pomdp), E=np.int32(E), max_step=np.int32(500))
 
 
+class TracingSpread(pyref.SimpleSpreadShim):
+    def __init__(self, *a, **kw):
+        self.log = []
+        super().__init__(*a, **kw)
+
+    def reset(self):
+        self.log.append(("reset",))
+        return super().reset()
+
+    def step(self, action):
+        out = super().step(action)
+        self.log.append(([int(action[a]) for a in self.agents], self.apos.copy().ravel(), self.avel.copy().ravel(), out[1]))
+        return out
+
+
+def golden_spread(ref, N, P, E, seed, sigma, n_trace):
+    """Reference RolloutWorker + one GymEnvModel copy per agent (utils.wrap_agentid semantics) over the
+    simple_spread restatement, fixed [E, 4N] initial positions shared by every offspring."""
+    from copy import deepcopy
+    rng = np.random.RandomState(seed)
+    obs_dim, act = 6 * N, 5
+    D = pyref.param_count(obs_dim, act, False)
+    init = rng.uniform(-1, 1, size=(E, 4 * N))
+    W = rng.normal(0, sigma, size=(P, D)).astype(np.float32)
+    W[0] = 0.0
+    fitness = np.zeros(P)
+    traces = np.full((n_trace, 25, 4 * N), np.nan)
+    tr_actions = np.full((n_trace, 25, N), -1, dtype=np.int32)
+    tr_rewards = np.full((n_trace, 25), np.nan)
+    for i in range(P):
+        model = ref.GymEnvModel(obs_dim, act, True, False)
+        set_flat(model, W[i], obs_dim, act, False)
+        env = TracingSpread(N=N, init_states=init)
+        env.log = []
+        group = {a: deepcopy(model) for a in env.get_agent_ids()}
+        fitness[i] = ref.RolloutWorker((env, group, E))
+        if i < n_trace:
+            for t, rec in enumerate(env.log[1:26]):
+                tr_actions[i, t] = rec[0]
+                traces[i, t] = np.concatenate([rec[1], rec[2]])
+                tr_rewards[i, t] = rec[3]
+    return dict(W=W, init=init, fitness=fitness, traces=traces, trace_actions=tr_actions, trace_rewards=tr_rewards,
+                N=np.int32(N), E=np.int32(E))
+
+
 def reward_vectors(P, rng):
     """Three synthetic reward vectors: tie-free floats, CartPole-like tie-heavy k/5, mixed."""
     r0 = rng.uniform(8, 500, size=P)
@@ -177,6 +222,8 @@ def main():
         "policy_gru": lambda: golden_policy(ref, True, 12, 40, 12),
         "rollout_cartpole_mlp": lambda: golden_rollout(ref, False, False, 256, 5, 21, 2.0, 6),
         "rollout_cartpole_gru_pomdp": lambda: golden_rollout(ref, True, True, 24, 3, 22, 0.7, 3),
+        "rollout_spread_n2": lambda: golden_spread(ref, 2, 128, 5, 41, 1.0, 4),
+        "rollout_spread_n3": lambda: golden_spread(ref, 3, 48, 3, 42, 1.0, 2),
         "strategy_simple_evolution": lambda: golden_strategy(ref, "simple_evolution", 31),
         "strategy_simple_genetic": lambda: golden_strategy(ref, "simple_genetic", 32),
         "strategy_openai_es": lambda: golden_strategy(ref, "openai_es", 33),

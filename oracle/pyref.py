@@ -135,7 +135,8 @@ class SimpleSpreadShim:
         self.init_states = None if init_states is None else np.asarray(init_states, dtype=np.float64)
         self._reset_count = 0
         self.rng = np.random.RandomState(seed)
-        self.reset()
+        self.reset()              # pettingzoo_wrapper.py:20 resets once at construction
+        self._reset_count = 0     # ... which must not consume a row of an explicit init table
 
     # -- world -------------------------------------------------------------------------
     def _observe(self, i):

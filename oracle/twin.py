@@ -211,3 +211,49 @@ def elite_mean(elites):
     mu = np.empty(D, dtype=np.float32)
     lib().tw_elite_mean(_p(elites), C.c_int(k), C.c_int(D), _p(mu))
     return mu
+
+
+# ---------------------------------------------------------------------------- MPE simple_spread
+def logaddexp0(y):
+    y = _f64(y); out = np.empty_like(y)
+    lib().tw_logaddexp0_v(_p(y), _p(out), C.c_int64(y.size))
+    return out
+
+
+def spread_init(seed, init_mode, gen, idx, e, N=2):
+    st = np.empty(4 * N, dtype=np.float64)
+    lib().tw_spread_init(C.c_uint32(seed), C.c_int(init_mode), C.c_uint32(gen), C.c_uint32(idx), C.c_uint32(e), C.c_int(N), _p(st))
+    return st
+
+
+def spread_policy(w, N, o):
+    w = _f32(w); o = _f32(o)
+    logits = np.zeros(5, dtype=np.float32)
+    a = lib().tw_spread_policy(_p(w), C.c_int(N), _p(o), _p(logits))
+    return int(a), logits
+
+
+def rollout_mpe(w, N=2, E=5, max_cycles=25, init=None, seed=0, init_mode=0, gen=0, idx=0, trace_steps=0):
+    """One offspring.  Returns (fitness, steps, trace[trace_steps,4N], actions[trace_steps,N])."""
+    w = _f32(w)
+    init_a = None if init is None else _f64(init)
+    trace = np.full((max(trace_steps, 1), 4 * N), np.nan, dtype=np.float64)
+    acts = np.full((max(trace_steps, 1), N), -1, dtype=np.int32)
+    steps = C.c_int64(0)
+    f = lib().tw_rollout_mpe(_p(w), C.c_int(N), C.c_int(E), C.c_int(max_cycles), _p(init_a), C.c_uint32(seed),
+                             C.c_int(init_mode), C.c_uint32(gen), C.c_uint32(idx), _p(trace), _p(acts), C.c_int(trace_steps),
+                             C.byref(steps))
+    return float(f), int(steps.value), trace[:trace_steps], acts[:trace_steps]
+
+
+def population_mpe(parents, N=2, sigma=0.0, seed=0, gen=0, group=1, n_head=1, id0=0, n=1, E=5, max_cycles=25,
+                   W_override=None, init=None, init_mode=0):
+    parents = _f32(parents)
+    Wo = None if W_override is None else _f32(W_override)
+    init_a = None if init is None else _f64(init)
+    fit = np.empty(n, dtype=np.float64)
+    steps = np.empty(n, dtype=np.int64)
+    lib().tw_population_mpe(_p(parents), C.c_int(N), C.c_float(sigma), C.c_uint32(seed), C.c_uint32(gen), C.c_int(group),
+                            C.c_int(n_head), C.c_int(id0), C.c_int(n), C.c_int(E), C.c_int(max_cycles), _p(Wo), _p(init_a),
+                            C.c_int(init_mode), _p(fit), _p(steps))
+    return fit, steps

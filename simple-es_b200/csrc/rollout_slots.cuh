@@ -1,0 +1,226 @@
+// rollout_slots.cuh -- the persistent "warp owns S offspring slots, lane owns one episode" rollout
+// kernel, generic over the environment / policy pair (CartPole-v1 MLP, simple_spread MLP).
+//
+// Replaces, per generation: the mp.Pool fan-out (loop.py:66-78), RolloutWorker (loop.py:108-125),
+// GymEnvModel.forward (networks/neural_network.py:20-36), the env wrappers' reset/step
+// (envs/gym_wrapper.py:23-45,69-77, envs/pettingzoo_wrapper.py:22-58), the third-party physics
+//  and the perturbation half of _gen_offsprings
+// (offspring_strategies.py:53-60,169-176,312-326).
+//
+// Mapping: persistent warps, no inter-warp communication.
+//   * a warp owns S "offspring slots" in shared memory; a slot holds the D perturbed weights of one
+//     offspring as float4 quads, slot-interleaved ([quad][slot]) so that an LDS.128 of one quad by 32
+//     lanes touches at most S*16 B = one conflict-free wavefront (S = 8).
+//   * a lane runs ONE episode at a time: env state in registers, fp32 policy from the slot's weights.
+//     When its episode ends it is handed the next pending (slot, episode) pair by a warp-synchronous
+//     scheduler (ballot + prefix), so lanes stay busy although CartPole episodes last 8..500 steps.
+//   * refill is demand driven: the warp takes just enough new offspring ids from a global atomic
+//     counter to occupy its idle lanes, never more.  Only `lanes_used` = E*floor(32/E) lanes take
+//     work, so when every episode has the same length (a converged CartPole population, or
+//     simple_spread's fixed 25 cycles) whole slots start and finish together, no episode is left
+//     waiting for a later round, and the last round of a generation is packed into few full warps
+//     while the others exit.
+//   * the weights of a new offspring are re-derived from Philox(generation, id) by the whole warp:
+//     there is no noise table, and nothing but 16 B per offspring ever goes to HBM.
+//
+// An Env type provides:
+//   D, NQ, STATE_DIM, N_AGENTS, UNIT_REWARD (reward == 1.0 per step: fitness = steps / E exactly)
+//   struct State;  init(State&, p, id, ep);
+//   step<S>(State&, w[NQ][S], slot, p, int *actions) -> done   (also adds the step reward to State::ret)
+//   store_trace(State&, double *row)
+#pragma once
+#include "ses_common.cuh"
+
+namespace ses {
+
+struct RolloutParams {
+    const float *parents;        // [n_parents][D]
+    const float *w_override;     // optional [n_local][D]
+    const double *init_states;   // optional [E][state_dim]
+    double *fitness;             // [P]
+    long long *steps;            // [P]
+    double *trace;               // optional [n_trace][200][state_dim]
+    int *trace_actions;          // optional [n_trace][200][n_agents]
+    int *work_counter;           // zeroed before launch
+    float sigma;
+    uint32_t seed;
+    uint32_t gen;
+    Layout layout;
+    int id_begin, id_end;
+    int E;
+    int max_step;
+    int pomdp;
+    int init_mode;
+    int n_trace;
+    int slots_cap;               // <= S: slots a warp may hold
+    int lanes_used;              // lanes of a warp that take episodes (E*floor(32/E) by default)
+    int n_agents;                // simple_spread only
+};
+
+constexpr int MAX_E = 32;
+
+template <class Env, int S, bool NeedRet>
+struct __align__(16) SlotSmem;
+
+template <class Env, int S>
+struct __align__(16) SlotSmem<Env, S, false> {
+    float4 w[Env::NQ][S];
+    int off_id[S];
+    int ep_next[S];
+    int ep_done[S];
+    int steps[S];
+};
+
+template <class Env, int S>
+struct __align__(16) SlotSmem<Env, S, true> {
+    float4 w[Env::NQ][S];
+    double ret[S][MAX_E];        // per-episode returns, summed in episode order when the slot retires
+    int off_id[S];
+    int ep_next[S];
+    int ep_done[S];
+    int steps[S];
+};
+
+template <class Env, int S, int WARPS, bool TRACE>
+__global__ void __launch_bounds__(WARPS * 32) k_rollout_slots(const RolloutParams p)
+{
+    using Smem = SlotSmem<Env, S, !Env::UNIT_REWARD>;
+    constexpr int NQ = Env::NQ, D = Env::D;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem &sm = reinterpret_cast<Smem *>(smem_raw)[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lt = lanemask_lt();
+    const bool usable = lane < p.lanes_used;
+
+    if (lane < S) { sm.off_id[lane] = -1; sm.ep_next[lane] = 0; sm.ep_done[lane] = 0; sm.steps[lane] = 0; }
+    __syncwarp();
+
+    // per-lane episode state
+    int slot = -1, nstep = 0;
+    [[maybe_unused]] int ep = 0;
+    typename Env::State st;
+    bool more = true;          // warp-uniform: the global offspring queue may still hold work
+    bool sched = true;         // warp-uniform: something changed that the scheduler must look at
+
+    for (;;) {
+        if (sched) {
+            // ------------------------------------------------------------------ scheduler
+            __syncwarp();
+            int my_id = -1;
+            if (lane < S) {
+                my_id = sm.off_id[lane];
+                if (my_id >= 0 && sm.ep_done[lane] == p.E) {       // offspring finished: emit fitness
+                    const int stp = sm.steps[lane];
+                    p.steps[my_id] = (long long)stp;
+                    double total;
+                    if constexpr (Env::UNIT_REWARD) {
+                        total = (double)stp;                        // reward 1.0 per step
+                    } else {
+                        total = 0.0;
+                        for (int e = 0; e < p.E; ++e) total = __dadd_rn(total, sm.ret[lane][e]);
+                    }
+                    p.fitness[my_id] = __ddiv_rn(total, (double)p.E);   // loop.py:124
+                    sm.off_id[lane] = -1;
+                    my_id = -1;
+                }
+            }
+            const unsigned empty_mask = __ballot_sync(FULL, lane < p.slots_cap && my_id < 0);
+            const int pend_mine = (lane < S && my_id >= 0) ? (p.E - sm.ep_next[lane]) : 0;
+            int pending = pend_mine;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) pending += __shfl_xor_sync(FULL, pending, o);
+            const unsigned idle_mask = __ballot_sync(FULL, usable && slot < 0);
+            const int n_idle = __popc(idle_mask);
+            // demand-driven refill: just enough new offspring to occupy the idle lanes
+            int want = (n_idle - pending + p.E - 1) / p.E;
+            want = min(max(want, 0), __popc(empty_mask));
+            if (want > 0 && more) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(p.work_counter, want);
+                base = __shfl_sync(FULL, base, 0) + p.id_begin;
+                if (base + want >= p.id_end) more = false;
+                const int got = max(0, min(want, p.id_end - base));
+                const int my_rank = __popc(empty_mask & lt);       // rank of this lane's slot among the empty ones
+                const bool fill = ((empty_mask >> lane) & 1u) && my_rank < got;
+                if (fill) {
+                    sm.off_id[lane] = base + my_rank;
+                    sm.ep_next[lane] = 0;
+                    sm.ep_done[lane] = 0;
+                    sm.steps[lane] = 0;
+                }
+                const unsigned fill_mask = __ballot_sync(FULL, fill);
+                __syncwarp();
+                // regenerate the weights of the newly filled slots: (slot, quad) tasks over 32 lanes
+                const int ntask = got * NQ;
+                for (int t = lane; t < ntask; t += 32) {
+                    const int k = t / NQ, q = t - k * NQ;
+                    const int s = __fns(fill_mask, 0, k + 1);      // k-th filled slot
+                    const int id = sm.off_id[s];
+                    float4 wq;
+                    if (p.w_override) {
+                        const float *row = p.w_override + (size_t)(id - p.id_begin) * D;
+                        const int d = 4 * q;
+                        wq.x = row[d];
+                        wq.y = d + 1 < D ? row[d + 1] : 0.0f;
+                        wq.z = d + 2 < D ? row[d + 2] : 0.0f;
+                        wq.w = d + 3 < D ? row[d + 3] : 0.0f;
+                    } else {
+                        wq = offspring_quad(p.parents + (size_t)p.layout.parent(id) * D, D, q,
+                                            p.layout.perturbed(id), p.sigma, p.seed, (uint32_t)id, p.gen);
+                    }
+                    sm.w[q][s] = wq;
+                }
+                __syncwarp();
+            }
+            // hand pending (slot, episode) pairs to idle lanes, in slot order
+            const int r = __popc(idle_mask & lt);
+            int acc = 0, my_slot = -1, my_ep = 0, my_prefix = 0, my_avail = 0;
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                const int nx = sm.ep_next[s];
+                const int av = (sm.off_id[s] >= 0) ? (p.E - nx) : 0;
+                if (usable && slot < 0 && my_slot < 0 && r < acc + av) { my_slot = s; my_ep = nx + (r - acc); }
+                if (lane == s) { my_prefix = acc; my_avail = av; }
+                acc += av;
+            }
+            __syncwarp();
+            if (lane < S) sm.ep_next[lane] += max(0, min(my_avail, n_idle - my_prefix));
+            __syncwarp();
+            if (my_slot >= 0) {
+                slot = my_slot; ep = my_ep; nstep = 0;
+                Env::init(st, p, sm.off_id[my_slot], my_ep);
+            }
+            if (__ballot_sync(FULL, slot >= 0) == 0) break;        // queue empty and every lane idle
+        }
+
+        bool just_done = false;
+        if (slot >= 0) {
+            // ------------------------------------------------------------------ one env step
+            int actions[Env::N_AGENTS];
+            bool done = Env::template step<S>(st, sm.w, slot, p, actions);
+            ++nstep;                                               // gym_wrapper.py:33 / pettingzoo_wrapper.py:34
+            if (nstep >= p.max_step) done = true;                  // gym_wrapper.py:37-39, TimeLimit / max_cycles
+            if constexpr (TRACE) {
+                const int local = sm.off_id[slot] - p.id_begin;
+                if (ep == 0 && local < p.n_trace && nstep <= 200) {
+                    Env::store_trace(st, p.trace + ((size_t)local * 200 + (nstep - 1)) * Env::STATE_DIM);
+#pragma unroll
+                    for (int a = 0; a < Env::N_AGENTS; ++a) p.trace_actions[((size_t)local * 200 + (nstep - 1)) * Env::N_AGENTS + a] = actions[a];
+                }
+            }
+            if (done) {
+                if constexpr (!Env::UNIT_REWARD) sm.ret[slot][ep] = st.ret;
+                atomicAdd(&sm.steps[slot], nstep);
+                atomicAdd(&sm.ep_done[slot], 1);
+                slot = -1;
+                just_done = true;
+            }
+        }
+        // the scheduler has work only right after an episode ended (a lane to re-arm, maybe a slot
+        // to retire and refill); otherwise idle lanes stay idle and the warp keeps stepping
+        sched = __ballot_sync(FULL, just_done) != 0;
+    }
+}
+
+}  // namespace ses

@@ -68,7 +68,6 @@ struct ses_handle {
     int *h_order = nullptr;
     unsigned long long *h_total = nullptr;
     // rollout launch configuration
-    int cta_warps = 4;
     int lanes_used_override = 0;
     int ctas_per_sm = 0;
     int64_t launches = 0;
@@ -121,7 +120,6 @@ extern "C" int ses_create(const ses_config *cfg, ses_handle **out)
     // (gym_wrapper.py:37-39) can only shorten it.  simple_spread: max_cycles=25.
     const int env_cap = cfg->env == SES_ENV_CARTPOLE ? 500 : 25;
     h->eff_max_step = cfg->max_step > 0 ? (cfg->max_step < env_cap ? cfg->max_step : env_cap) : env_cap;
-    h->cta_warps = env_int("SES_ROLLOUT_CTA_WARPS", 4);
     h->lanes_used_override = env_int("SES_ROLLOUT_LANES", 0);
     h->ctas_per_sm = env_int("SES_ROLLOUT_CTAS_PER_SM", 0);
 
@@ -160,20 +158,24 @@ extern "C" int64_t ses_launch_count(ses_handle *h) { return h ? h->launches : 0;
 // ------------------------------------------------------------------------------------------------
 // K1
 // ------------------------------------------------------------------------------------------------
-template <typename Kernel>
-static int launch_persistent(ses_handle *h, Kernel kernel, int threads, size_t smem, int units_per_cta, int n_units,
-                             const RolloutParams &rp, cudaStream_t st)
+template <class Env, int SL>
+static int launch_slots(ses_handle *h, RolloutParams &rp, int need_warps, bool trace, cudaStream_t st)
 {
+    constexpr int WARPS = 4;
+    using Smem = SlotSmem<Env, SL, !Env::UNIT_REWARD>;
+    auto kernel = trace ? k_rollout_slots<Env, SL, WARPS, true> : k_rollout_slots<Env, SL, WARPS, false>;
+    const size_t smem = WARPS * sizeof(Smem);
+    rp.slots_cap = SL;
     CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, WARPS * 32, smem));
     if (per_sm < 1) return fail("rollout kernel does not fit on an SM (smem %zu B)", smem);
     if (h->ctas_per_sm > 0 && h->ctas_per_sm < per_sm) per_sm = h->ctas_per_sm;
     int grid = per_sm * h->num_sms;
-    const int need = (n_units + units_per_cta - 1) / units_per_cta;
+    const int need = (need_warps + WARPS - 1) / WARPS;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    kernel<<<grid, threads, smem, st>>>(rp);
+    kernel<<<grid, WARPS * 32, smem, st>>>(rp);
     CU(cudaGetLastError());
     h->launches += 1;
     return 0;
@@ -210,24 +212,19 @@ extern "C" int ses_rollout(ses_handle *h, uint32_t generation, float sigma, cons
     rp.lanes_used = c.eval_ep_num >= 32 ? 32 : c.eval_ep_num * (32 / c.eval_ep_num);
     if (h->lanes_used_override > 0) rp.lanes_used = h->lanes_used_override < 32 ? h->lanes_used_override : 32;
 
+    // as few warps as give every episode a lane at once; all resident warps when there is more work than that
+    const long long n_episodes = (long long)n_local * c.eval_ep_num;
+    const int need_warps = (int)((n_episodes + rp.lanes_used - 1) / rp.lanes_used);
+    const bool tr = n_trace > 0;
     if (c.env == SES_ENV_CARTPOLE && !c.gru) {
-        constexpr int SL = 8;
-        rp.slots_cap = SL;
-        // as few warps as give every episode a lane at once; all resident warps when there is more work than that
-        const long long n_episodes = (long long)n_local * c.eval_ep_num;
-        const bool tr = n_trace > 0;
-        if (h->cta_warps == 1) {
-            const int need_warps = (int)((n_episodes + rp.lanes_used - 1) / rp.lanes_used);
-            return tr ? launch_persistent(h, k_rollout_cartpole_mlp<SL, 1, true>, 32, sizeof(CartpoleWarpSmem<SL>), 1, need_warps, rp, st)
-                      : launch_persistent(h, k_rollout_cartpole_mlp<SL, 1, false>, 32, sizeof(CartpoleWarpSmem<SL>), 1, need_warps, rp, st);
-        }
-        constexpr int WARPS = 4;
-        const int need_warps = (int)((n_episodes + rp.lanes_used - 1) / rp.lanes_used);
-        return tr ? launch_persistent(h, k_rollout_cartpole_mlp<SL, WARPS, true>, WARPS * 32, WARPS * sizeof(CartpoleWarpSmem<SL>), WARPS, need_warps, rp, st)
-                  : launch_persistent(h, k_rollout_cartpole_mlp<SL, WARPS, false>, WARPS * 32, WARPS * sizeof(CartpoleWarpSmem<SL>), WARPS, need_warps, rp, st);
+        // slots per warp: enough offspring to occupy 32 lanes (E >= 4: 8, E in {2,3}: 16, E = 1: 32)
+        if (c.eval_ep_num >= 4) return launch_slots<CartpoleMlpEnv, 8>(h, rp, need_warps, tr, st);
+        if (c.eval_ep_num >= 2) return launch_slots<CartpoleMlpEnv, 16>(h, rp, need_warps, tr, st);
+        return launch_slots<CartpoleMlpEnv, 32>(h, rp, need_warps, tr, st);
     }
-    if (c.env == SES_ENV_CARTPOLE && c.gru) return launch_rollout_cartpole_gru(h->num_sms, h->ctas_per_sm, rp, n_trace > 0, st, &h->launches, g_err, sizeof(g_err));
-    return launch_rollout_mpe(h->num_sms, h->ctas_per_sm, rp, n_trace > 0, st, &h->launches, g_err, sizeof(g_err));
+    if (c.env == SES_ENV_CARTPOLE && c.gru) return launch_rollout_cartpole_gru(h->num_sms, h->ctas_per_sm, rp, tr, st, &h->launches, g_err, sizeof(g_err));
+    if (c.n_agents == 2) return launch_slots<SpreadEnv<2>, 8>(h, rp, need_warps, tr, st);
+    return launch_slots<SpreadEnv<3>, 8>(h, rp, need_warps, tr, st);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -285,3 +285,72 @@ def test_generation_openai_host_matches_twin_composition(twin):
         tmu, tm, tv = twin.adam(tmu, tm, tv, g, eng.adam_a(lr, gen + 1))
         assert np.array_equal(mu, tmu) and np.array_equal(m, tm) and np.array_equal(v, tv)
         sigma *= 0.999
+
+
+# ------------------------------------------------------------------------------------- K1: GRU policy (BASELINE config 2)
+DG = 6562
+
+
+@pytest.mark.parametrize("pomdp,E,sigma", [(True, 5, 0.7), (False, 3, 0.3), (True, 7, 0.7)])
+def test_rollout_gru_philox_bit_exact(twin, pomdp, E, sigma):
+    P = 600
+    eng = _engine(population=P, group=P, n_head=2, eval_ep_num=E, gru=True, pomdp=pomdp, seed=13)
+    rng = np.random.default_rng(7)
+    mu = rng.normal(0, 0.3, (1, DG)).astype(np.float32)
+    fit, steps = eng.rollout(4, sigma, _cuda(mu))
+    tf, ts = twin.population_cartpole(mu, gru=True, pomdp=pomdp, sigma=sigma, seed=13, gen=4, group=P, n_head=2, n=P, E=E, nthreads=8)
+    assert np.array_equal(steps.cpu().numpy(), ts)
+    assert np.array_equal(fit.cpu().numpy(), tf)
+    assert ts[0] == ts[1]                                   # simple_evolution layout: offspring 0 and 1 are both mu
+
+
+def test_rollout_gru_verification_mode_matches_reference(twin, golden):
+    g = golden("rollout_cartpole_gru_pomdp")
+    W, init, E = g["W"], g["init"], int(g["E"])
+    tid = [int(i) for i in g["trace_ids"]]
+    perm = np.array(tid + [i for i in range(W.shape[0]) if i not in tid])
+    P = W.shape[0]
+    eng = _engine(population=P, group=P, n_head=1, eval_ep_num=E, gru=True, pomdp=True)
+    fit, steps, trace, actions = eng.rollout(0, 0.0, None, w_override=_cuda(W[perm]), init_states=_cuda(init), n_trace=len(tid))
+    assert (fit.cpu().numpy() == g["fitness"][perm]).mean() >= 0.999
+    trace = trace.cpu().numpy(); actions = actions.cpu().numpy()[:, :, 0]
+    for j in range(len(tid)):
+        ref = g["traces"][j]
+        n = int(np.isfinite(ref[:, 0]).sum())
+        assert np.array_equal(actions[j, :n], g["trace_actions"][j, :n])
+        assert np.abs(trace[j, :n] - ref[:n]).max() <= 1e-9
+
+
+# ------------------------------------------------------------------------------------- K1: simple_spread (BASELINE config 4)
+@pytest.mark.parametrize("N,E,init_mode", [(2, 5, "shared"), (3, 5, "shared"), (2, 4, "fresh"), (3, 2, "fresh")])
+def test_rollout_spread_philox_bit_exact(twin, N, E, init_mode):
+    P = 1500
+    Dn = 6 * N * 32 + 32 + 5 * 32 + 5
+    eng = _engine(env_name="simple_spread", obs_dim=6 * N, act_dim=5, n_agents=N, max_step="None", population=P, group=P,
+                  n_head=1, eval_ep_num=E, seed=19, init_mode=init_mode)
+    assert eng.D == Dn
+    rng = np.random.default_rng(3)
+    mu = rng.normal(0, 0.5, (1, Dn)).astype(np.float32)
+    fit, steps = eng.rollout(6, 0.8, _cuda(mu))
+    tf, ts = twin.population_mpe(mu, N=N, sigma=0.8, seed=19, gen=6, group=P, n_head=1, n=P, E=E,
+                                 init_mode=0 if init_mode == "shared" else 1)
+    assert np.array_equal(steps.cpu().numpy(), ts) and np.all(ts == 25 * E)
+    assert np.array_equal(fit.cpu().numpy(), tf)            # float64 returns under the contract: bit-exact
+
+
+@pytest.mark.parametrize("name", ["rollout_spread_n2", "rollout_spread_n3"])
+def test_rollout_spread_verification_mode_matches_reference(twin, golden, name):
+    """Golden = reference RolloutWorker + GymEnvModel copies per agent over the float64 numpy restatement of
+    simple_spread.  Returns must agree to rtol 1e-4 (north_star); they agree to ~1e-15 (the reference keeps one
+    running sum over all episodes, the engine sums per episode first)."""
+    g = golden(name)
+    W, init, N, E = g["W"], g["init"], int(g["N"]), int(g["E"])
+    P = W.shape[0]
+    eng = _engine(env_name="simple_spread", obs_dim=6 * N, act_dim=5, n_agents=N, max_step="None", population=P, group=P,
+                  n_head=1, eval_ep_num=E)
+    nt = g["traces"].shape[0]
+    fit, steps, trace, actions = eng.rollout(0, 0.0, None, w_override=_cuda(W), init_states=_cuda(init), n_trace=nt)
+    np.testing.assert_allclose(fit.cpu().numpy(), g["fitness"], rtol=1e-12)
+    trace = trace.cpu().numpy(); actions = actions.cpu().numpy()
+    assert np.array_equal(actions[:, :25], g["trace_actions"])
+    assert np.abs(trace[:, :25] - g["traces"]).max() <= 1e-9
