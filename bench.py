@@ -183,7 +183,7 @@ def run_reference(args):
 def workload_config(args, world):
     return {"workload": "CartPole-v1 MLP(4-32-2, D=226) openai_es pop=%d eval_ep_num=%d max_step=500 "
                         "(BASELINE configs[2]; conf/cartpole_openai.yaml)" % (args.pop, E_DEFAULT),
-            "population": args.pop, "eval_ep_num": E_DEFAULT, "strategy": STRATEGY, "parallelism": "pop-shard x%d" % world,
+            "population": args.pop, "eval_ep_num": E_DEFAULT, "strategy": STRATEGY, "parallelism": "pop-shard x%d" % world, "fitness_exchange": (args.exchange if world > 1 else "local"),
             "init_states": "shared [E] table (reference mp.Pool semantics)",
             "l2": "flushed between timed generations (256 MiB write); the hot path itself reads 904 B of parameters per generation"}
 
@@ -203,7 +203,8 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     config = {"env": {"name": "CartPole-v1", "max_step": 500, "pomdp": False},
               "network": {"name": "gym_model", "num_state": 4, "num_action": 2, "discrete_action": True, "gru": False},
-              "strategy": dict(STRATEGY, offspring_num=args.pop), "engine": {"name": "b200"}}
+              "strategy": dict(STRATEGY, offspring_num=args.pop),
+              "engine": {"name": "b200", "fitness_exchange": args.exchange}}
     loop = B200Loop(config, args.steps + args.warmup, 1, E_DEFAULT, log=False, save_model_period=0, seed=0, device=local, quiet=True)
     s = loop.strategy
     eng = s.engine
@@ -231,9 +232,13 @@ def run_b200(args):
         ev[k][0].record()
         # one generation, with an extra event after K1 so that the dominant kernel is timed alone
         e = s.engine
+        s.fitness = s._fit[s.generation & 1]
         e.rollout(s.generation, s.sigma, s.parents, fitness=s.fitness, steps=s.steps)
         ev[k][1].record()
-        sdist.exchange_fitness(s.fitness, s.lo, s.hi)
+        if s.exchange == "peer":
+            e.peer_barrier()
+        elif s.exchange == "nccl":
+            sdist.exchange_fitness(s.fitness, s.lo, s.hi)
         s.total_env_steps += s.steps[s.lo:s.hi].sum()
         e.rank_desc(s.fitness, shaped=True, order=s.order, shaped_out=s.shaped)
         s.t += 1
@@ -286,6 +291,10 @@ def run_b200(args):
                "generations_per_sec": args.steps / dt}
         eng2.close()
 
+    if world > 1:
+        s.engine.peer_check() if s.exchange == "peer" else None
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return 0
     peak_tf = measure_fp32_peak(local)
@@ -335,6 +344,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pop", type=int, default=P_DEFAULT)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--exchange", default=os.environ.get("SES_FITNESS_EXCHANGE", "peer"), choices=["peer", "nccl"],
+                    help="N > 1: fitness exchange fused into K1 over NVLink peer memory (default) or an NCCL all-gather")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -117,6 +117,20 @@ int ses_update_elite_mean(ses_handle *h, uint32_t generation, float sigma, const
                           const float *w_override_dev, const int32_t *order_dev, int32_t k, float *mu_out_dev,
                           void *stream);
 
+/* Multi-GPU fitness exchange fused into K1 (replaces the result half of Pool.map, loop.py:74: floats coming
+ * back from the workers).  Each handle owns an exchange buffer ([2][P] f64, double buffered by generation
+ * parity, + flags) allocated with cudaMalloc.  ses_peer_export writes its 64-byte CUDA IPC handle; after the
+ * ranks have exchanged those (any host channel), ses_peer_attach maps every peer's buffer over NVLink.  From
+ * then on a ses_rollout whose fitness_dev is ses_peer_fitness_ptr(parity) also stores each fitness value
+ * straight into every peer's buffer from inside the kernel, and ses_peer_barrier (a flag barrier over peer
+ * memory, stream ordered) makes the full vector visible on every rank -- no collective moves data.
+ * ses_peer_check reports a barrier that timed out (a dead peer). */
+int ses_peer_export(ses_handle *h, void *ipc_handle_out /* 64 bytes */);
+int ses_peer_attach(ses_handle *h, const void *ipc_handles /* [world][64] */, int32_t rank, int32_t world);
+int ses_peer_fitness_ptr(ses_handle *h, int32_t parity, double **out);
+int ses_peer_barrier(ses_handle *h, void *stream);
+int ses_peer_check(ses_handle *h);
+
 /* Whole generation with HOST buffers (the e2e path of bench.py): H2D of the strategy state,
  * K1+K2+K3 for openai_es, D2H of fitness [P] and the updated state; synchronises `stream`.
  * Requires a single-slice handle (id_begin = 0, id_end = P). */

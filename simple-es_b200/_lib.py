@@ -35,6 +35,11 @@ SYMBOLS = {
     "ses_materialize": (C.c_int, [_vp, _u32, _f32, _vp, _vp, _vp, _i32, _vp, _vp]),
     "ses_update_elite_mean": (C.c_int, [_vp, _u32, _f32, _vp, _vp, _vp, _i32, _vp, _vp]),
     "ses_generation_openai_host": (C.c_int, [_vp, _u32, _f32, _f64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ses_peer_export": (C.c_int, [_vp, _vp]),
+    "ses_peer_attach": (C.c_int, [_vp, _vp, _i32, _i32]),
+    "ses_peer_fitness_ptr": (C.c_int, [_vp, _i32, C.POINTER(_vp)]),
+    "ses_peer_barrier": (C.c_int, [_vp, _vp]),
+    "ses_peer_check": (C.c_int, [_vp]),
     "ses_test_math": (C.c_int, [_i32, _vp, _vp, _i64, _vp]),
     "ses_test_normals": (C.c_int, [_vp, _u32, _i32, _vp, _vp]),
     "ses_test_tanh_fast_exhaustive": (C.c_int, [_f32, _f32, C.POINTER(C.c_uint64)]),

@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_rollout_cartpole_gru(const Rollo
         }
         if (lane == 0) {
             p.steps[id] = total_steps;
-            p.fitness[id] = __ddiv_rn((double)total_steps, (double)p.E);
+            publish_fitness(p, id, __ddiv_rn((double)total_steps, (double)p.E));
         }
     }
 }

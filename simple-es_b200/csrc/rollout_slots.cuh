@@ -33,6 +33,8 @@
 
 namespace ses {
 
+constexpr int MAX_PEERS = 8;     // ranks of one NVSwitch box
+
 struct RolloutParams {
     const float *parents;        // [n_parents][D]
     const float *w_override;     // optional [n_local][D]
@@ -55,9 +57,24 @@ struct RolloutParams {
     int slots_cap;               // <= S: slots a warp may hold
     int lanes_used;              // lanes of a warp that take episodes (E*floor(32/E) by default)
     int n_agents;                // simple_spread only
+    int n_peers;                 // fused fitness exchange: other ranks' exchange buffers (NVLink peer memory)
+    double *peer_fitness[MAX_PEERS];
 };
 
 constexpr int MAX_E = 32;
+
+// Fitness all-gather fused into the rollout: the lane that retires an offspring stores its fitness into the
+// exchange buffer of every peer GPU (plain st.global on NVLink-mapped peer pointers), so no collective has
+// to move the vector afterwards; ses_peer_barrier() publishes the stores.
+__device__ __forceinline__ void publish_fitness(const RolloutParams &p, int id, double f)
+{
+    p.fitness[id] = f;
+    if (p.n_peers > 0) {
+#pragma unroll 1
+        for (int r = 0; r < p.n_peers; ++r) p.peer_fitness[r][id] = f;
+        __threadfence_system();
+    }
+}
 
 template <class Env, int S, bool NeedRet>
 struct __align__(16) SlotSmem;
@@ -120,7 +137,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_rollout_slots(const RolloutParam
                         total = 0.0;
                         for (int e = 0; e < p.E; ++e) total = __dadd_rn(total, sm.ret[lane][e]);
                     }
-                    p.fitness[my_id] = __ddiv_rn(total, (double)p.E);   // loop.py:124
+                    publish_fitness(p, my_id, __ddiv_rn(total, (double)p.E));   // loop.py:124
                     sm.off_id[lane] = -1;
                     my_id = -1;
                 }

@@ -67,6 +67,12 @@ struct ses_handle {
     long long *h_steps = nullptr;
     int *h_order = nullptr;
     unsigned long long *h_total = nullptr;
+    // peer (NVLink P2P) fitness exchange: [2][P] doubles (double buffered by generation parity) + flags
+    double *xbuf = nullptr;
+    double *peer_x[MAX_PEERS] = {nullptr};
+    int peer_rank = 0, peer_world = 0;
+    unsigned long long peer_epoch = 0;
+    int *peer_error = nullptr;
     // rollout launch configuration
     int lanes_used_override = 0;
     int ctas_per_sm = 0;
@@ -147,6 +153,9 @@ extern "C" int ses_destroy(ses_handle *h)
     cudaFree(h->keys[0]); cudaFree(h->keys[1]);
     cudaFree(h->vals_scratch); cudaFree(h->hist); cudaFree(h->tot);
     cudaFree(h->part0); cudaFree(h->part1);
+    for (int r = 0; r < h->peer_world; ++r)
+        if (r != h->peer_rank && h->peer_x[r]) cudaIpcCloseMemHandle(h->peer_x[r]);
+    cudaFree(h->xbuf); cudaFree(h->peer_error);
     cudaFree(h->h_parents); cudaFree(h->h_m); cudaFree(h->h_v);
     cudaFree(h->h_fitness); cudaFree(h->h_shaped); cudaFree(h->h_steps); cudaFree(h->h_order); cudaFree(h->h_total);
     delete h;
@@ -207,6 +216,15 @@ extern "C" int ses_rollout(ses_handle *h, uint32_t generation, float sigma, cons
     rp.id_begin = c.id_begin; rp.id_end = c.id_end;
     rp.E = c.eval_ep_num; rp.max_step = h->eff_max_step; rp.pomdp = c.pomdp; rp.init_mode = c.init_mode;
     rp.n_trace = n_trace; rp.slots_cap = 0; rp.lanes_used = 32; rp.n_agents = c.n_agents;
+    rp.n_peers = 0;
+    for (int r = 0; r < MAX_PEERS; ++r) rp.peer_fitness[r] = nullptr;
+    if (h->peer_world > 1 && h->xbuf) {
+        // fused exchange only when the caller rolls out into one of the two exchange buffers
+        for (int parity = 0; parity < 2; ++parity)
+            if (fitness_dev == h->xbuf + (size_t)parity * c.population)
+                for (int r = 0; r < h->peer_world; ++r)
+                    if (r != h->peer_rank) rp.peer_fitness[rp.n_peers++] = h->peer_x[r] + (size_t)parity * c.population;
+    }
 
     // lanes of a warp that take episodes: a multiple of E so that slots start and finish together
     rp.lanes_used = c.eval_ep_num >= 32 ? 32 : c.eval_ep_num * (32 / c.eval_ep_num);
@@ -225,6 +243,99 @@ extern "C" int ses_rollout(ses_handle *h, uint32_t generation, float sigma, cons
     if (c.env == SES_ENV_CARTPOLE && c.gru) return launch_rollout_cartpole_gru(h->num_sms, h->ctas_per_sm, rp, tr, st, &h->launches, g_err, sizeof(g_err));
     if (c.n_agents == 2) return launch_slots<SpreadEnv<2>, 8>(h, rp, need_warps, tr, st);
     return launch_slots<SpreadEnv<3>, 8>(h, rp, need_warps, tr, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// peer fitness exchange (multi-GPU): IPC-mapped exchange buffers + a flag barrier over NVLink
+// ------------------------------------------------------------------------------------------------
+static size_t xbuf_doubles(const ses_handle *h) { return 2 * (size_t)h->cfg.population + 2 * MAX_PEERS; }
+static unsigned long long *xbuf_flags(double *base, const ses_handle *h) { return reinterpret_cast<unsigned long long *>(base + 2 * (size_t)h->cfg.population); }
+
+extern "C" int ses_peer_export(ses_handle *h, void *ipc_handle_out)
+{
+    if (!h || !ipc_handle_out) return fail("ses_peer_export: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CU(cudaSetDevice(h->cfg.device));
+    if (!h->xbuf) {
+        CU(cudaMalloc(&h->xbuf, sizeof(double) * xbuf_doubles(h)));
+        CU(cudaMemset(h->xbuf, 0, sizeof(double) * xbuf_doubles(h)));
+        CU(cudaMalloc(&h->peer_error, sizeof(int)));
+        CU(cudaMemset(h->peer_error, 0, sizeof(int)));
+        CU(cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t mh;
+    CU(cudaIpcGetMemHandle(&mh, h->xbuf));
+    memcpy(ipc_handle_out, &mh, sizeof(mh));
+    return 0;
+}
+
+extern "C" int ses_peer_attach(ses_handle *h, const void *ipc_handles, int32_t rank, int32_t world)
+{
+    if (!h || !ipc_handles) return fail("ses_peer_attach: null argument");
+    if (world < 2 || world > MAX_PEERS || rank < 0 || rank >= world) return fail("ses_peer_attach: bad rank/world %d/%d (max %d ranks)", rank, world, MAX_PEERS);
+    if (!h->xbuf) return fail("ses_peer_attach: call ses_peer_export first");
+    CU(cudaSetDevice(h->cfg.device));
+    const cudaIpcMemHandle_t *mh = static_cast<const cudaIpcMemHandle_t *>(ipc_handles);
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { h->peer_x[r] = h->xbuf; continue; }
+        void *ptr = nullptr;
+        CU(cudaIpcOpenMemHandle(&ptr, mh[r], cudaIpcMemLazyEnablePeerAccess));
+        h->peer_x[r] = static_cast<double *>(ptr);
+    }
+    h->peer_rank = rank;
+    h->peer_world = world;
+    h->peer_epoch = 0;
+    return 0;
+}
+
+extern "C" int ses_peer_fitness_ptr(ses_handle *h, int32_t parity, double **out)
+{
+    if (!h || !out || !h->xbuf) return fail("ses_peer_fitness_ptr: exchange buffer not allocated");
+    *out = h->xbuf + (size_t)(parity & 1) * h->cfg.population;
+    return 0;
+}
+
+// one CTA, thread r <-> peer r: raise my flag in r's buffer, then wait for r's flag in mine
+__global__ void k_peer_barrier(unsigned long long *my_flags, unsigned long long *p0,
+                               unsigned long long *p1, unsigned long long *p2, unsigned long long *p3, unsigned long long *p4,
+                               unsigned long long *p5, unsigned long long *p6, unsigned long long *p7, int rank, int world,
+                               unsigned long long epoch, int *error)
+{
+    unsigned long long *peers[MAX_PEERS] = {p0, p1, p2, p3, p4, p5, p6, p7};
+    const int r = threadIdx.x;
+    if (r >= world || r == rank) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peers[r] + rank), "l"(epoch) : "memory");
+    unsigned long long seen = 0;
+    const long long t0 = clock64();
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(my_flags + r) : "memory");
+        if (seen >= epoch) break;
+        if (clock64() - t0 > 20000000000ll) { atomicExch(error, 1); break; }     // ~10 s: a peer died
+    }
+}
+
+extern "C" int ses_peer_barrier(ses_handle *h, void *stream)
+{
+    if (!h || h->peer_world < 2) return fail("ses_peer_barrier: peers not attached");
+    CU(cudaSetDevice(h->cfg.device));
+    h->peer_epoch += 1;
+    unsigned long long *f[MAX_PEERS] = {nullptr};
+    for (int r = 0; r < h->peer_world; ++r) f[r] = xbuf_flags(h->peer_x[r], h);
+    k_peer_barrier<<<1, 32, 0, S(stream)>>>(xbuf_flags(h->xbuf, h), f[0], f[1], f[2], f[3], f[4], f[5], f[6], f[7], h->peer_rank,
+                                            h->peer_world, h->peer_epoch, h->peer_error);
+    h->launches += 1;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ses_peer_check(ses_handle *h)
+{
+    if (!h || !h->peer_error) return 0;
+    int e = 0;
+    CU(cudaMemcpy(&e, h->peer_error, sizeof(int), cudaMemcpyDeviceToHost));
+    if (e) return fail("ses_peer_barrier timed out waiting for a peer GPU");
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------

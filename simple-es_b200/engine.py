@@ -50,6 +50,13 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
+class _DeviceArray:
+    """Wraps library-owned device memory for torch.as_tensor (CUDA array interface, no copy)."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
 class RolloutEngine:
     """One engine instance == one ses_handle == one GPU's slice of the population."""
 
@@ -195,6 +202,30 @@ class RolloutEngine:
         _lib.check(self.lib.ses_update_elite_mean(self._h, int(generation), float(sigma), _ptr(parents),
                                                   _ptr(w_override), _ptr(order), int(k), _ptr(out), self._stream()))
         return out
+
+    # ------------------------------------------------------------------------------ peer fitness exchange
+    def peer_setup(self, rank, world, all_gather_bytes):
+        """Map every rank's exchange buffer over NVLink.  `all_gather_bytes(b) -> [bytes per rank]` is any host
+        channel (torch.distributed.all_gather_object).  Returns the two [P] float64 exchange tensors (double
+        buffered by generation parity) that rollout() must be given as `fitness`."""
+        mine = C.create_string_buffer(64)
+        _lib.check(self.lib.ses_peer_export(self._h, mine))
+        handles = all_gather_bytes(mine.raw)
+        assert len(handles) == world and all(len(b) == 64 for b in handles)
+        blob = C.create_string_buffer(b"".join(handles), 64 * world)
+        _lib.check(self.lib.ses_peer_attach(self._h, blob, int(rank), int(world)))
+        bufs = []
+        for parity in (0, 1):
+            ptr = C.c_void_p()
+            _lib.check(self.lib.ses_peer_fitness_ptr(self._h, parity, C.byref(ptr)))
+            bufs.append(torch.as_tensor(_DeviceArray(ptr.value, self.P, "<f8"), device=self.device))
+        return bufs
+
+    def peer_barrier(self):
+        _lib.check(self.lib.ses_peer_barrier(self._h, self._stream()))
+
+    def peer_check(self):
+        _lib.check(self.lib.ses_peer_check(self._h))
 
     # ------------------------------------------------------------------------------ host-buffer generation
     def generation_openai_host(self, generation, sigma, lr, t, mu, m, v, fitness):

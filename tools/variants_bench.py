@@ -1,0 +1,57 @@
+#!/usr/bin/env python
+"""K1 throughput of the non-headline BASELINE configs: CartPole POMDP + GRU (P = 4097) and simple_spread
+(P = 16384, N = 2 / 3), plus the 2^20 CartPole genetic population.  Prints one JSON line per case."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from simple_es_b200.engine import RolloutEngine  # noqa: E402
+
+
+def timed(eng, gen0, sigma, parents, reps=3):
+    P = eng.P
+    fit = torch.zeros(P, dtype=torch.float64, device="cuda"); steps = torch.zeros(P, dtype=torch.int64, device="cuda")
+    eng.rollout(gen0, sigma, parents, fitness=fit, steps=steps)
+    torch.cuda.synchronize()
+    best = None
+    for r in range(reps):
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); eng.rollout(gen0 + 1 + r, sigma, parents, fitness=fit, steps=steps); e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1); n = int(steps.sum().item())
+        if best is None or ms < best[0]:
+            best = (ms, n, float(fit.max().item()), float(fit.mean().item()))
+    return {"ms": best[0], "env_steps": best[1], "steps_per_s": best[1] / (best[0] * 1e-3), "best": best[2], "mean": best[3]}
+
+
+def main():
+    out = {}
+    rng = np.random.default_rng(0)
+    # config 2: CartPole POMDP GRU, simple_evolution, P = 4097
+    for label, scale, sigma in (("gru_gen0", 0.0, 1.0), ("gru_random_parent", 0.3, 0.2)):
+        eng = RolloutEngine("CartPole-v1", 4, 2, True, True, 500, 5, 4097, 4097, 2, 1, seed=0)
+        mu = torch.from_numpy((rng.normal(0, 1, (1, 6562)) * scale).astype(np.float32)).cuda()
+        out[label] = timed(eng, 0, sigma, mu)
+        eng.close()
+    # config 4: simple_spread openai_es P = 16384
+    for N in (2, 3):
+        D = 6 * N * 32 + 32 + 165
+        eng = RolloutEngine("simple_spread", 6 * N, 5, False, False, "None", 5, 16384, 16384, 1, 1, seed=0, n_agents=N, init_mode="fresh")
+        mu = torch.zeros(1, D, dtype=torch.float32, device="cuda")
+        out["spread_n%d" % N] = timed(eng, 0, 0.2, mu)
+        eng.close()
+    # config 5: CartPole simple_genetic P = 2^20 (16 elites), gen-0 regime
+    eng = RolloutEngine("CartPole-v1", 4, 2, False, False, 500, 5, 1 << 20, (1 << 20) // 16, 1, 16, seed=0)
+    par = torch.zeros(16, 226, dtype=torch.float32, device="cuda")
+    out["genetic_2^20_gen0"] = timed(eng, 0, 1.0, par, reps=2)
+    eng.close()
+    for k, v in out.items():
+        print(json.dumps({k: v}))
+
+
+if __name__ == "__main__":
+    main()
