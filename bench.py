@@ -226,7 +226,6 @@ def run_b200(args):
         sampler.start()
     barrier()
     wall0 = time.perf_counter()
-    rollout_steps = []
     for k in range(args.steps):
         flush.fill_(k & 0xFF)                      # L2 flush, outside the timed events
         ev[k][0].record()
@@ -239,20 +238,18 @@ def run_b200(args):
             e.peer_barrier()
         elif s.exchange == "nccl":
             sdist.exchange_fitness(s.fitness, s.lo, s.hi)
-        s.total_env_steps += s.steps[s.lo:s.hi].sum()
         e.rank_desc(s.fitness, shaped=True, order=s.order, shaped_out=s.shaped)
         s.t += 1
         e.update_openai(s.generation, s.sigma, s.lr, s.t, s.shaped, s.parents.view(-1), s.m, s.v)
         s.sigma *= s.decay; s.curr_sigma = s.sigma; s.generation += 1
         ev[k][2].record()
-        rollout_steps.append(s.steps[s.lo:s.hi].sum())
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop() if rank == 0 else None
     gen_ms = sum(ev[k][0].elapsed_time(ev[k][2]) for k in range(args.steps))
     k1_ms = sum(ev[k][0].elapsed_time(ev[k][1]) for k in range(args.steps))
     local_steps = int(s.total_env_steps.item()) - steps_before
-    k1_local_steps = int(sum(int(x.item()) for x in rollout_steps))
+    k1_local_steps = local_steps
     best = float(s.best_reward().item())
     launches = eng.launches - launches_before
     t = torch.tensor([gen_ms, k1_ms], dtype=torch.float64, device=dev)

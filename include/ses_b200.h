@@ -150,6 +150,9 @@ int ses_test_tanh_fast_exhaustive(float lo, float hi, uint64_t *mismatches_host)
  * microbenchmark -- the denominator of the rollout kernel's roofline in bench.py. */
 int ses_measure_fp32_peak(int32_t device, double *tflops_out);
 
+/* Optional device counter (uint64): every ses_rollout adds the env steps it simulated (bench.py's numerator). */
+int ses_set_step_counter(ses_handle *h, uint64_t *counter_dev);
+
 /* Number of kernels this library has launched on behalf of the handle (bench.py "gpu_launches"). */
 int64_t ses_launch_count(ses_handle *h);
 

@@ -49,10 +49,14 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(const unsigned long 
     h[threadIdx.x] = 0;
     __syncthreads();
     const int base = blockIdx.x * SORT_TILE;
+    const int lane = threadIdx.x & 31;
 #pragma unroll 4
     for (int it = 0; it < SORT_ITEMS; ++it) {
         const int p = base + it * SORT_THREADS + threadIdx.x;
-        if (p < n) atomicAdd(&h[(int)((keys[p] >> shift) & 255ull)], 1);
+        // warp-aggregated: a converged CartPole population puts every key in one bin
+        const int d = p < n ? (int)((keys[p] >> shift) & 255ull) : 256 + lane;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        if (p < n && lane == __ffs(peers) - 1) atomicAdd(&h[d], __popc(peers));
     }
     __syncthreads();
     const int c = h[threadIdx.x];

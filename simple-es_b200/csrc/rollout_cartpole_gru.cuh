@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_rollout_cartpole_gru(const Rollo
     const unsigned FULL = 0xffffffffu;
     float *smallf = reinterpret_cast<float *>(sm.small);
 
+    unsigned long long warp_steps = 0;
     for (;;) {
         // ---------------------------------------------------------------- next offspring
         int id = 0;
@@ -185,11 +186,13 @@ __global__ void __launch_bounds__(WARPS * 32) k_rollout_cartpole_gru(const Rollo
             for (int o = 16; o; o >>= 1) n += __shfl_xor_sync(FULL, n, o);
             total_steps += n;
         }
+        warp_steps += (unsigned long long)total_steps;
         if (lane == 0) {
             p.steps[id] = total_steps;
             publish_fitness(p, id, __ddiv_rn((double)total_steps, (double)p.E));
         }
     }
+    if (p.total_steps && lane == 0 && warp_steps) atomicAdd(p.total_steps, warp_steps);
 }
 
 template <int EC>

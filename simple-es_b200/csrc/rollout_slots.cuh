@@ -44,6 +44,7 @@ struct RolloutParams {
     double *trace;               // optional [n_trace][200][state_dim]
     int *trace_actions;          // optional [n_trace][200][n_agents]
     int *work_counter;           // zeroed before launch
+    unsigned long long *total_steps;   // optional: += env steps simulated by this launch
     float sigma;
     uint32_t seed;
     uint32_t gen;
@@ -117,6 +118,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_rollout_slots(const RolloutParam
     int slot = -1, nstep = 0;
     [[maybe_unused]] int ep = 0;
     typename Env::State st;
+    unsigned long long warp_steps = 0;   // lanes < S: steps of the offspring they retired
     bool more = true;          // warp-uniform: the global offspring queue may still hold work
     bool sched = true;         // warp-uniform: something changed that the scheduler must look at
 
@@ -130,6 +132,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_rollout_slots(const RolloutParam
                 if (my_id >= 0 && sm.ep_done[lane] == p.E) {       // offspring finished: emit fitness
                     const int stp = sm.steps[lane];
                     p.steps[my_id] = (long long)stp;
+                    warp_steps += (unsigned long long)stp;
                     double total;
                     if constexpr (Env::UNIT_REWARD) {
                         total = (double)stp;                        // reward 1.0 per step
@@ -237,6 +240,11 @@ __global__ void __launch_bounds__(WARPS * 32) k_rollout_slots(const RolloutParam
         // the scheduler has work only right after an episode ended (a lane to re-arm, maybe a slot
         // to retire and refill); otherwise idle lanes stay idle and the warp keeps stepping
         sched = __ballot_sync(FULL, just_done) != 0;
+    }
+    if (p.total_steps) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) warp_steps += __shfl_xor_sync(FULL, warp_steps, o);
+        if (lane == 0 && warp_steps) atomicAdd(p.total_steps, warp_steps);
     }
 }
 

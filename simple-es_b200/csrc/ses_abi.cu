@@ -59,7 +59,7 @@ struct ses_handle {
     int *vals_scratch = nullptr;
     int *hist = nullptr;
     int *tot = nullptr;            // [8][256]
-    double *part0 = nullptr, *part1 = nullptr;
+    double *part1 = nullptr;
     int nb0 = 0, nb1 = 0, n_tiles = 0;
     // scratch for the host-buffer generation path
     float *h_parents = nullptr, *h_m = nullptr, *h_v = nullptr;
@@ -73,6 +73,7 @@ struct ses_handle {
     int peer_rank = 0, peer_world = 0;
     unsigned long long peer_epoch = 0;
     int *peer_error = nullptr;
+    unsigned long long *step_counter = nullptr;   // caller-owned, optional (ses_set_step_counter)
     // rollout launch configuration
     int lanes_used_override = 0;
     int ctas_per_sm = 0;
@@ -139,7 +140,6 @@ extern "C" int ses_create(const ses_config *cfg, ses_handle **out)
     CU(cudaMalloc(&h->vals_scratch, sizeof(int) * P));
     CU(cudaMalloc(&h->hist, sizeof(int) * h->n_tiles * 256));
     CU(cudaMalloc(&h->tot, sizeof(int) * 8 * 256));
-    CU(cudaMalloc(&h->part0, sizeof(double) * (size_t)h->nb0 * h->DP));
     CU(cudaMalloc(&h->part1, sizeof(double) * (size_t)h->nb1 * h->DP));
     *out = h;
     return 0;
@@ -152,7 +152,7 @@ extern "C" int ses_destroy(ses_handle *h)
     cudaFree(h->work_counter);
     cudaFree(h->keys[0]); cudaFree(h->keys[1]);
     cudaFree(h->vals_scratch); cudaFree(h->hist); cudaFree(h->tot);
-    cudaFree(h->part0); cudaFree(h->part1);
+    cudaFree(h->part1);
     for (int r = 0; r < h->peer_world; ++r)
         if (r != h->peer_rank && h->peer_x[r]) cudaIpcCloseMemHandle(h->peer_x[r]);
     cudaFree(h->xbuf); cudaFree(h->peer_error);
@@ -163,6 +163,13 @@ extern "C" int ses_destroy(ses_handle *h)
 }
 
 extern "C" int64_t ses_launch_count(ses_handle *h) { return h ? h->launches : 0; }
+
+extern "C" int ses_set_step_counter(ses_handle *h, uint64_t *counter_dev)
+{
+    if (!h) return fail("ses_set_step_counter: null handle");
+    h->step_counter = reinterpret_cast<unsigned long long *>(counter_dev);
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------------------
 // K1
@@ -216,6 +223,7 @@ extern "C" int ses_rollout(ses_handle *h, uint32_t generation, float sigma, cons
     rp.id_begin = c.id_begin; rp.id_end = c.id_end;
     rp.E = c.eval_ep_num; rp.max_step = h->eff_max_step; rp.pomdp = c.pomdp; rp.init_mode = c.init_mode;
     rp.n_trace = n_trace; rp.slots_cap = 0; rp.lanes_used = 32; rp.n_agents = c.n_agents;
+    rp.total_steps = h->step_counter;
     rp.n_peers = 0;
     for (int r = 0; r < MAX_PEERS; ++r) rp.peer_fitness[r] = nullptr;
     if (h->peer_world > 1 && h->xbuf) {
@@ -248,7 +256,8 @@ extern "C" int ses_rollout(ses_handle *h, uint32_t generation, float sigma, cons
 // ------------------------------------------------------------------------------------------------
 // peer fitness exchange (multi-GPU): IPC-mapped exchange buffers + a flag barrier over NVLink
 // ------------------------------------------------------------------------------------------------
-static size_t xbuf_doubles(const ses_handle *h) { return 2 * (size_t)h->cfg.population + 2 * MAX_PEERS; }
+static size_t xbuf_doubles(const ses_handle *h) { return 2 * (size_t)h->cfg.population + 2 * MAX_PEERS + (size_t)h->nb1 * h->DP; }
+static double *xbuf_part1(double *base, const ses_handle *h) { return base + 2 * (size_t)h->cfg.population + 2 * MAX_PEERS; }
 static unsigned long long *xbuf_flags(double *base, const ses_handle *h) { return reinterpret_cast<unsigned long long *>(base + 2 * (size_t)h->cfg.population); }
 
 extern "C" int ses_peer_export(ses_handle *h, void *ipc_handle_out)
@@ -389,14 +398,31 @@ extern "C" int ses_update_openai(ses_handle *h, uint32_t generation, const doubl
     cudaStream_t st = S(stream);
     const int P = h->cfg.population;
     Layout lay{h->cfg.group, h->cfg.n_head};
-    const int t0 = h->nb0 * h->NQ;
-    k_grad_level0<<<(t0 + 255) / 256, 256, 0, st>>>(shaped_dev, P, h->D, h->NQ, h->cfg.seed, generation, lay, eps_override_dev, h->part0, h->nb0);
-    const int t1 = h->nb1 * h->DP;
-    k_grad_level1<<<(t1 + 255) / 256, 256, 0, st>>>(h->part0, h->nb0, h->DP, h->part1, h->nb1);
-    k_grad_final_adam<<<(h->D + 255) / 256, 256, 0, st>>>(h->part1, h->nb1, h->DP, h->D, (float)update_factor, adam_a, (float)beta1,
+    // levels 0+1 of the gradient: all groups here, or -- with peers attached -- this rank's share of the groups,
+    // each row stored into every peer's table over NVLink, then the flag barrier
+    const bool shard = h->peer_world > 1 && h->xbuf && !eps_override_dev;
+    double *part1 = shard ? xbuf_part1(h->xbuf, h) : h->part1;
+    int g0 = 0, g1 = h->nb1;
+    PeerRows peers;
+    int n_peers = 0;
+    for (int r = 0; r < 8; ++r) peers.p[r] = nullptr;
+    if (shard) {
+        g0 = (int)((long long)h->peer_rank * h->nb1 / h->peer_world);
+        g1 = (int)((long long)(h->peer_rank + 1) * h->nb1 / h->peer_world);
+        for (int r = 0; r < h->peer_world; ++r)
+            if (r != h->peer_rank) peers.p[n_peers++] = xbuf_part1(h->peer_x[r], h);
+    }
+    const int n_chunks = (h->NQ + GQC - 1) / GQC;
+    if (g1 > g0) {
+        k_grad_partial<<<(g1 - g0) * n_chunks, GB1 * GQC, 0, st>>>(shaped_dev, P, h->D, h->NQ, h->cfg.seed, generation, lay, eps_override_dev,
+                                                                  part1, h->nb0, g0, n_chunks, n_peers, peers);
+        h->launches += 1;
+    }
+    if (shard && ses_peer_barrier(h, stream)) return -1;
+    k_grad_final_adam<<<(h->D + 255) / 256, 256, 0, st>>>(part1, h->nb1, h->DP, h->D, (float)update_factor, adam_a, (float)beta1,
                                                          (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)adam_eps,
                                                          mu_dev, m_dev, v_dev, grad_out_dev);
-    h->launches += 3;
+    h->launches += 1;
     CU(cudaGetLastError());
     return 0;
 }
@@ -436,14 +462,6 @@ extern "C" int ses_update_elite_mean(ses_handle *h, uint32_t generation, float s
 // ------------------------------------------------------------------------------------------------
 // whole openai_es generation with host buffers (bench.py e2e)
 // ------------------------------------------------------------------------------------------------
-__global__ void k_sum_steps(const long long *__restrict__ steps, int n, unsigned long long *__restrict__ total)
-{
-    long long s = 0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += steps[i];
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if ((threadIdx.x & 31) == 0 && s) atomicAdd(total, (unsigned long long)s);
-}
-
 extern "C" int ses_generation_openai_host(ses_handle *h, uint32_t generation, float sigma, double learning_rate,
                                           int64_t adam_t, float *mu_host, float *m_host, float *v_host,
                                           double *fitness_host, int64_t *total_steps_host, void *stream)
@@ -470,9 +488,13 @@ extern "C" int ses_generation_openai_host(ses_handle *h, uint32_t generation, fl
     CU(cudaMemcpyAsync(h->h_parents, mu_host, db, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(h->h_m, m_host, db, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(h->h_v, v_host, db, cudaMemcpyHostToDevice, st));
-    if (ses_rollout(h, generation, sigma, h->h_parents, nullptr, nullptr, h->h_fitness, reinterpret_cast<int64_t *>(h->h_steps), nullptr,
-                    nullptr, 0, stream))
-        return -1;
+    CU(cudaMemsetAsync(h->h_total, 0, sizeof(unsigned long long), st));
+    unsigned long long *saved_counter = h->step_counter;
+    h->step_counter = h->h_total;
+    const int rc_roll = ses_rollout(h, generation, sigma, h->h_parents, nullptr, nullptr, h->h_fitness, reinterpret_cast<int64_t *>(h->h_steps),
+                                    nullptr, nullptr, 0, stream);
+    h->step_counter = saved_counter;
+    if (rc_roll) return -1;
     int key_bits = 0;
     double key_scale = 1.0;
     if (c.env == SES_ENV_CARTPOLE) {          // fitness = steps / E with integer steps <= E * max_step
@@ -486,9 +508,6 @@ extern "C" int ses_generation_openai_host(ses_handle *h, uint32_t generation, fl
     const double uf = -(learning_rate / ((double)P * (double)sigma));
     if (ses_update_openai(h, generation, h->h_shaped, nullptr, uf, a, beta1, beta2, 1e-8, h->h_parents, h->h_m, h->h_v, nullptr, stream))
         return -1;
-    CU(cudaMemsetAsync(h->h_total, 0, sizeof(unsigned long long), st));
-    k_sum_steps<<<64, 256, 0, st>>>(h->h_steps, P, h->h_total);
-    h->launches += 1;
     CU(cudaMemcpyAsync(fitness_host, h->h_fitness, sizeof(double) * P, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(mu_host, h->h_parents, db, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(m_host, h->h_m, db, cudaMemcpyDeviceToHost, st));

@@ -17,50 +17,61 @@ namespace ses {
 constexpr int GB0 = 32;
 constexpr int GB1 = 64;
 
-// level 0: thread <-> (block b, quad q); grid covers nb0*NQ threads.  part0[b][4*NQ] float64.
-__global__ void __launch_bounds__(256) k_grad_level0(const double *__restrict__ shaped, int P, int D, int NQ, uint32_t seed,
-                                                     uint32_t gen, Layout layout, const float *__restrict__ eps_override,
-                                                     double *__restrict__ part0, int nb0)
-{
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nb0 * NQ) return;
-    const int b = t / NQ, q = t - b * NQ;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    const int j1 = min(P, (b + 1) * GB0);
-    for (int j = b * GB0; j < j1; ++j) {
-        float4 e;
-        if (eps_override) {
-            const float *row = eps_override + (size_t)j * D;
-            const int d = 4 * q;
-            e.x = d + 0 < D ? row[d + 0] : 0.0f;
-            e.y = d + 1 < D ? row[d + 1] : 0.0f;
-            e.z = d + 2 < D ? row[d + 2] : 0.0f;
-            e.w = d + 3 < D ? row[d + 3] : 0.0f;
-        } else {
-            if (!layout.perturbed(j)) continue;               // eps == 0 (offspring_strategies.py:302-308)
-            e = normal4(seed, (uint32_t)q, (uint32_t)j, gen);
-        }
-        const double f = shaped[j];
-        a0 = fma((double)e.x, f, a0);
-        a1 = fma((double)e.y, f, a1);
-        a2 = fma((double)e.z, f, a2);
-        a3 = fma((double)e.w, f, a3);
-    }
-    double *o = part0 + ((size_t)b * NQ + q) * 4;
-    o[0] = a0; o[1] = a1; o[2] = a2; o[3] = a3;
-}
+struct PeerRows { double *p[8]; };
 
-// level 1: thread <-> (group g, padded parameter d)
-__global__ void __launch_bounds__(256) k_grad_level1(const double *__restrict__ part0, int nb0, int DP, double *__restrict__ part1,
-                                                     int nb1)
+constexpr int GQC = 4;     // quads per CTA of k_grad_partial (CTA = 64 blocks x 4 quads = 256 threads)
+
+// levels 0 and 1 fused: CTA <-> (group g, chunk of GQC quads); thread <-> (block b of the group, quad q).
+// Level 0 runs in registers (32 sequential fma per parameter), the 64 block partials of the group meet in
+// shared memory and are added sequentially in block order (level 1).  part1[g][DP] float64.
+// Groups [g_begin, g_end) only: with several ranks each computes its share of the groups and stores the rows
+// into every peer's part1 buffer over NVLink (peer_part1), so that all ranks finish with the same table.
+__global__ void __launch_bounds__(GB1 * GQC) k_grad_partial(const double *__restrict__ shaped, int P, int D, int NQ, uint32_t seed,
+                                                            uint32_t gen, Layout layout, const float *__restrict__ eps_override,
+                                                            double *__restrict__ part1, int nb0, int g_begin, int n_chunks,
+                                                            int n_peers, PeerRows peers)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nb1 * DP) return;
-    const int g = t / DP, d = t - g * DP;
-    double s = 0.0;
-    const int b1 = min(nb0, (g + 1) * GB1);
-    for (int b = g * GB1; b < b1; ++b) s = __dadd_rn(s, part0[(size_t)b * DP + d]);
-    part1[(size_t)g * DP + d] = s;
+    __shared__ double sp[GB1][GQC * 4];
+    const int g = g_begin + blockIdx.x / n_chunks;
+    const int qc = blockIdx.x % n_chunks;
+    const int bb = threadIdx.x / GQC, qq = threadIdx.x % GQC;
+    const int b = g * GB1 + bb, q = qc * GQC + qq;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    if (b < nb0 && q < NQ) {
+        const int j1 = min(P, (b + 1) * GB0);
+        for (int j = b * GB0; j < j1; ++j) {
+            float4 e;
+            if (eps_override) {
+                const float *row = eps_override + (size_t)j * D;
+                const int d = 4 * q;
+                e.x = d + 0 < D ? row[d + 0] : 0.0f;
+                e.y = d + 1 < D ? row[d + 1] : 0.0f;
+                e.z = d + 2 < D ? row[d + 2] : 0.0f;
+                e.w = d + 3 < D ? row[d + 3] : 0.0f;
+            } else {
+                if (!layout.perturbed(j)) continue;           // eps == 0 (offspring_strategies.py:302-308)
+                e = normal4(seed, (uint32_t)q, (uint32_t)j, gen);
+            }
+            const double f = shaped[j];
+            a0 = fma((double)e.x, f, a0);
+            a1 = fma((double)e.y, f, a1);
+            a2 = fma((double)e.z, f, a2);
+            a3 = fma((double)e.w, f, a3);
+        }
+    }
+    sp[bb][qq * 4 + 0] = a0; sp[bb][qq * 4 + 1] = a1; sp[bb][qq * 4 + 2] = a2; sp[bb][qq * 4 + 3] = a3;
+    __syncthreads();
+    if (threadIdx.x < GQC * 4) {
+        const int d = qc * GQC * 4 + threadIdx.x;
+        if (d < NQ * 4) {
+            const int nb = min(GB1, nb0 - g * GB1);
+            double t = 0.0;
+            for (int k = 0; k < nb; ++k) t = __dadd_rn(t, sp[k][threadIdx.x]);
+            const size_t o = (size_t)g * (NQ * 4) + d;
+            part1[o] = t;
+            for (int r = 0; r < n_peers; ++r) peers.p[r][o] = t;
+        }
+    }
 }
 
 // level 2 + scale + Adam with the dtypes numpy>=2 gives the reference (m, v float32 with separately

@@ -128,6 +128,12 @@ class RolloutEngine:
     def launches(self):
         return int(self.lib.ses_launch_count(self._h))
 
+    def set_step_counter(self, counter):
+        """`counter`: 0-d / 1-element int64 CUDA tensor; every rollout() adds the env steps it simulated."""
+        self._chk(counter, torch.int64, 1, "counter")
+        self._step_counter = counter            # keep alive
+        _lib.check(self.lib.ses_set_step_counter(self._h, _ptr(counter)))
+
     # ------------------------------------------------------------------------------ K1
     def rollout(self, generation, sigma, parents, fitness=None, steps=None, w_override=None, init_states=None,
                 n_trace=0):

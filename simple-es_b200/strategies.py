@@ -54,7 +54,8 @@ class _Base:
         self.steps = torch.zeros(self.P, dtype=torch.int64, device=dev)
         self.order = torch.empty(self.P, dtype=torch.int32, device=dev)
         self.generation = 0
-        self.total_env_steps = torch.zeros((), dtype=torch.int64, device=dev)
+        self.total_env_steps = torch.zeros(1, dtype=torch.int64, device=dev)     # accumulated by K1 itself
+        self.engine.set_step_counter(self.total_env_steps)
 
     def _rollout_and_exchange(self):
         """K1 on this rank's slice, then the full fitness vector on every rank."""
@@ -65,7 +66,6 @@ class _Base:
             e.peer_barrier()
         elif self.exchange == "nccl":
             sdist.exchange_fitness(self.fitness, self.lo, self.hi)
-        self.total_env_steps += self.steps[self.lo:self.hi].sum()
 
     def _rollout_and_rank(self, shaped=False):
         self._rollout_and_exchange()
