@@ -15,10 +15,11 @@
 namespace ses {
 
 constexpr int SORT_THREADS = 256;
-constexpr int SORT_ITEMS = 16;                            // chunks of 32 per warp
-constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;      // 4096 keys per CTA
 constexpr int SORT_WARPS = SORT_THREADS / 32;
-constexpr int SORT_WSEG = 32 * SORT_ITEMS;                // 512 consecutive keys per warp
+// keys per thread: 4 (1024-key tiles, more CTAs in flight) up to 2^18 keys, 16 (4096-key tiles, fewer per-tile
+// histograms to walk) above
+constexpr int SORT_ITEMS_SMALL = 4, SORT_ITEMS_LARGE = 16;
+__host__ __device__ constexpr int sort_tile(int items) { return SORT_THREADS * items; }
 
 // position p holds offspring i = n-1-p; key ascends when fitness descends
 __global__ void k_sort_init(const double *__restrict__ fitness, int n, int key_bits, double key_scale,
@@ -42,15 +43,17 @@ __global__ void k_sort_init(const double *__restrict__ fitness, int n, int key_b
 }
 
 // per-CTA digit histogram -> hist[cta][256]; digit totals -> tot[256] (zeroed by the host)
+template <int SORT_ITEMS>
 __global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(const unsigned long long *__restrict__ keys, int n, int shift,
                                                             int *__restrict__ hist, int *__restrict__ tot)
 {
+    constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
     __shared__ int h[256];
     h[threadIdx.x] = 0;
     __syncthreads();
     const int base = blockIdx.x * SORT_TILE;
     const int lane = threadIdx.x & 31;
-#pragma unroll 4
+#pragma unroll
     for (int it = 0; it < SORT_ITEMS; ++it) {
         const int p = base + it * SORT_THREADS + threadIdx.x;
         // warp-aggregated: a converged CartPole population puts every key in one bin
@@ -64,14 +67,16 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(const unsigned long 
     if (c) atomicAdd(&tot[threadIdx.x], c);
 }
 
-// stable scatter of one tile: CTA c owns keys [c*4096, ...), warp w the 512 consecutive keys
-// [c*4096 + w*512, ...) in 16 chunks of 32 (so "earlier position" == lower (warp, chunk, lane)).
+// stable scatter of one tile: CTA c owns keys [c*TILE, ...), warp w the 32*ITEMS consecutive keys
+// [c*TILE + w*32*ITEMS, ...) in ITEMS chunks of 32 (so "earlier position" == lower (warp, chunk, lane)).
+template <int SORT_ITEMS>
 __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const unsigned long long *__restrict__ keys_in,
                                                                const int *__restrict__ vals_in, int n, int shift,
                                                                const int *__restrict__ hist, const int *__restrict__ tot,
                                                                unsigned long long *__restrict__ keys_out,
                                                                int *__restrict__ vals_out)
 {
+    constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS, SORT_WSEG = 32 * SORT_ITEMS;
     __shared__ int digit_base[256];
     __shared__ int whist[SORT_WARPS][256];
     __shared__ int scan_tmp[256];

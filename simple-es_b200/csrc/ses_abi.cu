@@ -131,7 +131,7 @@ extern "C" int ses_create(const ses_config *cfg, ses_handle **out)
     h->ctas_per_sm = env_int("SES_ROLLOUT_CTAS_PER_SM", 0);
 
     const int P = cfg->population;
-    h->n_tiles = (P + SORT_TILE - 1) / SORT_TILE;
+    h->n_tiles = (P + sort_tile(SORT_ITEMS_SMALL) - 1) / sort_tile(SORT_ITEMS_SMALL);
     h->nb0 = (P + GB0 - 1) / GB0;
     h->nb1 = (h->nb0 + GB1 - 1) / GB1;
     CU(cudaMalloc(&h->work_counter, sizeof(int)));
@@ -360,7 +360,9 @@ extern "C" int ses_rank_desc(ses_handle *h, const double *fitness_dev, int32_t n
     CU(cudaSetDevice(h->cfg.device));
     cudaStream_t st = S(stream);
     const int passes = key_bits == 0 ? 8 : (key_bits + 7) / 8;
-    const int tiles = (n + SORT_TILE - 1) / SORT_TILE;
+    const bool small = n <= (1 << 18);
+    const int tile = sort_tile(small ? SORT_ITEMS_SMALL : SORT_ITEMS_LARGE);
+    const int tiles = (n + tile - 1) / tile;
     // ping-pong so that the last pass lands in order_dev
     int *vals[2];
     vals[0] = (passes % 2 == 0) ? order_dev : h->vals_scratch;
@@ -370,8 +372,13 @@ extern "C" int ses_rank_desc(ses_handle *h, const double *fitness_dev, int32_t n
     h->launches += 1;
     for (int ps = 0; ps < passes; ++ps) {
         const int a = ps & 1, b = a ^ 1;
-        k_sort_hist<<<tiles, SORT_THREADS, 0, st>>>(h->keys[a], n, 8 * ps, h->hist, h->tot + 256 * ps);
-        k_sort_scatter<<<tiles, SORT_THREADS, 0, st>>>(h->keys[a], vals[a], n, 8 * ps, h->hist, h->tot + 256 * ps, h->keys[b], vals[b]);
+        if (small) {
+            k_sort_hist<SORT_ITEMS_SMALL><<<tiles, SORT_THREADS, 0, st>>>(h->keys[a], n, 8 * ps, h->hist, h->tot + 256 * ps);
+            k_sort_scatter<SORT_ITEMS_SMALL><<<tiles, SORT_THREADS, 0, st>>>(h->keys[a], vals[a], n, 8 * ps, h->hist, h->tot + 256 * ps, h->keys[b], vals[b]);
+        } else {
+            k_sort_hist<SORT_ITEMS_LARGE><<<tiles, SORT_THREADS, 0, st>>>(h->keys[a], n, 8 * ps, h->hist, h->tot + 256 * ps);
+            k_sort_scatter<SORT_ITEMS_LARGE><<<tiles, SORT_THREADS, 0, st>>>(h->keys[a], vals[a], n, 8 * ps, h->hist, h->tot + 256 * ps, h->keys[b], vals[b]);
+        }
         h->launches += 2;
     }
     if (shaped_dev) {
