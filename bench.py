@@ -130,7 +130,7 @@ def cpu_reference_generation(n_offspring, cores, gen_seed, eval_ep_num=E_DEFAULT
 
 def cpu_baseline_block(cores):
     """Bounded CPU baseline reported beside the GPU number (rank 0, N = 1)."""
-    n = max(64, min(4096, 48 * cores))
+    n = max(64, min(P_DEFAULT, 1536 * cores))          # ~10-20 s of CPU work on the box's cores
     steps, dt = cpu_reference_generation(n, cores, 12345)
     out = {"value": steps / dt, "unit": "env-steps/s", "cores": cores, "kind": "port",
            "sample": "1 generation of the reference CPU path (oracle/pyref.py port: torch-CPU policy, Python CartPole, "
@@ -157,7 +157,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    n = max(64, min(2048, 24 * cores))
+    n = max(64, min(4096, 64 * cores))
     for w in range(args.warmup):
         cpu_reference_generation(max(16, cores), cores, 100 + w)
     tot_steps, tot_t = 0, 0.0
