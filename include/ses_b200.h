@@ -143,6 +143,8 @@ int ses_generation_openai_host(ses_handle *h, uint32_t generation, float sigma, 
  *       5 sin64, 6 cos64 (in/out f64); 7 tanh32 with the division fast path written out (what K1 runs). */
 int ses_test_math(int32_t kind, const void *in_dev, void *out_dev, int64_t n, void *stream);
 int ses_test_normals(ses_handle *h, uint32_t generation, int32_t id, float *out_dev /* [D] */, void *stream);
+/* counts mismatches between K1's 3-instruction x/1.1 and IEEE division over n pseudo-random doubles */
+int ses_test_div_total_mass(uint64_t n, uint64_t *mismatches_host);
 /* counts float32 inputs x in [lo, hi] (and -x) for which K1's fast-path tanh differs from the contract's tanh32 */
 int ses_test_tanh_fast_exhaustive(float lo, float hi, uint64_t *mismatches_host);
 

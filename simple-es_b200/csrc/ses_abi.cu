@@ -656,3 +656,33 @@ extern "C" int ses_test_tanh_fast_exhaustive(float lo, float hi, uint64_t *misma
     *mismatches_host = r;
     return 0;
 }
+
+// div_total_mass(x) vs __ddiv_rn(x, 1.1) on n pseudo-random doubles (random sign, mantissa, exponent in [-60, 60])
+__global__ void k_div11_check(unsigned long long n, unsigned long long *mismatches)
+{
+    unsigned long long bad = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint4 r = philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), 0x51u, 0u, 0xC0FFEEu, 7u);
+        const unsigned long long mant = (((unsigned long long)r.x << 32) | r.y) & 0x000FFFFFFFFFFFFFull;
+        const unsigned long long expo = 1023ull - 60ull + (r.z % 121u);
+        const unsigned long long sign = (unsigned long long)(r.w & 1u) << 63;
+        const double x = __longlong_as_double((long long)(sign | (expo << 52) | mant));
+        bad += __double_as_longlong(div_total_mass(x)) != __double_as_longlong(__ddiv_rn(x, 1.1));
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+extern "C" int ses_test_div_total_mass(uint64_t n, uint64_t *mismatches_host)
+{
+    if (!mismatches_host) return fail("ses_test_div_total_mass: null argument");
+    unsigned long long *d = nullptr;
+    CU(cudaMalloc(&d, sizeof(unsigned long long)));
+    CU(cudaMemset(d, 0, sizeof(unsigned long long)));
+    k_div11_check<<<148 * 16, 256>>>((unsigned long long)n, d);
+    CU(cudaGetLastError());
+    unsigned long long r = 0;
+    CU(cudaMemcpy(&r, d, sizeof(r), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    *mismatches_host = r;
+    return 0;
+}

@@ -259,6 +259,12 @@ class RolloutEngine:
         _lib.check(self.lib.ses_test_tanh_fast_exhaustive(float(lo), float(hi), C.byref(bad)))
         return int(bad.value)
 
+    def test_div_total_mass(self, n=1 << 33):
+        """Mismatches between K1's multiply+2fma division by total_mass (1.1) and IEEE division on n random doubles."""
+        bad = C.c_uint64(0)
+        _lib.check(self.lib.ses_test_div_total_mass(int(n), C.byref(bad)))
+        return int(bad.value)
+
     def test_normals(self, generation, idx):
         out = torch.empty(self.D, dtype=torch.float32, device=self.device)
         _lib.check(self.lib.ses_test_normals(self._h, int(generation), int(idx), _ptr(out), self._stream()))

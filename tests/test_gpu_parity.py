@@ -35,6 +35,8 @@ def test_math_contract_bit_exact(twin):
     # K1 runs tanh with the division fast path written out; it must be the same function, for EVERY float
     assert np.array_equal(eng.test_math("tanh_fast", _cuda(x)).cpu().numpy(), twin.tanhf(x))
     assert eng.test_tanh_fast_exhaustive(0.0, 3.0e38) == 0
+    # ... and its 3-instruction division by total_mass must be the IEEE quotient (2^33 random operands)
+    assert eng.test_div_total_mass(1 << 33) == 0
     u = ((rng.integers(0, 2 ** 24, 1_000_000) + 0.5) * 2.0 ** -24).astype(np.float32)
     assert np.array_equal(eng.test_math("ln", _cuda(u)).cpu().numpy(), twin.lnf(u))
     v = (rng.integers(0, 2 ** 24, 1_000_000) * 2.0 ** -24).astype(np.float32)
