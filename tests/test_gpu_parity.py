@@ -356,3 +356,70 @@ def test_rollout_spread_verification_mode_matches_reference(twin, golden, name):
     trace = trace.cpu().numpy(); actions = actions.cpu().numpy()
     assert np.array_equal(actions[:, :25], g["trace_actions"])
     assert np.abs(trace[:, :25] - g["traces"]).max() <= 1e-9
+
+
+# ------------------------------------------------------------------------------------- BASELINE full sizes: size-independent properties
+def test_full_size_gru_config_properties(twin):
+    """BASELINE config 1: CartPole POMDP + GRU, simple_evolution, offspring_num 4096 (P = 4097)."""
+    P, E = 4097, 5
+    rng = np.random.default_rng(5)
+    mu = _cuda(rng.normal(0, 0.3, (1, DG)).astype(np.float32))
+    eng = _engine(population=P, group=P, n_head=2, eval_ep_num=E, gru=True, pomdp=True, seed=2)
+    fit, steps = eng.rollout(3, 0.5, mu)
+    fit2, steps2 = eng.rollout(3, 0.5, mu)
+    assert torch.equal(steps, steps2)                                             # deterministic
+    s = steps.cpu().numpy()
+    assert s[0] == s[1] and s.min() >= 5 * 8 and s.max() <= 5 * 500 and np.array_equal(fit.cpu().numpy(), s / E)
+    a = _engine(population=P, group=P, n_head=2, eval_ep_num=E, gru=True, pomdp=True, seed=2, id_begin=0, id_end=1500)
+    b = _engine(population=P, group=P, n_head=2, eval_ep_num=E, gru=True, pomdp=True, seed=2, id_begin=1500, id_end=P)
+    fa, sa = a.rollout(3, 0.5, mu)
+    b.rollout(3, 0.5, mu, fitness=fa, steps=sa)
+    assert torch.equal(sa, steps)                                                 # shards reproduce the whole
+    ids = rng.choice(P, 64, replace=False)                                        # spot-check against the oracle
+    for i in ids:
+        w = twin.materialize(mu.cpu().numpy(), 0.5, 2, 3, P, 2, np.array([i], np.int32))[0]
+        t, _, _ = twin.rollout_cartpole(w, gru=True, pomdp=True, E=E, seed=2, gen=3, idx=int(i))
+        assert t == s[i]
+
+
+def test_full_size_spread_config_properties(twin):
+    """BASELINE config 3: simple_spread, shared MLP, openai_es, population 16384 (N = 2 as the reference, and N = 3)."""
+    for N in (2, 3):
+        P, E = 16384, 5
+        Dn = 6 * N * 32 + 32 + 165
+        eng = _engine(env_name="simple_spread", obs_dim=6 * N, act_dim=5, n_agents=N, max_step="None", population=P, group=P,
+                      n_head=1, eval_ep_num=E, seed=4, init_mode="fresh")
+        mu = _cuda(np.zeros((1, Dn), np.float32))
+        fit, steps = eng.rollout(0, 0.2, mu)
+        fit2, _ = eng.rollout(0, 0.2, mu)
+        assert torch.equal(fit, fit2) and torch.all(steps == 25 * E)
+        f = fit.cpu().numpy()
+        assert np.all(f < 0) and np.isfinite(f).all()                             # rewards are negative distances / collisions
+        order, shaped = eng.rank_desc(fit, shaped=True)
+        o = order.cpu().numpy()
+        assert np.array_equal(np.sort(o), np.arange(P)) and np.all(np.diff(f[o]) <= 0)      # a permutation, descending
+        sh = shaped.cpu().numpy()
+        assert abs(sh.mean()) < 1e-12 and abs(sh.std() - 1) < 1e-12 and sh[o[0]] == sh.max()
+        for i in np.random.default_rng(N).choice(P, 48, replace=False):
+            w = twin.materialize(np.zeros((1, Dn), np.float32), 0.2, 4, 0, P, 1, np.array([i], np.int32))[0]
+            tf, _, _, _ = twin.rollout_mpe(w, N=N, E=E, seed=4, init_mode=1, gen=0, idx=int(i))
+            assert tf == f[i]
+
+
+def test_full_size_genetic_config_properties():
+    """BASELINE config 4: CartPole simple_genetic, k*(n//k) = 2^20 offspring, 16 elites."""
+    P, k = 1 << 20, 16
+    eng = _engine(population=P, group=P // k, n_head=1, n_parents=k, seed=1)
+    rng = np.random.default_rng(0)
+    parents = _cuda(rng.normal(0, 1, (k, D)).astype(np.float32))
+    fit, steps = eng.rollout(2, 1.0, parents)
+    s = steps.cpu().numpy()
+    assert s.min() >= 40 and s.max() <= 2500
+    order = eng.rank_desc(fit).cpu().numpy()
+    want = np.flip(np.argsort(fit.cpu().numpy(), kind="stable"))
+    assert np.array_equal(order, want)                                            # bit-exact top-k / full order at 2^20 with heavy ties
+    elites = eng.materialize(2, 1.0, parents, _cuda(order[:k].astype(np.int32))).cpu().numpy()
+    heads = np.arange(k) * (P // k)                                               # first of each group is the unperturbed elite
+    fit_heads = fit.cpu().numpy()[heads]
+    el_heads = eng.materialize(2, 1.0, parents, _cuda(heads.astype(np.int32))).cpu().numpy()
+    assert np.array_equal(el_heads, parents.cpu().numpy()) and np.isfinite(elites).all() and fit_heads.shape == (k,)
