@@ -147,10 +147,15 @@ int ses_test_normals(ses_handle *h, uint32_t generation, int32_t id, float *out_
 int ses_test_div_total_mass(uint64_t n, uint64_t *mismatches_host);
 /* counts float32 inputs x in [lo, hi] (and -x) for which K1's fast-path tanh differs from the contract's tanh32 */
 int ses_test_tanh_fast_exhaustive(float lo, float hi, uint64_t *mismatches_host);
+/* the same for the packed (FFMA2) tanh of K1's hidden-unit pairs, both halves; newton = 0 drops the Newton step on
+ * the reciprocal seed (K1 variant 2), newton = 1 keeps it (variant 1) */
+int ses_test_tanh_x2_exhaustive(int32_t newton, float lo, float hi, uint64_t *mismatches_host);
 
 /* Measurement hook: FP32 (non-tensor) FFMA peak of `device` in TFLOP/s from a dependent-free FFMA
  * microbenchmark -- the denominator of the rollout kernel's roofline in bench.py. */
 int ses_measure_fp32_peak(int32_t device, double *tflops_out);
+/* The same with packed FFMA2 (fma.rn.f32x2): two FMAs per issue slot. */
+int ses_measure_fp32x2_peak(int32_t device, double *tflops_out);
 
 /* Optional device counter (uint64): every ses_rollout adds the env steps it simulated (bench.py's numerator). */
 int ses_set_step_counter(ses_handle *h, uint64_t *counter_dev);

@@ -121,6 +121,9 @@ struct SpreadEnv {
     }
 
     template <int S>
+    __device__ static __forceinline__ void store_quad(float4 (&w)[NQ][S], int q, int s, const float4 v) { w[q][s] = v; }
+
+    template <int S>
     __device__ static __forceinline__ bool step(State &s, const float4 (&w)[NQ][S], int slot, const RolloutParams &, int *actions)
     {
         // observations (Scenario.observation): [vel, pos, landmarks - pos, others - pos, comm = 0], f64 -> f32
@@ -142,12 +145,24 @@ struct SpreadEnv {
                     o[i][c++] = (float)__dsub_rn(s.apos[j][1], s.apos[i][1]);
                 }
         }
-        // shared MLP, both agents off the same weight loads; logits in the contract's sequential order
-        float z[N][ACT];
+        // shared MLP, all agents off the same weight loads; logits in the contract's sequential order.
+        // Agents 0 and 1 run as the two halves of packed FFMA2 operations (same weight, two observations);
+        // a third agent runs scalar.  Same operations, same order, one rounding each as the oracle.
+        constexpr int NS = N - 2;                              // agents beyond the packed pair
+        float2 op[OBS_EFF];
+#pragma unroll
+        for (int k = 0; k < OBS_EFF; ++k) op[k] = make_float2(o[0][k], o[1][k]);
+        float2 zp[ACT];
+        float zs[NS > 0 ? NS : 1][ACT];
         {
             const float4 ba = w[O_B2 / 4][slot], bb = w[O_B2 / 4 + 1][slot];
+            const float bz[ACT] = {ba.x, ba.y, ba.z, ba.w, bb.x};
 #pragma unroll
-            for (int i = 0; i < N; ++i) { z[i][0] = ba.x; z[i][1] = ba.y; z[i][2] = ba.z; z[i][3] = ba.w; z[i][4] = bb.x; }
+            for (int m = 0; m < ACT; ++m) {
+                zp[m] = make_float2(bz[m], bz[m]);
+#pragma unroll
+                for (int i = 0; i < NS; ++i) zs[i][m] = bz[m];
+            }
         }
 #pragma unroll 1
         for (int jq = 0; jq < HID / 4; ++jq) {
@@ -168,17 +183,30 @@ struct SpreadEnv {
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
+                float2 a = make_float2(bias[u], bias[u]);
 #pragma unroll
-                for (int i = 0; i < N; ++i) {
-                    float a = bias[u];
+                for (int k = 0; k < OBS_EFF; ++k) a = __ffma2_rn(make_float2(wr[u * OBS + k], wr[u * OBS + k]), op[k], a);
+                // the skipped comm inputs are exactly 0: fmaf(w, 0, a) == a
+                const float2 h = tanh32x2<true>(a);
 #pragma unroll
-                    for (int k = 0; k < OBS_EFF; ++k) a = fmaf(wr[u * OBS + k], o[i][k], a);
-                    // the skipped comm inputs are exactly 0: fmaf(w, 0, a) == a
-                    const float h = tanh32_fast(a);
+                for (int m = 0; m < ACT; ++m) zp[m] = __ffma2_rn(make_float2(w2[m][u], w2[m][u]), h, zp[m]);
 #pragma unroll
-                    for (int m = 0; m < ACT; ++m) z[i][m] = fmaf(w2[m][u], h, z[i][m]);
+                for (int i = 0; i < NS; ++i) {
+                    float as = bias[u];
+#pragma unroll
+                    for (int k = 0; k < OBS_EFF; ++k) as = fmaf(wr[u * OBS + k], o[2 + i][k], as);
+                    const float hs = tanh32_fast(as);
+#pragma unroll
+                    for (int m = 0; m < ACT; ++m) zs[i][m] = fmaf(w2[m][u], hs, zs[i][m]);
                 }
             }
+        }
+        float z[N][ACT];
+#pragma unroll
+        for (int m = 0; m < ACT; ++m) {
+            z[0][m] = zp[m].x; z[1][m] = zp[m].y;
+#pragma unroll
+            for (int i = 0; i < NS; ++i) z[2 + i][m] = zs[i][m];
         }
         // argmax(softmax(z)) with the float32 collapse rule (neural_network.py:30-31)
 #pragma unroll

@@ -26,6 +26,7 @@
 // An Env type provides:
 //   D, NQ, STATE_DIM, N_AGENTS, UNIT_REWARD (reward == 1.0 per step: fitness = steps / E exactly)
 //   struct State;  init(State&, p, id, ep);
+//   store_quad<S>(w[NQ][S], q, s, float4)   place flat parameter quad q of slot s (an Env may permute the table)
 //   step<S>(State&, w[NQ][S], slot, p, int *actions) -> done   (also adds the step reward to State::ret)
 //   store_trace(State&, double *row)
 #pragma once
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_rollout_slots(const RolloutParam
                         wq = offspring_quad(p.parents + (size_t)p.layout.parent(id) * D, D, q,
                                             p.layout.perturbed(id), p.sigma, p.seed, (uint32_t)id, p.gen);
                     }
-                    sm.w[q][s] = wq;
+                    Env::template store_quad<S>(sm.w, q, s, wq);
                 }
                 __syncwarp();
             }

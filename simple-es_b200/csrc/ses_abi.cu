@@ -77,6 +77,8 @@ struct ses_handle {
     // rollout launch configuration
     int lanes_used_override = 0;
     int ctas_per_sm = 0;
+    int k1_variant = 1;
+    int k1_slots = 8;
     int64_t launches = 0;
 };
 
@@ -129,6 +131,9 @@ extern "C" int ses_create(const ses_config *cfg, ses_handle **out)
     h->eff_max_step = cfg->max_step > 0 ? (cfg->max_step < env_cap ? cfg->max_step : env_cap) : env_cap;
     h->lanes_used_override = env_int("SES_ROLLOUT_LANES", 0);
     h->ctas_per_sm = env_int("SES_ROLLOUT_CTAS_PER_SM", 0);
+    h->k1_variant = env_int("SES_K1_VARIANT", 1);
+    if (h->k1_variant < 0 || h->k1_variant > 2) h->k1_variant = 1;
+    h->k1_slots = env_int("SES_K1_SLOTS", 8);
 
     const int P = cfg->population;
     h->n_tiles = (P + sort_tile(SORT_ITEMS_SMALL) - 1) / sort_tile(SORT_ITEMS_SMALL);
@@ -244,9 +249,14 @@ extern "C" int ses_rollout(ses_handle *h, uint32_t generation, float sigma, cons
     const bool tr = n_trace > 0;
     if (c.env == SES_ENV_CARTPOLE && !c.gru) {
         // slots per warp: enough offspring to occupy 32 lanes (E >= 4: 8, E in {2,3}: 16, E = 1: 32)
-        if (c.eval_ep_num >= 4) return launch_slots<CartpoleMlpEnv, 8>(h, rp, need_warps, tr, st);
-        if (c.eval_ep_num >= 2) return launch_slots<CartpoleMlpEnv, 16>(h, rp, need_warps, tr, st);
-        return launch_slots<CartpoleMlpEnv, 32>(h, rp, need_warps, tr, st);
+        if (c.eval_ep_num >= 4) {
+            if (h->k1_variant == 0) return launch_slots<CartpoleMlpEnvT<0>, 8>(h, rp, need_warps, tr, st);
+            if (h->k1_variant == 2 && h->k1_slots == 6 && rp.lanes_used <= 6 * c.eval_ep_num) return launch_slots<CartpoleMlpEnvT<2>, 6>(h, rp, need_warps, tr, st);
+            if (h->k1_variant == 2) return launch_slots<CartpoleMlpEnvT<2>, 8>(h, rp, need_warps, tr, st);
+            return launch_slots<CartpoleMlpEnvT<1>, 8>(h, rp, need_warps, tr, st);
+        }
+        if (c.eval_ep_num >= 2) return launch_slots<CartpoleMlpEnvT<1>, 16>(h, rp, need_warps, tr, st);
+        return launch_slots<CartpoleMlpEnvT<1>, 32>(h, rp, need_warps, tr, st);
     }
     if (c.env == SES_ENV_CARTPOLE && c.gru) return launch_rollout_cartpole_gru(h->num_sms, h->ctas_per_sm, rp, tr, st, &h->launches, g_err, sizeof(g_err));
     if (c.n_agents == 2) return launch_slots<SpreadEnv<2>, 8>(h, rp, need_warps, tr, st);
@@ -596,9 +606,25 @@ __global__ void __launch_bounds__(256) k_ffma_peak(float *out, int iters, float 
     if (s == 123.456f) out[0] = s;
 }
 
-extern "C" int ses_measure_fp32_peak(int32_t device, double *tflops_out)
+__global__ void __launch_bounds__(256) k_ffma2_peak(float *out, int iters, float a, float b)
 {
-    if (!tflops_out) return fail("ses_measure_fp32_peak: null argument");
+    const float t = threadIdx.x;
+    float2 x0 = make_float2(t, t + 1.f), x1 = make_float2(t + 2.f, t + 3.f), x2 = make_float2(t + 4.f, t + 5.f), x3 = make_float2(t + 6.f, t + 7.f);
+    float2 x4 = make_float2(t + 8.f, t + 9.f), x5 = make_float2(t + 10.f, t + 11.f), x6 = make_float2(t + 12.f, t + 13.f), x7 = make_float2(t + 14.f, t + 15.f);
+    const float2 a2 = make_float2(a, a), b2 = make_float2(b, b);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = __ffma2_rn(x0, a2, b2); x1 = __ffma2_rn(x1, a2, b2); x2 = __ffma2_rn(x2, a2, b2); x3 = __ffma2_rn(x3, a2, b2);
+            x4 = __ffma2_rn(x4, a2, b2); x5 = __ffma2_rn(x5, a2, b2); x6 = __ffma2_rn(x6, a2, b2); x7 = __ffma2_rn(x7, a2, b2);
+        }
+    }
+    const float s = ((x0.x + x1.x) + (x2.x + x3.x)) + ((x4.x + x5.x) + (x6.x + x7.x)) + ((x0.y + x1.y) + (x2.y + x3.y)) + ((x4.y + x5.y) + (x6.y + x7.y));
+    if (s == 123.456f) out[0] = s;
+}
+
+static int measure_peak(int32_t device, double *tflops_out, bool packed)
+{
     CU(cudaSetDevice(device));
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
@@ -611,18 +637,31 @@ extern "C" int ses_measure_fp32_peak(int32_t device, double *tflops_out)
     double best = 0.0;
     for (int rep = 0; rep < 5; ++rep) {
         CU(cudaEventRecord(e0));
-        k_ffma_peak<<<grid, threads>>>(out, iters, 0.999f, 0.001f);
+        if (packed) k_ffma2_peak<<<grid, threads>>>(out, iters, 0.999f, 0.001f);
+        else k_ffma_peak<<<grid, threads>>>(out, iters, 0.999f, 0.001f);
         CU(cudaEventRecord(e1));
         CU(cudaEventSynchronize(e1));
         float ms = 0.f;
         CU(cudaEventElapsedTime(&ms, e0, e1));
-        const double fl = (double)grid * threads * (double)iters * 64.0 * 2.0;
+        const double fl = (double)grid * threads * (double)iters * 64.0 * 2.0 * (packed ? 2.0 : 1.0);
         const double tf = fl / (ms * 1e-3) / 1e12;
         if (rep > 0 && tf > best) best = tf;
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
     *tflops_out = best;
     return 0;
+}
+
+extern "C" int ses_measure_fp32x2_peak(int32_t device, double *tflops_out)
+{
+    if (!tflops_out) return fail("ses_measure_fp32x2_peak: null argument");
+    return measure_peak(device, tflops_out, true);
+}
+
+extern "C" int ses_measure_fp32_peak(int32_t device, double *tflops_out)
+{
+    if (!tflops_out) return fail("ses_measure_fp32_peak: null argument");
+    return measure_peak(device, tflops_out, false);
 }
 
 // every float32 bit pattern b in [lo_bits, hi_bits]: tanh32_fast(x) must equal tanh32(x) bit for bit
@@ -638,6 +677,40 @@ __global__ void k_tanh_fast_exhaustive(uint32_t lo_bits, uint32_t hi_bits, unsig
         bad += ((a != b) && ((a | b) << 1) != 0) + ((an != bn) && ((an | bn) << 1) != 0);
     }
     if (bad) atomicAdd(mismatches, bad);
+}
+
+// packed tanh: x in the low half with a far-away value in the high half and vice versa -- both halves must equal tanh32
+template <bool NEWTON>
+__global__ void k_tanh_x2_exhaustive(uint32_t lo_bits, uint32_t hi_bits, unsigned long long *mismatches)
+{
+    unsigned long long bad = 0;
+    const unsigned long long n = (unsigned long long)hi_bits - lo_bits + 1ull;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const float x = __uint_as_float(lo_bits + (uint32_t)i);
+        const float2 y = tanh32x2<NEWTON>(make_float2(x, -x));
+        const uint32_t a = __float_as_uint(y.x), b = __float_as_uint(tanh32(x));
+        const uint32_t an = __float_as_uint(y.y), bn = __float_as_uint(tanh32(-x));
+        bad += ((a != b) && ((a | b) << 1) != 0) + ((an != bn) && ((an | bn) << 1) != 0);
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+extern "C" int ses_test_tanh_x2_exhaustive(int32_t newton, float lo, float hi, uint64_t *mismatches_host)
+{
+    if (!mismatches_host || !(lo >= 0.0f) || !(hi >= lo)) return fail("ses_test_tanh_x2_exhaustive: bad arguments");
+    unsigned long long *d = nullptr;
+    CU(cudaMalloc(&d, sizeof(unsigned long long)));
+    CU(cudaMemset(d, 0, sizeof(unsigned long long)));
+    uint32_t lb, hb;
+    memcpy(&lb, &lo, 4); memcpy(&hb, &hi, 4);
+    if (newton) k_tanh_x2_exhaustive<true><<<148 * 16, 256>>>(lb, hb, d);
+    else k_tanh_x2_exhaustive<false><<<148 * 16, 256>>>(lb, hb, d);
+    CU(cudaGetLastError());
+    unsigned long long r = 0;
+    CU(cudaMemcpy(&r, d, sizeof(r), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    *mismatches_host = r;
+    return 0;
 }
 
 extern "C" int ses_test_tanh_fast_exhaustive(float lo, float hi, uint64_t *mismatches_host)

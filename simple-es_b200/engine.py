@@ -259,6 +259,12 @@ class RolloutEngine:
         _lib.check(self.lib.ses_test_tanh_fast_exhaustive(float(lo), float(hi), C.byref(bad)))
         return int(bad.value)
 
+    def test_tanh_x2_exhaustive(self, newton, lo=0.0, hi=10.0):
+        """The same for the packed (FFMA2) tanh of K1's hidden-unit pairs; newton=False is K1 variant 2."""
+        bad = C.c_uint64(0)
+        _lib.check(self.lib.ses_test_tanh_x2_exhaustive(int(bool(newton)), float(lo), float(hi), C.byref(bad)))
+        return int(bad.value)
+
     def test_div_total_mass(self, n=1 << 33):
         """Mismatches between K1's multiply+2fma division by total_mass (1.1) and IEEE division on n random doubles."""
         bad = C.c_uint64(0)

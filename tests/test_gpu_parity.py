@@ -35,6 +35,8 @@ def test_math_contract_bit_exact(twin):
     # K1 runs tanh with the division fast path written out; it must be the same function, for EVERY float
     assert np.array_equal(eng.test_math("tanh_fast", _cuda(x)).cpu().numpy(), twin.tanhf(x))
     assert eng.test_tanh_fast_exhaustive(0.0, 3.0e38) == 0
+    # the packed FFMA2 form K1 runs on pairs of hidden units (default variant 1): the same function in both halves
+    assert eng.test_tanh_x2_exhaustive(True, 0.0, 3.0e38) == 0
     # ... and its 3-instruction division by total_mass must be the IEEE quotient (2^33 random operands)
     assert eng.test_div_total_mass(1 << 33) == 0
     u = ((rng.integers(0, 2 ** 24, 1_000_000) + 0.5) * 2.0 ** -24).astype(np.float32)
@@ -83,6 +85,32 @@ def test_rollout_philox_bit_exact(twin, init_mode, pomdp, E):
     assert np.array_equal(steps.cpu().numpy(), ts)          # integer returns: bit-exact
     assert np.array_equal(fit.cpu().numpy(), tf)
     assert ts.max() > 3 * ts.min()                          # the case really has ragged episode lengths
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_rollout_k1_variants_bit_exact(twin, variant, monkeypatch):
+    """K1 variant 0 (scalar FFMA, flat slot table) and variant 1 (packed FFMA2 over hidden-unit pairs, permuted
+    slot table; the default) are the same function: both must reproduce the oracle bit for bit, Philox and
+    verification (w_override) paths, ragged and 500-step episodes."""
+    monkeypatch.setenv("SES_K1_VARIANT", str(variant))
+    P, E = 2048, 5
+    rng = np.random.default_rng(5)
+    for sigma, seed in [(2.0, 21), (0.05, 22)]:
+        mu = np.zeros((1, D), np.float32)
+        if sigma < 1.0:
+            w1 = mu[0, :128].reshape(32, 4); w2 = mu[0, 160:224].reshape(2, 32)
+            w1[0] = [0.0, 0.5, 10.0, 3.0]; w2[1, 0] = 5.0; w2[0, 0] = -5.0
+        eng = _engine(population=P, group=P, n_head=1, eval_ep_num=E, seed=seed)
+        fit, steps = eng.rollout(1, sigma, _cuda(mu))
+        tf, ts = twin.population_cartpole(mu, sigma=sigma, seed=seed, gen=1, group=P, n_head=1, n=P, E=E, nthreads=8)
+        assert np.array_equal(steps.cpu().numpy(), ts) and np.array_equal(fit.cpu().numpy(), tf)
+        eng.close()
+    W = rng.normal(0, 1.5, (256, D)).astype(np.float32)
+    init = rng.uniform(-0.05, 0.05, (E, 4))
+    eng = _engine(population=256, group=256, n_head=1, eval_ep_num=E)
+    fit, steps = eng.rollout(0, 0.0, None, w_override=_cuda(W), init_states=_cuda(init))
+    tf, ts = twin.population_cartpole(np.zeros((1, D), np.float32), n=256, group=256, E=E, W_override=W, init=init, nthreads=8)
+    assert np.array_equal(steps.cpu().numpy(), ts) and np.array_equal(fit.cpu().numpy(), tf)
 
 
 def test_rollout_trained_parent_long_episodes(twin):
