@@ -35,7 +35,9 @@ def test_math_contract_bit_exact(twin):
     # K1 runs tanh with the division fast path written out; it must be the same function, for EVERY float
     assert np.array_equal(eng.test_math("tanh_fast", _cuda(x)).cpu().numpy(), twin.tanhf(x))
     assert eng.test_tanh_fast_exhaustive(0.0, 3.0e38) == 0
-    # the packed FFMA2 form K1 runs on pairs of hidden units (default variant 1): the same function in both halves
+    # the packed FFMA2 forms K1 runs on pairs of hidden units (variant 2, the default, has no Newton step on the
+    # reciprocal seed; variant 1 keeps it): the same function in both halves, for EVERY float
+    assert eng.test_tanh_x2_exhaustive(False, 0.0, 3.0e38) == 0
     assert eng.test_tanh_x2_exhaustive(True, 0.0, 3.0e38) == 0
     # ... and its 3-instruction division by total_mass must be the IEEE quotient (2^33 random operands)
     assert eng.test_div_total_mass(1 << 33) == 0
@@ -87,22 +89,25 @@ def test_rollout_philox_bit_exact(twin, init_mode, pomdp, E):
     assert ts.max() > 3 * ts.min()                          # the case really has ragged episode lengths
 
 
-@pytest.mark.parametrize("variant", [0, 1])
-def test_rollout_k1_variants_bit_exact(twin, variant, monkeypatch):
-    """K1 variant 0 (scalar FFMA, flat slot table) and variant 1 (packed FFMA2 over hidden-unit pairs, permuted
-    slot table; the default) are the same function: both must reproduce the oracle bit for bit, Philox and
-    verification (w_override) paths, ragged and 500-step episodes."""
-    monkeypatch.setenv("SES_K1_VARIANT", str(variant))
-    P, E = 2048, 5
+@pytest.mark.parametrize("knobs,E", [({"SES_K1_VARIANT": "0"}, 5), ({"SES_K1_VARIANT": "1"}, 5), ({"SES_K1_VARIANT": "2"}, 5),
+                                     ({"SES_K1_VARIANT": "2"}, 3), ({"SES_K1_VARIANT": "2"}, 1)])
+def test_rollout_k1_variants_bit_exact(twin, knobs, E, monkeypatch):
+    """Every K1 code path is the same function: variant 0 (scalar FFMA, flat slot table), 1 / 2 (packed FFMA2 over
+    hidden-unit pairs, permuted slot table, with / without the Newton step of the tanh division; 2 is the default)
+    must all reproduce the oracle bit for bit: Philox and verification (w_override) paths, ragged and 500-step
+    episodes, 8 / 16 / 32 slots per warp (E = 5 / 3 / 1)."""
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    P = 2048
     rng = np.random.default_rng(5)
-    for sigma, seed in [(2.0, 21), (0.05, 22)]:
+    for sigma, seed, pomdp in [(2.0, 21, False), (0.05, 22, False), (1.0, 23, True)]:
         mu = np.zeros((1, D), np.float32)
         if sigma < 1.0:
             w1 = mu[0, :128].reshape(32, 4); w2 = mu[0, 160:224].reshape(2, 32)
             w1[0] = [0.0, 0.5, 10.0, 3.0]; w2[1, 0] = 5.0; w2[0, 0] = -5.0
-        eng = _engine(population=P, group=P, n_head=1, eval_ep_num=E, seed=seed)
+        eng = _engine(population=P, group=P, n_head=1, eval_ep_num=E, seed=seed, pomdp=pomdp)
         fit, steps = eng.rollout(1, sigma, _cuda(mu))
-        tf, ts = twin.population_cartpole(mu, sigma=sigma, seed=seed, gen=1, group=P, n_head=1, n=P, E=E, nthreads=8)
+        tf, ts = twin.population_cartpole(mu, pomdp=pomdp, sigma=sigma, seed=seed, gen=1, group=P, n_head=1, n=P, E=E, nthreads=8)
         assert np.array_equal(steps.cpu().numpy(), ts) and np.array_equal(fit.cpu().numpy(), tf)
         eng.close()
     W = rng.normal(0, 1.5, (256, D)).astype(np.float32)
