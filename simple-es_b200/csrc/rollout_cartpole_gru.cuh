@@ -6,11 +6,16 @@
 // Mapping: 26 kB of weights per offspring do not fit per lane, so a WARP owns
 // one offspring: its weights live in shared memory, lane j owns hidden unit j, and the warp steps up
 // to EC episodes of that offspring in lockstep so that every weight read from shared memory feeds EC
-// FMAs.  W_ih / W_hh are stored tiled as [k/4][row][4]: lane j reads its three gate rows with
-// conflict-free LDS.128, the x / h vectors come back as broadcast LDS.128 from small per-warp
-// buffers.  Lane e (e < EC) additionally owns the float64 cart-pole state of episode e and evaluates
-// the two logits with the contract's sequential order, then the physics.  8 warps (offspring) are
-// resident per SM -- shared-memory capacity is what bounds this variant.
+// FMAs.  The six gate rows of lane j are stored as PAIRS so that the GEMV runs on packed FFMA2
+// (two IEEE fmas per issue slot, same bits as two FFMA):
+//     wrz_i[k/2][j] = { W_ir[j][k], W_iz[j][k], W_ir[j][k+1], W_iz[j][k+1] }     x[k] is the broadcast scalar
+//     wrz_h[k/2][j] = { W_hr[j][k], W_hz[j][k], W_hr[j][k+1], W_hz[j][k+1] }     h[k] is the broadcast scalar
+//     wn   [k/2][j] = { W_in[j][k], W_hn[j][k], W_in[j][k+1], W_hn[j][k+1] }     times the pair { x[k], h[k] }
+// (conflict-free LDS.128 per lane); x and h live interleaved in xh[e][k] = { x[k], h[k] } and come back as
+// broadcast LDS.128.  Every accumulator still sees its products in ascending k, one rounding per fma, as the
+// contract states.  Lane e (e < EC) additionally owns the float64 cart-pole state of episode e and evaluates
+// the two logits (packed as { z0, z1 }) in the contract's sequential order, then the physics.  8 warps
+// (offspring) are resident per SM -- shared-memory capacity is what bounds this variant.
 #pragma once
 #include <cstdio>
 #include "rollout_cartpole_mlp.cuh"
@@ -27,19 +32,35 @@ constexpr int GRU_NQ = (GRU_D + 3) / 4;                // 1641 quads (flat order
 
 template <int EC>
 struct __align__(16) GruWarpSmem {
-    float4 wih[HID / 4][G3];       // [k/4][row] -> W_ih[row][4*(k/4) .. +3]
-    float4 whh[HID / 4][G3];
+    float4 wrz_i[HID / 2][HID];    // see the header comment
+    float4 wrz_h[HID / 2][HID];
+    float4 wn[HID / 2][HID];
     float4 small[(GRU_D - 2 * G3 * HID + 3) / 4 + 1];   // W1, b1 | b_ih, b_hh, W2, b2 in flat order (gap removed)
-    float xbuf[EC][HID];           // tanh(fc1) per episode
-    float hbuf[EC][HID];           // GRU hidden state per episode
-    float obuf[EC][HID + 1];       // tanh(h') per episode, padded: lane e walks row e
+    float2 w2p[HID];               // { W2[0][j], W2[1][j] }
+    float2 xh[EC][HID];            // { tanh(fc1)[k], h[k] } per episode
+    float obuf[EC][HID + 4];       // tanh(h') per episode; rows 16 B aligned and 4 banks apart: lane e walks row e
 };
+
+// place flat quad (4 consecutive columns c0..c0+3 of gate row `row`) of W_ih (hh = 0) or W_hh (hh = 1)
+template <int EC>
+__device__ __forceinline__ void gru_store_gate_quad(GruWarpSmem<EC> &sm, int hh, int row, int c0, const float4 w)
+{
+    const int g = row >> 5, j = row & 31;                      // torch gate order r, z, n
+    float *base;
+    int comp;
+    if (g == 2) { base = reinterpret_cast<float *>(&sm.wn[0][0]); comp = hh; }
+    else { base = reinterpret_cast<float *>(hh ? &sm.wrz_h[0][0] : &sm.wrz_i[0][0]); comp = g; }
+    // element (k, j) of a [HID/2][HID] float4 table: quad (k/2, j), component 2*(k&1) + comp
+    const int kp = c0 >> 1;                                    // c0 is a multiple of 4
+    float *q0 = base + ((size_t)kp * HID + j) * 4, *q1 = base + ((size_t)(kp + 1) * HID + j) * 4;
+    q0[comp] = w.x; q0[2 + comp] = w.y; q1[comp] = w.z; q1[2 + comp] = w.w;
+}
 
 // index into `small` (floats) of flat parameter d outside the two big matrices
 __device__ __forceinline__ int gru_small_index(int d) { return d < GO_WIH ? d : d - 2 * G3 * HID; }
 
 template <int EC, int WARPS, bool TRACE>
-__global__ void __launch_bounds__(WARPS * 32) k_rollout_cartpole_gru(const RolloutParams p)
+__global__ void __launch_bounds__(WARPS * 32, 2) k_rollout_cartpole_gru(const RolloutParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GruWarpSmem<EC> &sm = reinterpret_cast<GruWarpSmem<EC> *>(smem_raw)[threadIdx.x >> 5];
@@ -65,11 +86,16 @@ __global__ void __launch_bounds__(WARPS * 32) k_rollout_cartpole_gru(const Rollo
                 const float4 w = offspring_quad(prow, GRU_D, q, pert, p.sigma, p.seed, (uint32_t)id, p.gen);
                 const int d = 4 * q;
                 if (d >= GO_WIH && d < GO_WHH) {
-                    const int o = d - GO_WIH; sm.wih[(o & 31) >> 2][o >> 5] = w;
+                    const int o = d - GO_WIH; gru_store_gate_quad<EC>(sm, 0, o >> 5, o & 31, w);
                 } else if (d >= GO_WHH && d < GO_BIH) {
-                    const int o = d - GO_WHH; sm.whh[(o & 31) >> 2][o >> 5] = w;
+                    const int o = d - GO_WHH; gru_store_gate_quad<EC>(sm, 1, o >> 5, o & 31, w);
                 } else {
                     sm.small[gru_small_index(d) >> 2] = w;
+                    if (d >= GO_W2 && d < GO_B2) {             // fc2 rows also as { W2[0][j], W2[1][j] } pairs
+                        const int r = (d - GO_W2) >> 5, j = (d - GO_W2) & 31;
+                        float *wp = reinterpret_cast<float *>(&sm.w2p[0]);
+                        wp[2 * j + r] = w.x; wp[2 * (j + 1) + r] = w.y; wp[2 * (j + 2) + r] = w.z; wp[2 * (j + 3) + r] = w.w;
+                    }
                 }
             }
         }
@@ -81,7 +107,6 @@ __global__ void __launch_bounds__(WARPS * 32) k_rollout_cartpole_gru(const Rollo
                     bin = smallf[gru_small_index(GO_BIH) + 2 * HID + lane];
         const float bhr = smallf[gru_small_index(GO_BHH) + lane], bhz = smallf[gru_small_index(GO_BHH) + HID + lane],
                     bhn = smallf[gru_small_index(GO_BHH) + 2 * HID + lane];
-        const float *w2 = smallf + gru_small_index(GO_W2);
         const float b20 = smallf[gru_small_index(GO_B2)], b21 = smallf[gru_small_index(GO_B2) + 1];
 
         long long total_steps = 0;
@@ -101,69 +126,98 @@ __global__ void __launch_bounds__(WARPS * 32) k_rollout_cartpole_gru(const Rollo
             }
             float h[EC];
 #pragma unroll
-            for (int e = 0; e < EC; ++e) { h[e] = 0.0f; sm.hbuf[e][lane] = 0.0f; }      // model.reset() (neural_network.py:38-40)
+            for (int e = 0; e < EC; ++e) { h[e] = 0.0f; sm.xh[e][lane] = make_float2(0.0f, 0.0f); }      // model.reset() (neural_network.py:38-40)
             unsigned alive_mask = __ballot_sync(FULL, alive);
+            constexpr int NP = EC / 2;                                 // episode pairs for the packed tanh
 
             while (alive_mask) {
                 // fc1 for every live episode: obs of episode e lives in lane e
                 const float o0 = (float)x, o2 = (float)th;
                 const float o1 = p.pomdp ? 0.0f : (float)xd;
                 const float o3 = p.pomdp ? 0.0f : (float)thd;
-#pragma unroll
-                for (int e = 0; e < EC; ++e) {
-                    const float q0 = __shfl_sync(FULL, o0, e), q1 = __shfl_sync(FULL, o1, e),
-                                q2 = __shfl_sync(FULL, o2, e), q3 = __shfl_sync(FULL, o3, e);
-                    float a = b1;
-                    a = fmaf(w1.x, q0, a); a = fmaf(w1.y, q1, a); a = fmaf(w1.z, q2, a); a = fmaf(w1.w, q3, a);
-                    sm.xbuf[e][lane] = tanh32_fast(a);
-                }
-                __syncwarp();
-                // gate pre-activations: lane j accumulates rows j, 32+j, 64+j of W_ih x and W_hh h
-                float gir[EC], giz[EC], gin[EC], ghr[EC], ghz[EC], ghn[EC];
-#pragma unroll
-                for (int e = 0; e < EC; ++e) { gir[e] = bir; giz[e] = biz; gin[e] = bin; ghr[e] = bhr; ghz[e] = bhz; ghn[e] = bhn; }
-#pragma unroll 2
-                for (int kq = 0; kq < HID / 4; ++kq) {
-                    const float4 ar = sm.wih[kq][lane], az = sm.wih[kq][HID + lane], an = sm.wih[kq][2 * HID + lane];
-                    const float4 cr = sm.whh[kq][lane], cz = sm.whh[kq][HID + lane], cn = sm.whh[kq][2 * HID + lane];
+                {
+                    float a[EC];
 #pragma unroll
                     for (int e = 0; e < EC; ++e) {
-                        const float4 xv = *reinterpret_cast<const float4 *>(&sm.xbuf[e][4 * kq]);
-                        const float4 hv = *reinterpret_cast<const float4 *>(&sm.hbuf[e][4 * kq]);
-                        gir[e] = fmaf(ar.x, xv.x, gir[e]); gir[e] = fmaf(ar.y, xv.y, gir[e]); gir[e] = fmaf(ar.z, xv.z, gir[e]); gir[e] = fmaf(ar.w, xv.w, gir[e]);
-                        giz[e] = fmaf(az.x, xv.x, giz[e]); giz[e] = fmaf(az.y, xv.y, giz[e]); giz[e] = fmaf(az.z, xv.z, giz[e]); giz[e] = fmaf(az.w, xv.w, giz[e]);
-                        gin[e] = fmaf(an.x, xv.x, gin[e]); gin[e] = fmaf(an.y, xv.y, gin[e]); gin[e] = fmaf(an.z, xv.z, gin[e]); gin[e] = fmaf(an.w, xv.w, gin[e]);
-                        ghr[e] = fmaf(cr.x, hv.x, ghr[e]); ghr[e] = fmaf(cr.y, hv.y, ghr[e]); ghr[e] = fmaf(cr.z, hv.z, ghr[e]); ghr[e] = fmaf(cr.w, hv.w, ghr[e]);
-                        ghz[e] = fmaf(cz.x, hv.x, ghz[e]); ghz[e] = fmaf(cz.y, hv.y, ghz[e]); ghz[e] = fmaf(cz.z, hv.z, ghz[e]); ghz[e] = fmaf(cz.w, hv.w, ghz[e]);
-                        ghn[e] = fmaf(cn.x, hv.x, ghn[e]); ghn[e] = fmaf(cn.y, hv.y, ghn[e]); ghn[e] = fmaf(cn.z, hv.z, ghn[e]); ghn[e] = fmaf(cn.w, hv.w, ghn[e]);
+                        const float q0 = __shfl_sync(FULL, o0, e), q1 = __shfl_sync(FULL, o1, e),
+                                    q2 = __shfl_sync(FULL, o2, e), q3 = __shfl_sync(FULL, o3, e);
+                        a[e] = b1;
+                        a[e] = fmaf(w1.x, q0, a[e]); a[e] = fmaf(w1.y, q1, a[e]); a[e] = fmaf(w1.z, q2, a[e]); a[e] = fmaf(w1.w, q3, a[e]);
                     }
-                }
-                __syncwarp();                                          // everyone has read hbuf before it is rewritten
-                // GRU cell (torch gate order r, z, n) and the output non-linearity
 #pragma unroll
-                for (int e = 0; e < EC; ++e) {
-                    const float rg = fmaf(0.5f, tanh32_fast(__fmul_rn(0.5f, __fadd_rn(gir[e], ghr[e]))), 0.5f);
-                    const float zg = fmaf(0.5f, tanh32_fast(__fmul_rn(0.5f, __fadd_rn(giz[e], ghz[e]))), 0.5f);
-                    const float ng = tanh32_fast(fmaf(rg, ghn[e], gin[e]));
-                    const float hn = fmaf(zg, h[e], __fmul_rn(__fsub_rn(1.0f, zg), ng));
-                    // a finished episode keeps its (unused) state; the values are simply never read again
-                    h[e] = hn;
-                    sm.hbuf[e][lane] = hn;
-                    sm.obuf[e][lane] = tanh32_fast(hn);
+                    for (int pe = 0; pe < NP; ++pe) {
+                        const float2 t = tanh32x2<false>(make_float2(a[2 * pe], a[2 * pe + 1]));
+                        sm.xh[2 * pe][lane].x = t.x; sm.xh[2 * pe + 1][lane].x = t.y;
+                    }
+                    if constexpr (EC & 1) sm.xh[EC - 1][lane].x = tanh32_fast_t<false>(a[EC - 1]);
                 }
                 __syncwarp();
-                // lane e: logits in the contract's sequential order, action, physics
+                // gate pre-activations of lane j, as pairs: { r_i, z_i } (W_ih x), { r_h, z_h } (W_hh h), { n_i, n_h }
+                float2 grz_i[EC], grz_h[EC], gn[EC];
+#pragma unroll
+                for (int e = 0; e < EC; ++e) { grz_i[e] = make_float2(bir, biz); grz_h[e] = make_float2(bhr, bhz); gn[e] = make_float2(bin, bhn); }
+#pragma unroll 2
+                for (int kp = 0; kp < HID / 2; ++kp) {
+                    const float4 a = sm.wrz_i[kp][lane], c = sm.wrz_h[kp][lane], n = sm.wn[kp][lane];
+#pragma unroll
+                    for (int e = 0; e < EC; ++e) {
+                        const float4 v = *reinterpret_cast<const float4 *>(&sm.xh[e][2 * kp]);      // { x[k], h[k], x[k+1], h[k+1] }
+                        grz_i[e] = __ffma2_rn(make_float2(a.x, a.y), make_float2(v.x, v.x), grz_i[e]);
+                        grz_h[e] = __ffma2_rn(make_float2(c.x, c.y), make_float2(v.y, v.y), grz_h[e]);
+                        gn[e] = __ffma2_rn(make_float2(n.x, n.y), make_float2(v.x, v.y), gn[e]);
+                        grz_i[e] = __ffma2_rn(make_float2(a.z, a.w), make_float2(v.z, v.z), grz_i[e]);
+                        grz_h[e] = __ffma2_rn(make_float2(c.z, c.w), make_float2(v.w, v.w), grz_h[e]);
+                        gn[e] = __ffma2_rn(make_float2(n.z, n.w), make_float2(v.z, v.w), gn[e]);
+                    }
+                }
+                __syncwarp();                                          // everyone has read xh before h is rewritten
+                // GRU cell (torch gate order r, z, n) and the output non-linearity
+                float npre[EC], zg[EC];
+#pragma unroll
+                for (int e = 0; e < EC; ++e) {
+                    // { r, z } = sigm32({ r_i + r_h, z_i + z_h }) = 0.5 * tanh32(0.5 * s) + 0.5
+                    const float2 sres = __fadd2_rn(grz_i[e], grz_h[e]);
+                    const float2 t = tanh32x2<false>(__fmul2_rn(make_float2(0.5f, 0.5f), sres));
+                    const float2 rz = __ffma2_rn(make_float2(0.5f, 0.5f), t, make_float2(0.5f, 0.5f));
+                    npre[e] = fmaf(rz.x, gn[e].y, gn[e].x);
+                    zg[e] = rz.y;
+                }
+                float ng[EC];
+#pragma unroll
+                for (int pe = 0; pe < NP; ++pe) {
+                    const float2 t = tanh32x2<false>(make_float2(npre[2 * pe], npre[2 * pe + 1]));
+                    ng[2 * pe] = t.x; ng[2 * pe + 1] = t.y;
+                }
+                if constexpr (EC & 1) ng[EC - 1] = tanh32_fast_t<false>(npre[EC - 1]);
+#pragma unroll
+                for (int e = 0; e < EC; ++e) {
+                    // a finished episode keeps its (unused) state; the values are simply never read again
+                    h[e] = fmaf(zg[e], h[e], __fmul_rn(__fsub_rn(1.0f, zg[e]), ng[e]));
+                    sm.xh[e][lane].y = h[e];
+                }
+#pragma unroll
+                for (int pe = 0; pe < NP; ++pe) {
+                    const float2 t = tanh32x2<false>(make_float2(h[2 * pe], h[2 * pe + 1]));
+                    sm.obuf[2 * pe][lane] = t.x; sm.obuf[2 * pe + 1][lane] = t.y;
+                }
+                if constexpr (EC & 1) sm.obuf[EC - 1][lane] = tanh32_fast_t<false>(h[EC - 1]);
+                __syncwarp();
+                // lane e: logits in the contract's sequential order (as the pair { z0, z1 }), action, physics
                 bool done = false;
                 int action = 0;
                 if (alive) {
-                    float z0 = b20, z1 = b21;
-                    const float *orow = sm.obuf[lane];
-#pragma unroll 8
-                    for (int j = 0; j < HID; ++j) {
-                        const float oj = orow[j];
-                        z0 = fmaf(w2[j], oj, z0);
-                        z1 = fmaf(w2[HID + j], oj, z1);
+                    float2 z = make_float2(b20, b21);
+                    const float4 *orow = reinterpret_cast<const float4 *>(sm.obuf[lane]);
+                    const float4 *wp = reinterpret_cast<const float4 *>(sm.w2p);
+#pragma unroll
+                    for (int jq = 0; jq < HID / 4; ++jq) {
+                        const float4 o = orow[jq], wa = wp[2 * jq], wb = wp[2 * jq + 1];
+                        z = __ffma2_rn(make_float2(wa.x, wa.y), make_float2(o.x, o.x), z);
+                        z = __ffma2_rn(make_float2(wa.z, wa.w), make_float2(o.y, o.y), z);
+                        z = __ffma2_rn(make_float2(wb.x, wb.y), make_float2(o.z, o.z), z);
+                        z = __ffma2_rn(make_float2(wb.z, wb.w), make_float2(o.w, o.w), z);
                     }
+                    const float z0 = z.x, z1 = z.y;
                     action = argmax_softmax2(z0, z1);
                     done = cartpole_step(x, xd, th, thd, action);
                     ++nstep;

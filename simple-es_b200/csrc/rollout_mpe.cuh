@@ -187,7 +187,7 @@ struct SpreadEnv {
 #pragma unroll
                 for (int k = 0; k < OBS_EFF; ++k) a = __ffma2_rn(make_float2(wr[u * OBS + k], wr[u * OBS + k]), op[k], a);
                 // the skipped comm inputs are exactly 0: fmaf(w, 0, a) == a
-                const float2 h = tanh32x2<true>(a);
+                const float2 h = tanh32x2<false>(a);
 #pragma unroll
                 for (int m = 0; m < ACT; ++m) zp[m] = __ffma2_rn(make_float2(w2[m][u], w2[m][u]), h, zp[m]);
 #pragma unroll
@@ -195,7 +195,7 @@ struct SpreadEnv {
                     float as = bias[u];
 #pragma unroll
                     for (int k = 0; k < OBS_EFF; ++k) as = fmaf(wr[u * OBS + k], o[2 + i][k], as);
-                    const float hs = tanh32_fast(as);
+                    const float hs = tanh32_fast_t<false>(as);
 #pragma unroll
                     for (int m = 0; m < ACT; ++m) zs[i][m] = fmaf(w2[m][u], hs, zs[i][m]);
                 }

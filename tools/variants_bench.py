@@ -28,9 +28,31 @@ def timed(eng, gen0, sigma, parents, reps=3):
     return {"ms": best[0], "env_steps": best[1], "steps_per_s": best[1] / (best[0] * 1e-3), "best": best[2], "mean": best[3]}
 
 
+def gru_balancing_parent():
+    """A GRU policy that balances the (fully observed) pole: fc1 unit 0 = bang-bang feature, the n gate carries it,
+    z ~ 0 -- every episode runs the full 500 steps (the converged regime of the GRU rollout kernel)."""
+    mu = np.zeros(6562, np.float32)
+    W1 = mu[0:128].reshape(32, 4)
+    Wih = mu[160:160 + 3072].reshape(96, 32)
+    bih = mu[160 + 6144:160 + 6144 + 96]
+    W2 = mu[160 + 6144 + 192:160 + 6144 + 192 + 64].reshape(2, 32)
+    W1[0] = [0.0, 0.5, 10.0, 3.0]
+    Wih[64, 0] = 3.0
+    bih[32:64] = -10.0
+    W2[1, 0] = 5.0; W2[0, 0] = -5.0
+    return mu[None]
+
+
 def main():
     out = {}
     rng = np.random.default_rng(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "gru_converged":
+        eng = RolloutEngine("CartPole-v1", 4, 2, True, False, 500, 5, 4097, 4097, 2, 1, seed=0)
+        print(json.dumps({"gru_converged": timed(eng, 0, 0.02, torch.from_numpy(gru_balancing_parent()).cuda(), reps=2)}))
+        return
+    eng = RolloutEngine("CartPole-v1", 4, 2, True, False, 500, 5, 4097, 4097, 2, 1, seed=0)
+    out["gru_converged"] = timed(eng, 0, 0.02, torch.from_numpy(gru_balancing_parent()).cuda())
+    eng.close()
     # config 2: CartPole POMDP GRU, simple_evolution, P = 4097
     for label, scale, sigma in (("gru_gen0", 0.0, 1.0), ("gru_random_parent", 0.3, 0.2)):
         eng = RolloutEngine("CartPole-v1", 4, 2, True, True, 500, 5, 4097, 4097, 2, 1, seed=0)
