@@ -28,6 +28,7 @@ P_DEFAULT = 65536
 E_DEFAULT = 5
 D = 226
 FLOP_PER_STEP = 418          # 192 FMA + 34 bias adds per env step (CartPole MLP)
+FMA_LANE_OPS_PER_STEP = 640  # executed on the FP32 FMA pipe per env step: fc1 128 + fc2 64 + 32 tanh x 14
 STRATEGY = dict(name="openai_es", init_sigma=0.2, sigma_decay=0.9999, learning_rate=0.1)
 
 
@@ -260,9 +261,10 @@ def run_b200(args):
     gen_ms, k1_ms = float(t[0]), float(t[1])
     total_steps = int(n[0])
 
-    # ---------------- e2e: the same generations through the host-buffer C-ABI call (N = 1 path on each rank's own full copy)
+    # ---------------- e2e: the same generations with HOST buffers, copies inside the timed region (wall clock, max over ranks)
     e2e = None
-    if rank == 0:
+    if world == 1:
+        # the reference-facing C-ABI call: ses_generation_openai_host (H2D mu/m/v, K1-K3, D2H fitness[P] + mu/m/v + steps)
         import numpy as np
         from simple_es_b200.engine import RolloutEngine
         P = args.pop
@@ -287,6 +289,34 @@ def run_b200(args):
                "api": "ses_generation_openai_host (C ABI, pinned host buffers, synchronous)", "n_gpus": 1, "env_steps": tot,
                "generations_per_sec": args.steps / dt}
         eng2.close()
+    else:
+        # N ranks: every rank stages mu/m/v from pinned host memory, runs its shard of the generation through the
+        # public strategy API (B200Loop.strategy.step()), and reads the full fitness vector + mu/m/v back to the host
+        P = args.pop
+        pinned = lambda n_, dt: torch.empty(n_, dtype=dt).pin_memory()
+        mu_h, m_h, v_h, fit_h = pinned(D, torch.float32), pinned(D, torch.float32), pinned(D, torch.float32), pinned(P, torch.float64)
+        mu_h.copy_(s.parents[0]); m_h.copy_(s.m); v_h.copy_(s.v)
+        torch.cuda.synchronize()
+        steps0 = int(s.total_env_steps.item())
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            s.parents[0].copy_(mu_h, non_blocking=True); s.m.copy_(m_h, non_blocking=True); s.v.copy_(v_h, non_blocking=True)
+            s.step()
+            fit_h.copy_(s.fitness, non_blocking=True)
+            mu_h.copy_(s.parents[0], non_blocking=True); m_h.copy_(s.m, non_blocking=True); v_h.copy_(s.v, non_blocking=True)
+            torch.cuda.synchronize()
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        nn = torch.tensor([int(s.total_env_steps.item()) - steps0], dtype=torch.int64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(nn, op=dist.ReduceOp.SUM)
+        e2e = {"value": int(nn[0]) / float(tt[0]), "unit": "env-steps/s", "h2d_bytes_per_step": 3 * D * 4,
+               "d2h_bytes_per_step": P * 8 + 3 * D * 4,
+               "api": "B200Loop.strategy.step() per rank with pinned host staging of mu/m/v (H2D) and fitness[P] + mu/m/v (D2H), "
+                      "synchronous; bytes are per rank", "n_gpus": world, "env_steps": int(nn[0]),
+               "generations_per_sec": args.steps / float(tt[0])}
 
     if world > 1:
         s.engine.peer_check() if s.exchange == "peer" else None
@@ -308,7 +338,10 @@ def run_b200(args):
                      "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
                      "peak_source": "measured live: dependent-free FFMA microbenchmark on this GPU (MEASURED_PEAKS.json has only HBM and bf16-tensor peaks)",
                      "algorithmic": "%d FP32 FLOP per env step (SURVEY 8d) x %d env steps of rank 0 / %.3f ms in K1" % (FLOP_PER_STEP, k1_local_steps, k1_ms),
-                     "k1_share_of_step": k1_ms / gen_ms if gen_ms else None},
+                     "k1_share_of_step": k1_ms / gen_ms if gen_ms else None,
+                     "fma_pipe_frac": (k1_local_steps * FMA_LANE_OPS_PER_STEP * 2 / (k1_ms * 1e-3) / 1e12 / peak_tf) if (peak_tf and k1_ms > 0) else None,
+                     "fma_pipe_note": "share of the FP32 FMA pipe K1 keeps busy: 640 FMA-pipe lane operations per env step (the 418 algorithmic "
+                                      "FLOP count no tanh; an accurate float32 tanh costs 14 FMA-pipe operations) x 2 FLOP / measured FFMA peak"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
     }
     if world == 1 and not args.no_cpu:

@@ -689,6 +689,9 @@ __global__ void k_tanh_x2_exhaustive(uint32_t lo_bits, uint32_t hi_bits, unsigne
         const uint32_t a = __float_as_uint(y.x), b = __float_as_uint(tanh32(x));
         const uint32_t an = __float_as_uint(y.y), bn = __float_as_uint(tanh32(-x));
         bad += ((a != b) && ((a | b) << 1) != 0) + ((an != bn) && ((an | bn) << 1) != 0);
+        // the scalar form with the same NEWTON choice (odd episodes / agents)
+        const uint32_t s = __float_as_uint(tanh32_fast_t<NEWTON>(x)), sn = __float_as_uint(tanh32_fast_t<NEWTON>(-x));
+        bad += ((s != b) && ((s | b) << 1) != 0) + ((sn != bn) && ((sn | bn) << 1) != 0);
     }
     if (bad) atomicAdd(mismatches, bad);
 }
