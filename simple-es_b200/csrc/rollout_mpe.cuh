@@ -124,6 +124,9 @@ struct SpreadEnv {
     __device__ static __forceinline__ void store_quad(float4 (&w)[NQ][S], int q, int s, const float4 v) { w[q][s] = v; }
 
     template <int S>
+    __device__ static __forceinline__ void bind(State &, const float4 (&)[NQ][S], int) {}
+
+    template <int S>
     __device__ static __forceinline__ bool step(State &s, const float4 (&w)[NQ][S], int slot, const RolloutParams &, int *actions)
     {
         // observations (Scenario.observation): [vel, pos, landmarks - pos, others - pos, comm = 0], f64 -> f32

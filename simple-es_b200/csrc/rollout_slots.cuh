@@ -27,6 +27,7 @@
 //   D, NQ, STATE_DIM, N_AGENTS, UNIT_REWARD (reward == 1.0 per step: fitness = steps / E exactly)
 //   struct State;  init(State&, p, id, ep);
 //   store_quad<S>(w[NQ][S], q, s, float4)   place flat parameter quad q of slot s (an Env may permute the table)
+//   bind<S>(State&, w[NQ][S], slot)          a lane was handed an episode of `slot` (an Env may cache weights in registers)
 //   step<S>(State&, w[NQ][S], slot, p, int *actions) -> done   (also adds the step reward to State::ret)
 //   store_trace(State&, double *row)
 #pragma once
@@ -211,6 +212,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_rollout_slots(const RolloutParam
             if (my_slot >= 0) {
                 slot = my_slot; ep = my_ep; nstep = 0;
                 Env::init(st, p, sm.off_id[my_slot], my_ep);
+                Env::template bind<S>(st, sm.w, my_slot);
             }
             if (__ballot_sync(FULL, slot >= 0) == 0) break;        // queue empty and every lane idle
         }

@@ -77,7 +77,7 @@ struct ses_handle {
     // rollout launch configuration
     int lanes_used_override = 0;
     int ctas_per_sm = 0;
-    int k1_variant = 2;
+    int k1_variant = 4;
 
     int64_t launches = 0;
 };
@@ -131,8 +131,8 @@ extern "C" int ses_create(const ses_config *cfg, ses_handle **out)
     h->eff_max_step = cfg->max_step > 0 ? (cfg->max_step < env_cap ? cfg->max_step : env_cap) : env_cap;
     h->lanes_used_override = env_int("SES_ROLLOUT_LANES", 0);
     h->ctas_per_sm = env_int("SES_ROLLOUT_CTAS_PER_SM", 0);
-    h->k1_variant = env_int("SES_K1_VARIANT", 2);
-    if (h->k1_variant < 0 || h->k1_variant > 2) h->k1_variant = 2;
+    h->k1_variant = env_int("SES_K1_VARIANT", 4);
+    if (h->k1_variant < 0 || h->k1_variant > 5) h->k1_variant = 4;
 
     const int P = cfg->population;
     h->n_tiles = (P + sort_tile(SORT_ITEMS_SMALL) - 1) / sort_tile(SORT_ITEMS_SMALL);
@@ -251,10 +251,13 @@ extern "C" int ses_rollout(ses_handle *h, uint32_t generation, float sigma, cons
         if (c.eval_ep_num >= 4) {
             if (h->k1_variant == 0) return launch_slots<CartpoleMlpEnvT<0>, 8>(h, rp, need_warps, tr, st);
             if (h->k1_variant == 2) return launch_slots<CartpoleMlpEnvT<2>, 8>(h, rp, need_warps, tr, st);
+            if (h->k1_variant == 3) return launch_slots<CartpoleMlpEnvT<3>, 8>(h, rp, need_warps, tr, st);
+            if (h->k1_variant == 4) return launch_slots<CartpoleMlpEnvT<4>, 8>(h, rp, need_warps, tr, st);
+            if (h->k1_variant == 5) return launch_slots<CartpoleMlpEnvT<5>, 8>(h, rp, need_warps, tr, st);
             return launch_slots<CartpoleMlpEnvT<1>, 8>(h, rp, need_warps, tr, st);
         }
-        if (c.eval_ep_num >= 2) return launch_slots<CartpoleMlpEnvT<2>, 16>(h, rp, need_warps, tr, st);
-        return launch_slots<CartpoleMlpEnvT<2>, 32>(h, rp, need_warps, tr, st);
+        if (c.eval_ep_num >= 2) return launch_slots<CartpoleMlpEnvT<4>, 16>(h, rp, need_warps, tr, st);
+        return launch_slots<CartpoleMlpEnvT<4>, 32>(h, rp, need_warps, tr, st);
     }
     if (c.env == SES_ENV_CARTPOLE && c.gru) return launch_rollout_cartpole_gru(h->num_sms, h->ctas_per_sm, rp, tr, st, &h->launches, g_err, sizeof(g_err));
     if (c.n_agents == 2) return launch_slots<SpreadEnv<2>, 8>(h, rp, need_warps, tr, st);

@@ -90,10 +90,12 @@ def test_rollout_philox_bit_exact(twin, init_mode, pomdp, E):
 
 
 @pytest.mark.parametrize("knobs,E", [({"SES_K1_VARIANT": "0"}, 5), ({"SES_K1_VARIANT": "1"}, 5), ({"SES_K1_VARIANT": "2"}, 5),
-                                     ({"SES_K1_VARIANT": "2"}, 3), ({"SES_K1_VARIANT": "2"}, 1)])
+                                     ({"SES_K1_VARIANT": "3"}, 5), ({"SES_K1_VARIANT": "4"}, 5), ({"SES_K1_VARIANT": "5"}, 5),
+                                     ({"SES_K1_VARIANT": "4"}, 3), ({"SES_K1_VARIANT": "4"}, 1)])
 def test_rollout_k1_variants_bit_exact(twin, knobs, E, monkeypatch):
     """Every K1 code path is the same function: variant 0 (scalar FFMA, flat slot table), 1 / 2 (packed FFMA2 over
-    hidden-unit pairs, permuted slot table, with / without the Newton step of the tanh division; 2 is the default)
+    hidden-unit pairs, permuted slot table, with / without the Newton step of the tanh division), 3 / 4 / 5 (variant 2
+    with W2+b2 / W2+b2+b1 / b1 of the lane's slot held in registers; 4 is the default)
     must all reproduce the oracle bit for bit: Philox and verification (w_override) paths, ragged and 500-step
     episodes, 8 / 16 / 32 slots per warp (E = 5 / 3 / 1)."""
     for k, v in knobs.items():
