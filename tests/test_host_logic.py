@@ -71,6 +71,34 @@ def test_cli_flags_match_reference():
     assert (a.cfg_path, a.seed, a.process_num, a.generation_num, a.eval_ep_num, a.log, a.save_model_period) == ("x.yaml", 3, 2, 7, 9, True, 4)
 
 
+def test_sweep_cli_overrides_reach_the_engine_config():
+    """sweep_main.py keeps the reference's flags (sweep_main.py:33-69: generation-num 1000, --log store_false, the five
+    hyper-parameter overrides) and writes every given override into the YAML key of the same name, as change_value does
+    (sweep_main.py:16-30); keys a config does not have are not invented."""
+    import sweep_main
+    a = sweep_main.parse_args([])
+    assert (a.seed, a.process_num, a.generation_num, a.eval_ep_num, a.log, a.save_model_period) == (0, 12, 1000, 5, True, 10)
+    assert (a.init_sigma, a.sigma_decay, a.learning_rate, a.elite_num, a.offspring_num) == (None,) * 5
+    a = sweep_main.parse_args(["--cfg-path=conf/cartpole_openai.yaml", "--init-sigma=0.3", "--learning-rate=0.05",
+                               "--offspring-num=4096", "--elite-num=7", "--log"])
+    assert a.log is False
+    cfg = yaml.load(open(os.path.join(ROOT, a.cfg_path)), Loader=yaml.FullLoader)
+    before = dict(cfg["strategy"])
+    changed = sweep_main.apply_overrides(cfg, {"init_sigma": a.init_sigma, "sigma_decay": a.sigma_decay, "learning_rate": a.learning_rate,
+                                               "elite_num": a.elite_num, "offspring_num": a.offspring_num})
+    assert sorted(changed) == ["strategy.init_sigma", "strategy.learning_rate", "strategy.offspring_num"]
+    assert cfg["strategy"]["init_sigma"] == 0.3 and cfg["strategy"]["learning_rate"] == 0.05 and cfg["strategy"]["offspring_num"] == 4096
+    assert cfg["strategy"]["sigma_decay"] == before["sigma_decay"] and "elite_num" not in cfg["strategy"]
+    assert cfg["engine"]["name"] == "b200"
+    for name in os.listdir(os.path.join(ROOT, "sweep_config")):
+        sw = yaml.load(open(os.path.join(ROOT, "sweep_config", name)), Loader=yaml.FullLoader)
+        assert sw["program"] == "sweep_main.py" and sw["metric"]["name"] == "ep5_mean_reward"
+        target = yaml.load(open(os.path.join(ROOT, sw["parameters"]["cfg-path"]["value"])), Loader=yaml.FullLoader)
+        assert target["engine"]["name"] == "b200"
+        flags = {f.lstrip("-") for f, _ in sweep_main.OVERRIDES} | {f[0].lstrip("-") for f in __import__("run_es").FLAGS}
+        assert set(sw["parameters"]) <= flags
+
+
 @pytest.mark.parametrize("obs,act,gru,D", [(4, 2, False, 226), (4, 2, True, 6562), (12, 5, False, 581)])
 def test_checkpoint_roundtrip_and_reference_keys(obs, act, gru, D):
     from simple_es_b200 import checkpoint
