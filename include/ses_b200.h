@@ -26,7 +26,9 @@ extern "C" {
 
 #define SES_ABI_VERSION 1
 
-enum { SES_ENV_CARTPOLE = 0, SES_ENV_SIMPLE_SPREAD = 1 };
+/* env.name -> SES_ENV_*: "CartPole-v1" / "CartPole-v0" (same physics, TimeLimit 500 / 200: pass max_step), "simple_spread",
+ * "MountainCar-v0", "Acrobot-v1" (discrete classic control any reference config can name, envs/gym_wrapper.py:8-9) */
+enum { SES_ENV_CARTPOLE = 0, SES_ENV_SIMPLE_SPREAD = 1, SES_ENV_MOUNTAINCAR = 2, SES_ENV_ACROBOT = 3 };
 enum { SES_INIT_SHARED = 0, SES_INIT_FRESH = 1 };
 
 /* Static description of one engine instance (one per process / GPU).
@@ -34,8 +36,8 @@ enum { SES_INIT_SHARED = 0, SES_INIT_FRESH = 1 };
  * YAML (builder.py:10-75, conf/cartpole.yaml, conf/simplespread.yaml). */
 typedef struct ses_config {
     int32_t env;          /* SES_ENV_*                                   (env.name)                */
-    int32_t obs_dim;      /* network.num_state   4 | 12 (N=2) | 18 (N=3)                           */
-    int32_t act_dim;      /* network.num_action  2 | 5                                             */
+    int32_t obs_dim;      /* network.num_state   4 | 12 (N=2) | 18 (N=3) | 2 (MountainCar) | 6 (Acrobot)  */
+    int32_t act_dim;      /* network.num_action  2 | 5 | 3 | 3                                     */
     int32_t gru;          /* network.gru                                                           */
     int32_t pomdp;        /* env.pomdp: CartPole obs[1], obs[3] zeroed   (envs/gym_wrapper.py:69-77) */
     int32_t n_agents;     /* simple_spread N (reference hard-codes 2, envs/pettingzoo_wrapper.py:9) */
@@ -60,7 +62,7 @@ typedef struct ses_handle ses_handle;
 int ses_abi_version(void);
 const char *ses_last_error(void);
 
-/* D = number of policy parameters (networks/neural_network.py:12-17): 226 / 6562 / 581 / 773. */
+/* D = number of policy parameters (networks/neural_network.py:12-17): 226 / 6562 / 581 / 773 / 195 / 323. */
 int ses_param_count(int32_t obs_dim, int32_t act_dim, int32_t gru);
 
 int ses_create(const ses_config *cfg, ses_handle **out);

@@ -147,6 +147,60 @@ def golden_spread(ref, N, P, E, seed, sigma, n_trace):
                 N=np.int32(N), E=np.int32(E))
 
 
+class TracingClassic(pyref.ClassicShim):
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.log = []
+
+    def reset(self):
+        self.log.append(("reset",))
+        return super().reset()
+
+    def step(self, action):
+        out = super().step(action)
+        self.log.append((int(action["0"]), tuple(self.state), out[1]))
+        return out
+
+
+def golden_classic(ref, env_name, P, E, seed, sigma, n_trace):
+    """Reference RolloutWorker + GymEnvModel over MountainCar-v0 / Acrobot-v1 (oracle/pyref.py::ClassicShim), a fixed
+    [E, state_dim] table of initial states shared by every offspring (pool semantics)."""
+    rng = np.random.RandomState(seed)
+    sd, cap = pyref.ClassicShim.SPECS[env_name]
+    obs_dim, act = {"MountainCar-v0": (2, 3), "Acrobot-v1": (6, 3)}[env_name]
+    D = pyref.param_count(obs_dim, act, False)
+    if env_name == "MountainCar-v0":
+        init = np.stack([rng.uniform(-0.6, -0.4, size=E), np.zeros(E)], axis=1)
+    else:
+        init = rng.uniform(-0.1, 0.1, size=(E, 4))
+    W = rng.normal(0, sigma, size=(P, D)).astype(np.float32)
+    W[0] = 0.0
+    fitness = np.zeros(P)
+    steps = np.zeros(P, dtype=np.int64)
+    logs = []
+    for i in range(P):
+        model = ref.GymEnvModel(obs_dim, act, True, False)
+        set_flat(model, W[i], obs_dim, act, False)
+        env = TracingClassic(env_name, max_step=cap, init_states=init)
+        fitness[i] = ref.RolloutWorker((env, {"0": model}, E))
+        steps[i] = sum(1 for rec in env.log if rec[0] != "reset")
+        ep0 = []
+        for rec in env.log[1:]:
+            if rec[0] == "reset":
+                break
+            ep0.append(rec)
+        logs.append(ep0)
+    trace_ids = np.arange(n_trace, dtype=np.int32) + 1           # offspring 1..n_trace (0 is the all-zero policy)
+    traces = np.full((n_trace, 200, sd), np.nan)
+    tr_actions = np.full((n_trace, 200), -1, dtype=np.int32)
+    for j, i in enumerate(trace_ids):
+        for t, rec in enumerate(logs[i][:200]):
+            tr_actions[j, t] = rec[0]
+            traces[j, t] = rec[1]
+    return dict(W=W, init=init, fitness=fitness, steps=steps, trace_ids=trace_ids, traces=traces, trace_actions=tr_actions,
+                E=np.int32(E), max_step=np.int32(cap))
+
+
 def reward_vectors(P, rng):
     """Three synthetic reward vectors: tie-free floats, CartPole-like tie-heavy k/5, mixed."""
     r0 = rng.uniform(8, 500, size=P)
@@ -224,6 +278,8 @@ def main():
         "rollout_cartpole_gru_pomdp": lambda: golden_rollout(ref, True, True, 24, 3, 22, 0.7, 3),
         "rollout_spread_n2": lambda: golden_spread(ref, 2, 128, 5, 41, 1.0, 4),
         "rollout_spread_n3": lambda: golden_spread(ref, 3, 48, 3, 42, 1.0, 2),
+        "rollout_mountaincar": lambda: golden_classic(ref, "MountainCar-v0", 96, 3, 51, 3.0, 4),
+        "rollout_acrobot": lambda: golden_classic(ref, "Acrobot-v1", 64, 3, 52, 2.0, 4),
         "strategy_simple_evolution": lambda: golden_strategy(ref, "simple_evolution", 31),
         "strategy_simple_genetic": lambda: golden_strategy(ref, "simple_genetic", 32),
         "strategy_openai_es": lambda: golden_strategy(ref, "openai_es", 33),

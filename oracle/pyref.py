@@ -109,6 +109,118 @@ class CartPoleShim:
 
 
 # --------------------------------------------------------------------------------------
+# MountainCar-v0 and Acrobot-v1 (gym classic_control/mountain_car.py, acrobot.py, gym ~0.18-0.21): any reference
+# config can name them through GymWrapper (envs/gym_wrapper.py:8-9 hands the name to gym.make).  Restated from the
+# published algorithm; Python floats / numpy float64, libm sin / cos like the originals.
+# --------------------------------------------------------------------------------------
+def mountaincar_physics(state, action):
+    position, velocity = state
+    velocity += (action - 1) * 0.001 + math.cos(3 * position) * (-0.0025)
+    velocity = float(np.clip(velocity, -0.07, 0.07))
+    position += velocity
+    position = float(np.clip(position, -1.2, 0.6))
+    if position == -1.2 and velocity < 0:
+        velocity = 0
+    done = bool(position >= 0.5 and velocity >= 0)
+    return (position, float(velocity)), -1.0, done
+
+
+def _acrobot_dsdt(s_augmented):
+    m1 = m2 = l1 = 1.0
+    lc1 = lc2 = 0.5
+    I1 = I2 = 1.0
+    g = 9.8
+    pi, cos, sin = np.pi, np.cos, np.sin
+    a = s_augmented[-1]
+    theta1, theta2, dtheta1, dtheta2 = s_augmented[:-1]
+    d1 = m1 * lc1 ** 2 + m2 * (l1 ** 2 + lc2 ** 2 + 2 * l1 * lc2 * cos(theta2)) + I1 + I2
+    d2 = m2 * (lc2 ** 2 + l1 * lc2 * cos(theta2)) + I2
+    phi2 = m2 * lc2 * g * cos(theta1 + theta2 - pi / 2.)
+    phi1 = - m2 * l1 * lc2 * dtheta2 ** 2 * sin(theta2) - 2 * m2 * l1 * lc2 * dtheta2 * dtheta1 * sin(theta2) \
+        + (m1 * lc1 + m2 * l1) * g * cos(theta1 - pi / 2) + phi2
+    ddtheta2 = (a + d2 / d1 * phi1 - m2 * l1 * lc2 * dtheta1 ** 2 * sin(theta2) - phi2) / (m2 * lc2 ** 2 + I2 - d2 ** 2 / d1)
+    ddtheta1 = -(d2 * ddtheta2 + phi1) / d1
+    return np.array([dtheta1, dtheta2, ddtheta1, ddtheta2, 0.])
+
+
+def _wrap(x, m, M):
+    diff = M - m
+    while x > M:
+        x = x - diff
+    while x < m:
+        x = x + diff
+    return x
+
+
+def acrobot_physics(state, action):
+    s_augmented = np.append(np.asarray(state, dtype=np.float64), float(action - 1))     # AVAIL_TORQUE = [-1., 0., +1]
+    dt = 0.2
+    dt2 = dt / 2.0
+    y0 = s_augmented
+    k1 = _acrobot_dsdt(y0)                                   # rk4(derivs, y0, [0, dt])
+    k2 = _acrobot_dsdt(y0 + dt2 * k1)
+    k3 = _acrobot_dsdt(y0 + dt2 * k2)
+    k4 = _acrobot_dsdt(y0 + dt * k3)
+    ns = y0 + dt / 6.0 * (k1 + 2 * k2 + 2 * k3 + k4)
+    ns = [float(v) for v in ns[:4]]
+    ns[0] = _wrap(ns[0], -math.pi, math.pi)
+    ns[1] = _wrap(ns[1], -math.pi, math.pi)
+    ns[2] = min(max(ns[2], -4 * math.pi), 4 * math.pi)
+    ns[3] = min(max(ns[3], -9 * math.pi), 9 * math.pi)
+    terminal = bool(-np.cos(ns[0]) - np.cos(ns[1] + ns[0]) > 1.)
+    return tuple(ns), (-1.0 if not terminal else 0.0), terminal
+
+
+class ClassicShim:
+    """GymWrapper duck type (envs/gym_wrapper.py:7-54) over MountainCar-v0 / Acrobot-v1; `max_step` is
+    min(the config's max_step, gym's TimeLimit) as GymWrapper over a TimeLimit-wrapped env behaves."""
+    SPECS = {"MountainCar-v0": (2, 200), "Acrobot-v1": (4, 500)}
+
+    def __init__(self, name, max_step=None, init_states=None, seed=None):
+        self.name = name
+        self.state_dim, cap = self.SPECS[name]
+        self.max_step = cap if max_step in (None, "None") else min(int(max_step), cap)
+        self.curr_step = 0
+        self.init_states = None if init_states is None else np.asarray(init_states, dtype=np.float64)
+        self._reset_count = 0
+        self.rng = np.random.RandomState(seed)
+        self.state = None
+
+    def _obs(self):
+        s = self.state
+        if self.name == "MountainCar-v0":
+            return np.array(s, dtype=np.float64)
+        return np.array([np.cos(s[0]), np.sin(s[0]), np.cos(s[1]), np.sin(s[1]), s[2], s[3]], dtype=np.float64)
+
+    def reset(self):
+        self.curr_step = 0
+        if self.init_states is not None:
+            s = self.init_states[self._reset_count % len(self.init_states)]
+            self._reset_count += 1
+        elif self.name == "MountainCar-v0":
+            s = [self.rng.uniform(low=-0.6, high=-0.4), 0.0]
+        else:
+            s = self.rng.uniform(low=-0.1, high=0.1, size=(4,))
+        self.state = tuple(float(v) for v in s)
+        return {"0": {"state": self._obs()}}
+
+    def step(self, action):
+        self.curr_step += 1
+        physics = mountaincar_physics if self.name == "MountainCar-v0" else acrobot_physics
+        self.state, r, d = physics(self.state, int(action["0"]))
+        if self.curr_step >= self.max_step or d:
+            d = True
+        tr = {"state": self._obs(), "reward": r, "done": d, "info": {}}
+        return {"0": tr}, r, d, {}
+
+    def get_agent_ids(self):
+        return ["0"]
+
+    def close(self):
+        pass
+
+
+# --------------------------------------------------------------------------------------
 # PettingZoo MPE simple_spread_v2 (SURVEY.md Appendix A.2), float64 numpy like the original
 # --------------------------------------------------------------------------------------
 class SimpleSpreadShim:

@@ -15,7 +15,7 @@ _SO = os.path.join(_HERE, "_build", "libses_twin.so")
 
 def build(force=False):
     """Compile the twin with the committed Makefile (gcc only, seconds)."""
-    srcs = [os.path.join(_HERE, f) for f in ("ses_twin.c", "ses_twin_mpe.c", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("ses_twin.c", "ses_twin_mpe.c", "ses_twin_classic.c", "Makefile")]
     if not force and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs):
         return _SO
     subprocess.check_call(["make", "-s", "-C", _HERE], env={**os.environ, "CC": "/usr/bin/gcc"})
@@ -34,6 +34,8 @@ def lib():
         _lib.tw_rollout_cartpole.restype = C.c_int64
         if hasattr(_lib, "tw_rollout_mpe"):
             _lib.tw_rollout_mpe.restype = C.c_double
+        if hasattr(_lib, "tw_rollout_classic"):
+            _lib.tw_rollout_classic.restype = C.c_double
     return _lib
 
 
@@ -257,3 +259,66 @@ def population_mpe(parents, N=2, sigma=0.0, seed=0, gen=0, group=1, n_head=1, id
                             C.c_int(n_head), C.c_int(id0), C.c_int(n), C.c_int(E), C.c_int(max_cycles), _p(Wo), _p(init_a),
                             C.c_int(init_mode), _p(fit), _p(steps))
     return fit, steps
+
+
+# ---------------------------------------------------------------------------- classic control (ses_twin_classic.c)
+CLASSIC_ENVS = {"MountainCar-v0": 2, "Acrobot-v1": 3}
+
+
+def classic_dims(env):
+    """(obs, act, state_dim, time_limit) of a classic-control env name."""
+    o, a, sd, cap = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    assert lib().tw_classic_dims(CLASSIC_ENVS[env], C.byref(o), C.byref(a), C.byref(sd), C.byref(cap)) == 0
+    return o.value, a.value, sd.value, cap.value
+
+
+def sincos_full(x):
+    x = _f64(x)
+    s, c = np.empty_like(x), np.empty_like(x)
+    lib().tw_sincos_full_v(_p(x), _p(s), _p(c), C.c_int64(x.size))
+    return s, c
+
+
+def classic_step(env, state, action):
+    st = _f64(state).copy()
+    r = C.c_double()
+    done = lib().tw_classic_step(CLASSIC_ENVS[env], _p(st), int(action), C.byref(r))
+    return st, r.value, bool(done)
+
+
+def classic_init(env, seed, init_mode, gen, idx, e):
+    sd = classic_dims(env)[2]
+    st = np.zeros(sd)
+    lib().tw_classic_init(CLASSIC_ENVS[env], C.c_uint32(seed), int(init_mode), C.c_uint32(gen), C.c_uint32(idx), C.c_uint32(e), _p(st))
+    return st
+
+
+def rollout_classic(env, w, E=5, max_step=None, init=None, seed=0, init_mode=0, gen=0, idx=0, trace_steps=0):
+    """fitness, steps[, trace, actions] of one offspring."""
+    obs, act, sd, cap = classic_dims(env)
+    max_step = cap if max_step is None else min(int(max_step), cap)
+    w = _f32(w)
+    init = None if init is None else _f64(init)
+    trace = np.full((trace_steps, sd), np.nan) if trace_steps else None
+    actions = np.full(trace_steps, -1, dtype=np.int32) if trace_steps else None
+    steps = C.c_int64()
+    f = lib().tw_rollout_classic(CLASSIC_ENVS[env], _p(w), int(E), int(max_step), _p(init), C.c_uint32(seed), int(init_mode),
+                                 C.c_uint32(gen), C.c_uint32(idx), _p(trace), _p(actions), int(trace_steps), C.byref(steps))
+    if trace_steps:
+        return f, steps.value, trace, actions
+    return f, steps.value
+
+
+def population_classic(env, parents, sigma=0.0, seed=0, gen=0, group=1, n_head=1, id0=0, n=1, E=5, max_step=None,
+                       W_override=None, init=None, init_mode=0, nthreads=8):
+    obs, act, sd, cap = classic_dims(env)
+    max_step = cap if max_step is None else min(int(max_step), cap)
+    parents = _f32(parents)
+    W_override = None if W_override is None else _f32(W_override)
+    init = None if init is None else _f64(init)
+    fitness = np.zeros(n)
+    steps = np.zeros(n, dtype=np.int64)
+    lib().tw_population_classic(CLASSIC_ENVS[env], _p(parents), C.c_float(sigma), C.c_uint32(seed), C.c_uint32(gen), int(group),
+                                int(n_head), int(id0), int(n), int(E), int(max_step), _p(W_override), _p(init), int(init_mode),
+                                _p(fitness), _p(steps), int(nthreads))
+    return fitness, steps

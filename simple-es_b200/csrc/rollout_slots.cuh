@@ -195,7 +195,9 @@ __global__ void __launch_bounds__(WARPS * 32) k_rollout_slots(const RolloutParam
                 }
                 __syncwarp();
             }
-            // hand pending (slot, episode) pairs to idle lanes, in slot order
+            // hand pending (slot, episode) pairs to idle lanes, in slot order (the barrier orders the retire / refill
+            // writes of lanes < S to off_id / ep_next before every lane reads them: votes alone do not order memory)
+            __syncwarp();
             const int r = __popc(idle_mask & lt);
             int acc = 0, my_slot = -1, my_ep = 0, my_prefix = 0, my_avail = 0;
 #pragma unroll

@@ -15,6 +15,7 @@
 #include "rollout_cartpole_mlp.cuh"
 #include "rollout_cartpole_gru.cuh"
 #include "rollout_mpe.cuh"
+#include "rollout_classic.cuh"
 #include "ses_common.cuh"
 #include "update.cuh"
 
@@ -98,7 +99,13 @@ extern "C" int ses_create(const ses_config *cfg, ses_handle **out)
     if (e != cudaSuccess || ndev == 0)
         return fail("ses_create: no CUDA device (%s); this engine has no CPU fallback", cudaGetErrorString(e));
     if (cfg->device < 0 || cfg->device >= ndev) return fail("ses_create: device %d out of range (%d devices)", cfg->device, ndev);
-    if (cfg->env != SES_ENV_CARTPOLE && cfg->env != SES_ENV_SIMPLE_SPREAD) return fail("ses_create: unknown env %d", cfg->env);
+    if (cfg->env < SES_ENV_CARTPOLE || cfg->env > SES_ENV_ACROBOT) return fail("ses_create: unknown env %d", cfg->env);
+    if (cfg->env == SES_ENV_MOUNTAINCAR && (cfg->obs_dim != 2 || cfg->act_dim != 3))
+        return fail("ses_create: MountainCar-v0 needs num_state=2, num_action=3 (got %d, %d)", cfg->obs_dim, cfg->act_dim);
+    if (cfg->env == SES_ENV_ACROBOT && (cfg->obs_dim != 6 || cfg->act_dim != 3))
+        return fail("ses_create: Acrobot-v1 needs num_state=6, num_action=3 (got %d, %d)", cfg->obs_dim, cfg->act_dim);
+    if ((cfg->env == SES_ENV_MOUNTAINCAR || cfg->env == SES_ENV_ACROBOT) && (cfg->gru || cfg->pomdp))
+        return fail("ses_create: MountainCar-v0 / Acrobot-v1 run with the MLP policy and full observations only");
     if (cfg->env == SES_ENV_CARTPOLE && (cfg->obs_dim != 4 || cfg->act_dim != 2))
         return fail("ses_create: CartPole-v1 needs num_state=4, num_action=2 (got %d, %d)", cfg->obs_dim, cfg->act_dim);
     if (cfg->env == SES_ENV_SIMPLE_SPREAD) {
@@ -123,11 +130,13 @@ extern "C" int ses_create(const ses_config *cfg, ses_handle **out)
     h->D = param_count(cfg->obs_dim, cfg->act_dim, cfg->gru);
     h->NQ = (h->D + 3) / 4;
     h->DP = h->NQ * 4;
-    h->state_dim = cfg->env == SES_ENV_CARTPOLE ? 4 : 4 * cfg->n_agents;
+    h->state_dim = cfg->env == SES_ENV_SIMPLE_SPREAD ? 4 * cfg->n_agents : (cfg->env == SES_ENV_MOUNTAINCAR ? 2 : 4);
     h->num_sms = prop.multiProcessorCount;
     // gym registers CartPole-v1 with max_episode_steps=500 (TimeLimit); the wrapper's own max_step
-    // (gym_wrapper.py:37-39) can only shorten it.  simple_spread: max_cycles=25.
-    const int env_cap = cfg->env == SES_ENV_CARTPOLE ? 500 : 25;
+    // (gym_wrapper.py:37-39) can only shorten it (CartPole-v0: the caller passes max_step <= 200).
+    // simple_spread: max_cycles=25; MountainCar-v0: 200; Acrobot-v1: 500.
+    static const int caps[4] = {500, 25, 200, 500};
+    const int env_cap = caps[cfg->env];
     h->eff_max_step = cfg->max_step > 0 ? (cfg->max_step < env_cap ? cfg->max_step : env_cap) : env_cap;
     h->lanes_used_override = env_int("SES_ROLLOUT_LANES", 0);
     h->ctas_per_sm = env_int("SES_ROLLOUT_CTAS_PER_SM", 0);
@@ -201,6 +210,15 @@ static int launch_slots(ses_handle *h, RolloutParams &rp, int need_warps, bool t
     return 0;
 }
 
+// slots per warp: enough offspring to occupy 32 lanes (E >= 4: 8, E in {2,3}: 16, E = 1: 32)
+template <class Env>
+static int launch_slots_by_E(ses_handle *h, RolloutParams &rp, int need_warps, bool trace, cudaStream_t st)
+{
+    if (h->cfg.eval_ep_num >= 4) return launch_slots<Env, 8>(h, rp, need_warps, trace, st);
+    if (h->cfg.eval_ep_num >= 2) return launch_slots<Env, 16>(h, rp, need_warps, trace, st);
+    return launch_slots<Env, 32>(h, rp, need_warps, trace, st);
+}
+
 extern "C" int ses_rollout(ses_handle *h, uint32_t generation, float sigma, const float *parents_dev,
                            const float *w_override_dev, const double *init_states_dev, double *fitness_dev,
                            int64_t *steps_dev, double *trace_dev, int32_t *trace_actions_dev, int32_t n_trace,
@@ -260,6 +278,8 @@ extern "C" int ses_rollout(ses_handle *h, uint32_t generation, float sigma, cons
         return launch_slots<CartpoleMlpEnvT<4>, 32>(h, rp, need_warps, tr, st);
     }
     if (c.env == SES_ENV_CARTPOLE && c.gru) return launch_rollout_cartpole_gru(h->num_sms, h->ctas_per_sm, rp, tr, st, &h->launches, g_err, sizeof(g_err));
+    if (c.env == SES_ENV_MOUNTAINCAR) return launch_slots_by_E<MountainCarEnv>(h, rp, need_warps, tr, st);
+    if (c.env == SES_ENV_ACROBOT) return launch_slots_by_E<AcrobotEnv>(h, rp, need_warps, tr, st);
     if (c.n_agents == 2) return launch_slots<SpreadEnv<2>, 8>(h, rp, need_warps, tr, st);
     return launch_slots<SpreadEnv<3>, 8>(h, rp, need_warps, tr, st);
 }
@@ -556,13 +576,17 @@ __global__ void k_test_math(int kind, const void *in, void *out, long long n)
         static_cast<float *>(out)[i] = y;
     } else {
         const double x = static_cast<const double *>(in)[i];
-        static_cast<double *>(out)[i] = kind == 5 ? sin64(x) : cos64(x);
+        double y;
+        if (kind == 5) y = sin64(x);
+        else if (kind == 6) y = cos64(x);
+        else { double s, c; sincos64_full(x, s, c); y = kind == 8 ? s : c; }
+        static_cast<double *>(out)[i] = y;
     }
 }
 
 extern "C" int ses_test_math(int32_t kind, const void *in_dev, void *out_dev, int64_t n, void *stream)
 {
-    if (kind < 0 || kind > 7) return fail("ses_test_math: unknown kind %d", kind);
+    if (kind < 0 || kind > 9) return fail("ses_test_math: unknown kind %d", kind);
     if (n < 1) return 0;
     k_test_math<<<(unsigned)((n + 255) / 256), 256, 0, S(stream)>>>(kind, in_dev, out_dev, (long long)n);
     CU(cudaGetLastError());

@@ -16,9 +16,16 @@ import torch
 
 from . import _lib
 
-ENV_IDS = {"CartPole-v1": 0, "simple_spread": 1}
-CARTPOLE_TIME_LIMIT = 500       # gym registers CartPole-v1 with max_episode_steps=500
-SPREAD_MAX_CYCLES = 25          # simple_spread_v2 default max_cycles
+# env.name -> (SES_ENV_*, episode cap, state_dim, (num_state, num_action)); the cap is gym's TimeLimit
+# (max_episode_steps of the registered id) or simple_spread_v2's default max_cycles
+ENV_SPECS = {
+    "CartPole-v1": (0, 500, 4, (4, 2)),
+    "CartPole-v0": (0, 200, 4, (4, 2)),          # same physics, TimeLimit 200
+    "simple_spread": (1, 25, None, None),
+    "MountainCar-v0": (2, 200, 2, (2, 3)),
+    "Acrobot-v1": (3, 500, 4, (6, 3)),
+}
+ENV_IDS = {k: v[0] for k, v in ENV_SPECS.items()}
 
 
 def population_layout(strategy, offspring_num, elite_num=None):
@@ -64,8 +71,8 @@ class RolloutEngine:
                  n_parents, seed=0, init_mode="shared", n_agents=2, id_begin=0, id_end=None, device=0):
         if env_name not in ENV_IDS:
             raise ValueError(
-                "env %r is not supported by the B200 engine (CartPole-v1 and simple_spread only; Box2D, PyBullet and "
-                "Unity environments stay on the reference CPU path)" % (env_name,))
+                "env %r is not supported by the B200 engine (%s; Box2D, PyBullet and "
+                "Unity environments stay on the reference CPU path)" % (env_name, ", ".join(sorted(ENV_IDS))))
         if not torch.cuda.is_available():
             raise RuntimeError("simple-es_b200: no CUDA device; the engine has no CPU fallback")
         self.lib = _lib.load()
@@ -77,20 +84,22 @@ class RolloutEngine:
         self.env_name = env_name
         self.n_agents = int(n_agents) if env_name == "simple_spread" else 1
         ms = 0 if max_step in (None, "None") else int(max_step)
-        cap = CARTPOLE_TIME_LIMIT if env_name == "CartPole-v1" else SPREAD_MAX_CYCLES
+        _, cap, sdim, dims = ENV_SPECS[env_name]
+        if dims is not None and (int(obs_dim), int(act_dim)) != dims:
+            raise ValueError("%s needs num_state=%d, num_action=%d (got %d, %d)" % ((env_name,) + dims + (obs_dim, act_dim)))
         self.max_step = min(ms, cap) if ms > 0 else cap
-        self.state_dim = 4 if env_name == "CartPole-v1" else 4 * self.n_agents
+        self.state_dim = 4 * self.n_agents if sdim is None else sdim
         self.D = self.lib.ses_param_count(obs_dim, act_dim, int(bool(gru)))
         self.cfg = _lib.ses_config(
             env=ENV_IDS[env_name], obs_dim=obs_dim, act_dim=act_dim, gru=int(bool(gru)), pomdp=int(bool(pomdp)),
-            n_agents=self.n_agents, max_step=ms, eval_ep_num=self.E, population=self.P, group=int(group),
+            n_agents=self.n_agents, max_step=self.max_step, eval_ep_num=self.E, population=self.P, group=int(group),
             n_head=int(n_head), n_parents=int(n_parents), seed=int(seed) & 0xFFFFFFFF,
             init_mode={"shared": 0, "fresh": 1}[init_mode], id_begin=self.id_begin, id_end=self.id_end, device=device)
         h = C.c_void_p()
         _lib.check(self.lib.ses_create(C.byref(self.cfg), C.byref(h)))
         self._h = h
         # integer-key fast path of K2: CartPole fitness*E is an integer < 2^key_bits
-        if env_name == "CartPole-v1":
+        if env_name in ("CartPole-v1", "CartPole-v0"):
             self.key_bits = int(self.E * self.max_step).bit_length()
             self.key_scale = float(self.E)
         else:
@@ -248,7 +257,8 @@ class RolloutEngine:
 
     # ------------------------------------------------------------------------------ test hooks
     def test_math(self, kind, x):
-        kinds = {"tanh": 0, "sigmoid": 1, "ln": 2, "sin2pi": 3, "cos2pi": 4, "sin64": 5, "cos64": 6, "tanh_fast": 7}
+        kinds = {"tanh": 0, "sigmoid": 1, "ln": 2, "sin2pi": 3, "cos2pi": 4, "sin64": 5, "cos64": 6, "tanh_fast": 7,
+                 "sin64_full": 8, "cos64_full": 9}
         out = torch.empty_like(x)
         _lib.check(self.lib.ses_test_math(kinds[kind], _ptr(x), _ptr(out), x.numel(), self._stream()))
         return out
