@@ -66,6 +66,12 @@ def main():
         mu = torch.zeros(1, D, dtype=torch.float32, device="cuda")
         out["spread_n%d" % N] = timed(eng, 0, 0.2, mu)
         eng.close()
+    # classic control beyond CartPole (conf/mountaincar.yaml, conf/acrobot.yaml): P = 16384, random policies
+    for env, obs, act in (("MountainCar-v0", 2, 3), ("Acrobot-v1", 6, 3)):
+        eng = RolloutEngine(env, obs, act, False, False, None, 5, 16384, 16384, 1, 1, seed=0, init_mode="fresh")
+        mu = torch.zeros(1, eng.D, dtype=torch.float32, device="cuda")
+        out[env] = timed(eng, 0, 2.0, mu)
+        eng.close()
     # config 5: CartPole simple_genetic P = 2^20 (16 elites), gen-0 regime
     eng = RolloutEngine("CartPole-v1", 4, 2, False, False, 500, 5, 1 << 20, (1 << 20) // 16, 1, 16, seed=0)
     par = torch.zeros(16, 226, dtype=torch.float32, device="cuda")
