@@ -29,6 +29,7 @@ E_DEFAULT = 5
 D = 226
 FLOP_PER_STEP = 418          # 192 FMA + 34 bias adds per env step (CartPole MLP)
 FMA_LANE_OPS_PER_STEP = 640  # executed on the FP32 FMA pipe per env step: fc1 128 + fc2 64 + 32 tanh x 14
+K1_DRAM_BYTES_PER_LAUNCH = 33280   # ncu, profiles/r01_k1_v4_conv.txt (reads; no DRAM writes: results stay in L2)
 STRATEGY = dict(name="openai_es", init_sigma=0.2, sigma_decay=0.9999, learning_rate=0.1)
 
 
@@ -335,7 +336,9 @@ def run_b200(args):
         "per_gpu": value / world, "generations_per_sec": args.steps / (gen_ms * 1e-3), "env_steps": total_steps,
         "best_reward_last_gen": best, "wall_s": wall,
         "roofline": {"bound": "fp32_pipe", "kernel": "k_rollout_cartpole_mlp", "achieved": achieved_tf, "peak": peak_tf,
-                     "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
+                     "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": K1_DRAM_BYTES_PER_LAUNCH,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of K1 (profiles/r01_k1_v4_conv.txt); "
+                                       "algorithmic bytes per launch: 904 B of parameters + 16 B per offspring of results",
                      "peak_source": "measured live: dependent-free FFMA microbenchmark on this GPU (MEASURED_PEAKS.json has only HBM and bf16-tensor peaks)",
                      "algorithmic": "%d FP32 FLOP per env step (SURVEY 8d) x %d env steps of rank 0 / %.3f ms in K1" % (FLOP_PER_STEP, k1_local_steps, k1_ms),
                      "k1_share_of_step": k1_ms / gen_ms if gen_ms else None,
