@@ -158,7 +158,9 @@ struct AcrobotEnv {
     static constexpr int STATE_DIM = 4, N_AGENTS = 1;
     static constexpr bool UNIT_REWARD = false;
     static constexpr double PI = 3.141592653589793;
-    struct State { double s[4]; double ret; };
+    // sc = { sin th1, cos th1, sin th2, cos th2 } of the current state: computed once per step (terminal test) and reused
+    // by the next step's observation and first RK4 stage (same function, same argument: same bits as recomputing)
+    struct State { double s[4]; double sc[4]; double ret; };
 
     __device__ static __forceinline__ void init(State &st, const RolloutParams &p, int id, int ep)
     {
@@ -172,6 +174,8 @@ struct AcrobotEnv {
             st.s[2] = __dsub_rn(__dmul_rn(unit64(r.z), 0.2), 0.1);
             st.s[3] = __dsub_rn(__dmul_rn(unit64(r.w), 0.2), 0.1);
         }
+        sincos64_full(st.s[0], st.sc[0], st.sc[1]);
+        sincos64_full(st.s[1], st.sc[2], st.sc[3]);
         st.ret = 0.0;
     }
 
@@ -182,11 +186,12 @@ struct AcrobotEnv {
 
     // _dsdt of acrobot.py with m1 = m2 = l1 = 1, lc1 = lc2 = 0.5, I1 = I2 = 1, g = 9.8 (this translation unit is
     // compiled with -fmad=false: every operator below is one separately rounded IEEE operation, in Python's order)
-    __device__ static __forceinline__ void dsdt(const double (&y)[4], double a, double (&ds)[4])
+    template <bool CACHED>
+    __device__ static __forceinline__ void dsdt(const double (&y)[4], double a, double (&ds)[4], double sin2c = 0.0, double cos2c = 0.0)
     {
         const double theta1 = y[0], theta2 = y[1], dtheta1 = y[2], dtheta2 = y[3];
-        double sin2, cos2;
-        sincos64_full(theta2, sin2, cos2);
+        double sin2 = sin2c, cos2 = cos2c;
+        if constexpr (!CACHED) sincos64_full(theta2, sin2, cos2);
         const double d1 = ((0.25 + (1.25 + cos2)) + 1.0) + 1.0;
         const double d2 = (0.25 + 0.5 * cos2) + 1.0;
         const double phi2 = 4.9 * cos64_full((theta1 + theta2) - PI / 2.0);
@@ -209,25 +214,22 @@ struct AcrobotEnv {
     template <int S>
     __device__ static __forceinline__ bool step(State &st, const float4 (&w)[NQ][S], int slot, const RolloutParams &, int *actions)
     {
-        double s0, c0, s1, c1;
-        sincos64_full(st.s[0], s0, c0);
-        sincos64_full(st.s[1], s1, c1);
-        const float o[OBS] = {(float)c0, (float)s0, (float)c1, (float)s1, (float)st.s[2], (float)st.s[3]};
+        const float o[OBS] = {(float)st.sc[1], (float)st.sc[0], (float)st.sc[3], (float)st.sc[2], (float)st.s[2], (float)st.s[3]};
         const int act = mlp_policy_flat<OBS, ACT, NQ, S>(w, slot, o);
         actions[0] = act;
         const double torque = (double)(act - 1);
         const double dt = 0.2, dt2 = 0.2 / 2.0;
         double k1[4], k2[4], k3[4], k4[4], y[4];
-        dsdt(st.s, torque, k1);
+        dsdt<true>(st.s, torque, k1, st.sc[2], st.sc[3]);
 #pragma unroll
         for (int i = 0; i < 4; ++i) y[i] = st.s[i] + dt2 * k1[i];
-        dsdt(y, torque, k2);
+        dsdt<false>(y, torque, k2);
 #pragma unroll
         for (int i = 0; i < 4; ++i) y[i] = st.s[i] + dt2 * k2[i];
-        dsdt(y, torque, k3);
+        dsdt<false>(y, torque, k3);
 #pragma unroll
         for (int i = 0; i < 4; ++i) y[i] = st.s[i] + dt * k3[i];
-        dsdt(y, torque, k4);
+        dsdt<false>(y, torque, k4);
         double ns[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) ns[i] = st.s[i] + (dt / 6.0) * (((k1[i] + 2.0 * k2[i]) + 2.0 * k3[i]) + k4[i]);
@@ -237,7 +239,9 @@ struct AcrobotEnv {
         ns[3] = clip64(ns[3], -9.0 * PI, 9.0 * PI);
 #pragma unroll
         for (int i = 0; i < 4; ++i) st.s[i] = ns[i];
-        const bool terminal = (-cos64_full(ns[0]) - cos64_full(ns[1] + ns[0])) > 1.0;
+        sincos64_full(ns[0], st.sc[0], st.sc[1]);
+        sincos64_full(ns[1], st.sc[2], st.sc[3]);
+        const bool terminal = (-st.sc[1] - cos64_full(ns[1] + ns[0])) > 1.0;
         st.ret = st.ret + (terminal ? 0.0 : -1.0);
         return terminal;
     }

@@ -50,6 +50,11 @@ def main():
         eng = RolloutEngine("CartPole-v1", 4, 2, True, False, 500, 5, 4097, 4097, 2, 1, seed=0)
         print(json.dumps({"gru_converged": timed(eng, 0, 0.02, torch.from_numpy(gru_balancing_parent()).cuda(), reps=2)}))
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "classic":
+        for env, obs, act in (("MountainCar-v0", 2, 3), ("Acrobot-v1", 6, 3)):
+            eng = RolloutEngine(env, obs, act, False, False, None, 5, 16384, 16384, 1, 1, seed=0, init_mode="fresh")
+            print(json.dumps({env: timed(eng, 0, 2.0, torch.zeros(1, eng.D, dtype=torch.float32, device="cuda"), reps=2)}))
+        return
     eng = RolloutEngine("CartPole-v1", 4, 2, True, False, 500, 5, 4097, 4097, 2, 1, seed=0)
     out["gru_converged"] = timed(eng, 0, 0.02, torch.from_numpy(gru_balancing_parent()).cuda())
     eng.close()
