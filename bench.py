@@ -255,10 +255,14 @@ def run_b200(args):
     best = float(s.best_reward().item())
     launches = eng.launches - launches_before
     t = torch.tensor([gen_ms, k1_ms], dtype=torch.float64, device=dev)
+    tsum = t.clone()
     n = torch.tensor([local_steps], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         dist.all_reduce(n, op=dist.ReduceOp.SUM)
+    # load balance over ranks: K1 time of the slowest rank vs the mean
+    k1_rank_ms = {"max": float(t[1]) / args.steps, "mean": float(tsum[1]) / world / args.steps}
     gen_ms, k1_ms = float(t[0]), float(t[1])
     total_steps = int(n[0])
 
@@ -334,7 +338,7 @@ def run_b200(args):
         "vs_baseline": None, "dtype": "f32 policy / f64 physics", "data": "synthetic",
         "config": workload_config(args, world),
         "per_gpu": value / world, "generations_per_sec": args.steps / (gen_ms * 1e-3), "env_steps": total_steps,
-        "best_reward_last_gen": best, "wall_s": wall,
+        "best_reward_last_gen": best, "wall_s": wall, "k1_ms_per_generation_over_ranks": k1_rank_ms,
         "roofline": {"bound": "fp32_pipe", "kernel": "k_rollout_cartpole_mlp", "achieved": achieved_tf, "peak": peak_tf,
                      "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": K1_DRAM_BYTES_PER_LAUNCH,
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of K1 (profiles/r01_k1_v4_conv.txt); "

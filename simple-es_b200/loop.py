@@ -59,6 +59,17 @@ class B200Loop(BaseESLoop):
         self.net_cfg = net_cfg
         self.strategy = STRATEGIES[strat_cfg["name"]](strat_cfg, env_cfg, net_cfg, eval_ep_num, seed, device, self.engine_cfg)
         self.history = []
+        self.start_ep = 0
+        # engine.init_from: a reference-format checkpoint (GymEnvModel.state_dict(), e.g. a saved ep_<n>.pt) as the initial
+        # mu / elites; engine.resume: a resume_ep_<n>.pt written by this loop (engine.save_state: true) -- continues the
+        # run bit for bit (parameters, sigma, Adam state, generation counter)
+        if self.engine_cfg.get("init_from"):
+            sd = torch.load(self.engine_cfg["init_from"], map_location="cpu")
+            self.strategy.load_elite(checkpoint.state_dict_to_flat(sd, int(net_cfg["num_state"]), int(net_cfg["num_action"]), bool(net_cfg["gru"])))
+        if self.engine_cfg.get("resume"):
+            st = torch.load(self.engine_cfg["resume"], map_location="cpu")
+            self.strategy.load_state(st)
+            self.start_ep = int(st["generation"])
 
         self.save_dir = save_dir
         if self.rank == 0 and self.save_model_period and self.save_model_period > 0:
@@ -77,7 +88,7 @@ class B200Loop(BaseESLoop):
 
     def run(self):
         s = self.strategy
-        ep_num = 0
+        ep_num = self.start_ep
         for _ in range(self.generation_num):
             start = time.time()
             ep_num += 1
@@ -97,4 +108,6 @@ class B200Loop(BaseESLoop):
                                  "curr_sigma": curr_sigma})
             if self.rank == 0 and self.save_model_period and self.save_model_period > 0 and ep_num % self.save_model_period == 0:
                 torch.save(self.elite_state_dict(), self.save_dir + "/saved_models" + f"/ep_{ep_num}.pt")
+                if self.engine_cfg.get("save_state"):
+                    torch.save(s.state(), self.save_dir + "/saved_models" + f"/resume_ep_{ep_num}.pt")
         return self.history

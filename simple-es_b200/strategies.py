@@ -71,6 +71,39 @@ class _Base:
         self._rollout_and_exchange()
         return self.engine.rank_desc(self.fitness, shaped=shaped, order=self.order)
 
+    # ------------------------------------------------------------------ resume
+    def state(self):
+        """Everything needed to continue this run bit for bit: the reference cannot resume (it only saves the elite's
+        state_dict, loop.py:101-104); populations are functions of (parents, sigma, seed, generation) here."""
+        st = {"strategy": self.name, "generation": self.generation, "sigma": self.sigma, "curr_sigma": self.curr_sigma,
+              "parents": self.parents.detach().cpu().clone(), "population": self.P}
+        for k in ("m", "v"):
+            if hasattr(self, k):
+                st[k] = getattr(self, k).detach().cpu().clone()
+        if hasattr(self, "t"):
+            st["t"] = self.t
+        return st
+
+    def load_state(self, st):
+        if st.get("strategy") != self.name or tuple(st["parents"].shape) != tuple(self.parents.shape):
+            raise ValueError("resume state is for strategy %r with parents %s; this run is %r with parents %s"
+                             % (st.get("strategy"), tuple(st["parents"].shape), self.name, tuple(self.parents.shape)))
+        self.generation = int(st["generation"])
+        self.sigma, self.curr_sigma = float(st["sigma"]), float(st["curr_sigma"])
+        self.parents.copy_(st["parents"])
+        for k in ("m", "v"):
+            if hasattr(self, k):
+                getattr(self, k).copy_(st[k])
+        if hasattr(self, "t"):
+            self.t = int(st["t"])
+
+    def load_elite(self, flat):
+        """Start from a saved policy (a reference-format checkpoint): every parent row := flat."""
+        flat = torch.as_tensor(flat, dtype=torch.float32).reshape(-1)
+        if flat.numel() != self.D:
+            raise ValueError("checkpoint has %d parameters, the configured network has %d" % (flat.numel(), self.D))
+        self.parents.copy_(flat.to(self.parents.device).expand_as(self.parents))
+
     def best_reward(self):
         """max(rewards) (offspring_strategies.py:113,235,381) -- a 0-d device tensor."""
         return self.fitness[self.order[0].long()]

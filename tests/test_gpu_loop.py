@@ -92,3 +92,34 @@ def test_readme_claim_gru_solves_pomdp_cartpole():
         if best >= 500.0:
             break
     assert best >= 500.0, best
+
+
+@pytest.mark.parametrize("conf,over", [("cartpole_openai.yaml", dict(offspring_num=512)), ("cartpole.yaml", dict(offspring_num=300)),
+                                       ("cartpole_genetic.yaml", dict(offspring_num=256, elite_num=8))])
+def test_resume_continues_bit_for_bit(tmp_path, conf, over):
+    """engine.save_state / engine.resume: 6 generations in one run == 3 generations, stop, resume, 3 more (parameters,
+    sigma, Adam state, generation counter, fitness of the last generation); engine.init_from starts from a
+    reference-format checkpoint."""
+    from simple_es_b200.loop import B200Loop
+    cfg = _cfg(conf, **over)
+    full = B200Loop(cfg, 6, 1, 3, save_model_period=0, seed=7, quiet=True)
+    full.run()
+    cfg_a = _cfg(conf, **over); cfg_a["engine"]["save_state"] = True
+    a = B200Loop(cfg_a, 3, 1, 3, save_model_period=3, seed=7, quiet=True, save_dir=str(tmp_path / "a"))
+    a.run()
+    cfg_b = _cfg(conf, **over); cfg_b["engine"]["resume"] = str(tmp_path / "a" / "saved_models" / "resume_ep_3.pt")
+    b = B200Loop(cfg_b, 3, 1, 3, save_model_period=0, seed=7, quiet=True)
+    hist = b.run()
+    assert [h[0] for h in hist] == [4, 5, 6]
+    sf, sb = full.strategy, b.strategy
+    assert torch.equal(sf.parents, sb.parents) and torch.equal(sf.fitness, sb.fitness) and torch.equal(sf.order, sb.order)
+    assert sf.sigma == sb.sigma and sf.curr_sigma == sb.curr_sigma and sf.generation == sb.generation == 6
+    if hasattr(sf, "m"):
+        assert torch.equal(sf.m, sb.m) and torch.equal(sf.v, sb.v) and sf.t == sb.t
+    # init_from: the elite saved by run `a` becomes every parent row of a new run
+    cfg_c = _cfg(conf, **over); cfg_c["engine"]["init_from"] = str(tmp_path / "a" / "saved_models" / "ep_3.pt")
+    c = B200Loop(cfg_c, 1, 1, 3, save_model_period=0, seed=7, quiet=True)
+    assert all(torch.equal(row, a.strategy.elite_flat()) for row in c.strategy.parents)
+    wrong = _cfg("cartpole_pomdp_gru.yaml", offspring_num=64); wrong["engine"]["resume"] = cfg_b["engine"]["resume"]
+    with pytest.raises(ValueError, match="resume state"):
+        B200Loop(wrong, 1, 1, 3, save_model_period=0, seed=7, quiet=True)
