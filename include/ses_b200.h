@@ -92,7 +92,8 @@ int ses_rollout(ses_handle *h, uint32_t generation, float sigma, const float *pa
  * rank shaping (offspring_strategies.py:392-398).
  *   fitness_dev [n] f64 -> order_dev [n] i32 (order[0] = best); shaped_dev optional [n] f64.
  *   key_bits: 0 = sort the full float64 key; k>0 = caller guarantees fitness*key_scale is an
- *   integer in [0, 2^k) (CartPole: total steps), which needs k/8 radix passes instead of 8. */
+ *   integer of magnitude < 2^k (CartPole: total steps; MountainCar / Acrobot: minus the total steps),
+ *   which needs ceil((k+1)/8) radix passes instead of 8. */
 int ses_rank_desc(ses_handle *h, const double *fitness_dev, int32_t n, int32_t key_bits, double key_scale,
                   int32_t *order_dev, double *shaped_dev, void *stream);
 

@@ -6,8 +6,9 @@
 // Tie order is pinned: descending fitness, ties by DESCENDING index, which
 // equals np.flip(np.argsort(r, kind="stable")).  Implementation: the input is presented in
 // reverse index order with keys that ascend when fitness descends, then sorted with a STABLE
-// least-significant-digit radix sort (8-bit digits; 8 passes for a full float64 key, ceil(k/8)
-// when the caller bounds the key to k bits, e.g. CartPole's integer step totals).
+// least-significant-digit radix sort (8-bit digits; 8 passes for a full float64 key, ceil((k+1)/8)
+// when the caller bounds fitness*scale to an integer of magnitude < 2^k, e.g. CartPole's step totals or the
+// negative step totals of MountainCar / Acrobot).
 // HBM-trivial (<= 12 MB at P = 2^20); what matters is launch count and stability.
 #pragma once
 #include "ses_common.cuh"
@@ -35,8 +36,9 @@ __global__ void k_sort_init(const double *__restrict__ fitness, int n, int key_b
         const unsigned long long asc = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
         k = ~asc;
     } else {
-        const unsigned long long v = (unsigned long long)__double2ll_rn(__dmul_rn(f, key_scale));
-        k = ((1ull << key_bits) - 1ull) - v;
+        // integer key in (-2^key_bits, 2^key_bits), biased to [1, 2^(key_bits+1))
+        const long long v = __double2ll_rn(__dmul_rn(f, key_scale)) + (1ll << key_bits);
+        k = ((2ull << key_bits) - 1ull) - (unsigned long long)v;
     }
     keys[p] = k;
     vals[p] = i;

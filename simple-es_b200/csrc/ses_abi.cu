@@ -387,10 +387,10 @@ extern "C" int ses_rank_desc(ses_handle *h, const double *fitness_dev, int32_t n
     if (!h) return fail("ses_rank_desc: null handle");
     if (!fitness_dev || !order_dev) return fail("ses_rank_desc: null buffer");
     if (n < 1 || n > h->cfg.population) return fail("ses_rank_desc: n=%d outside (0, population=%d]", n, h->cfg.population);
-    if (key_bits < 0 || key_bits > 62) return fail("ses_rank_desc: key_bits must be in [0, 62]");
+    if (key_bits < 0 || key_bits > 61) return fail("ses_rank_desc: key_bits must be in [0, 61]");
     CU(cudaSetDevice(h->cfg.device));
     cudaStream_t st = S(stream);
-    const int passes = key_bits == 0 ? 8 : (key_bits + 7) / 8;
+    const int passes = key_bits == 0 ? 8 : (key_bits + 1 + 7) / 8;      // integer keys carry one bias bit (sign)
     const bool small = n <= (1 << 18);
     const int tile = sort_tile(small ? SORT_ITEMS_SMALL : SORT_ITEMS_LARGE);
     const int tiles = (n + tile - 1) / tile;

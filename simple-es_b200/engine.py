@@ -99,7 +99,8 @@ class RolloutEngine:
         _lib.check(self.lib.ses_create(C.byref(self.cfg), C.byref(h)))
         self._h = h
         # integer-key fast path of K2: CartPole fitness*E is an integer < 2^key_bits
-        if env_name in ("CartPole-v1", "CartPole-v0"):
+        # (CartPole: +1 per step; MountainCar / Acrobot: -1 or 0 per step => |fitness * E| <= E * max_step)
+        if env_name != "simple_spread":
             self.key_bits = int(self.E * self.max_step).bit_length()
             self.key_scale = float(self.E)
         else:

@@ -77,6 +77,21 @@ def test_rollout_classic_verification_mode_matches_reference(twin, golden, env):
         assert np.array_equal(trace[i, :L], tr[:L])                 # vs the twin: bit-exact states
 
 
+@pytest.mark.parametrize("n,E,max_step", [(1200, 5, 200), (65536, 3, 500), (4097, 32, 500)])
+def test_rank_desc_integer_key_path_with_negative_fitness(twin, n, E, max_step):
+    """K2's integer-key fast path (2 radix passes instead of 8) on the negative step totals of MountainCar / Acrobot:
+    same permutation as the full float64 sort and as the oracle, ties by descending index."""
+    rng = np.random.default_rng(n)
+    totals = -rng.integers(0, E * max_step + 1, n)                   # heavy ties
+    fit = totals.astype(np.float64) / E
+    eng = _engine("Acrobot-v1", population=n, group=n, eval_ep_num=E, max_step=max_step)
+    assert eng.key_bits == int(E * max_step).bit_length() and eng.key_scale == float(E)
+    fast = eng.rank_desc(_cuda(fit)).cpu().numpy()
+    full = eng.rank_desc(_cuda(fit), full_key=True).cpu().numpy()
+    want = twin.rank_desc(fit)
+    assert np.array_equal(fast, want) and np.array_equal(full, want)
+
+
 def test_cartpole_v0_is_cartpole_with_a_200_step_limit(twin):
     from simple_es_b200.engine import RolloutEngine
     P, E, D = 512, 5, 226
