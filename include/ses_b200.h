@@ -54,7 +54,9 @@ typedef struct ses_config {
     int32_t id_begin;     /* this handle's slice of the population (multi-GPU sharding)            */
     int32_t id_end;
     int32_t device;       /* CUDA device ordinal                                                   */
-    int32_t reserved[7];
+    int32_t antithetic;   /* opt-in, not in the reference: perturbed offspring of a group come in  */
+                          /* mirrored pairs (+eps, -eps) sharing one Philox counter; 0 = off       */
+    int32_t reserved[6];
 } ses_config;
 
 typedef struct ses_handle ses_handle;

@@ -282,7 +282,7 @@ static void *classic_worker(void *arg)
             int id = jb->id0 + j;
             if (jb->W_override) memcpy(w, jb->W_override + (size_t)j * jb->D, sizeof(float) * (size_t)jb->D);
             else tw_perturb(jb->parents + (size_t)(id / jb->group) * jb->D, jb->D, jb->sigma, jb->seed, jb->gen, (uint32_t)id,
-                            (id % jb->group) >= jb->n_head, w);
+                            (id % jb->group) - jb->n_head + 1, w);
             jb->fitness[j] = tw_rollout_classic(jb->env, w, jb->E, jb->max_step, jb->init, jb->seed, jb->init_mode, jb->gen,
                                                 (uint32_t)id, NULL, NULL, 0, &jb->steps[j]);
         }

@@ -263,7 +263,7 @@ TW_EXPORT void tw_population_mpe(const float *parents, int N, float sigma, uint3
     for (int j = 0; j < n; ++j) {
         int id = id0 + j;
         if (W_override) memcpy(w, W_override + (size_t)j * D, sizeof(float) * (size_t)D);
-        else tw_perturb(parents + (size_t)(id / group) * D, D, sigma, seed, gen, (uint32_t)id, (id % group) >= n_head, w);
+        else tw_perturb(parents + (size_t)(id / group) * D, D, sigma, seed, gen, (uint32_t)id, (id % group) - n_head + 1, w);
         fitness[j] = tw_rollout_mpe(w, N, E, max_cycles, init, seed, init_mode, gen, (uint32_t)id, NULL, NULL, 0, &steps[j]);
     }
     free(w);

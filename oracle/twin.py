@@ -53,6 +53,11 @@ def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
+def set_antithetic(on):
+    """Process-wide switch of the oracle's mirrored-sampling mode (engine.antithetic); tests reset it to False."""
+    lib().tw_set_antithetic(int(bool(on)))
+
+
 # ---------------------------------------------------------------------------- math hooks
 def philox(ctr, key):
     ctr = np.ascontiguousarray(ctr, dtype=np.uint32)

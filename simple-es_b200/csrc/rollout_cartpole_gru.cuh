@@ -81,9 +81,11 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_rollout_cartpole_gru(const Ro
             const float *prow = p.w_override ? p.w_override + (size_t)(id - p.id_begin) * GRU_D
                                              : p.parents + (size_t)p.layout.parent(id) * GRU_D;
             const bool pert = p.w_override ? false : p.layout.perturbed(id);
+            float sg;
+            const uint32_t nid = p.layout.noise_id(id, sg);
             for (int q = lane; q < GRU_NQ; q += 32) {
                 // 6562 = 4*1640 + 2 and every block boundary is a multiple of 4 except the very end
-                const float4 w = offspring_quad(prow, GRU_D, q, pert, p.sigma, p.seed, (uint32_t)id, p.gen);
+                const float4 w = offspring_quad(prow, GRU_D, q, pert, __fmul_rn(p.sigma, sg), p.seed, nid, p.gen);
                 const int d = 4 * q;
                 if (d >= GO_WIH && d < GO_WHH) {
                     const int o = d - GO_WIH; gru_store_gate_quad<EC>(sm, 0, o >> 5, o & 31, w);

@@ -188,8 +188,10 @@ __global__ void __launch_bounds__(WARPS * 32) k_rollout_slots(const RolloutParam
                         wq.z = d + 2 < D ? row[d + 2] : 0.0f;
                         wq.w = d + 3 < D ? row[d + 3] : 0.0f;
                     } else {
+                        float sg;
+                        const uint32_t nid = p.layout.noise_id(id, sg);
                         wq = offspring_quad(p.parents + (size_t)p.layout.parent(id) * D, D, q,
-                                            p.layout.perturbed(id), p.sigma, p.seed, (uint32_t)id, p.gen);
+                                            p.layout.perturbed(id), __fmul_rn(p.sigma, sg), p.seed, nid, p.gen);
                     }
                     Env::template store_quad<S>(sm.w, q, s, wq);
                 }

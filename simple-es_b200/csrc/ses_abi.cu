@@ -117,6 +117,7 @@ extern "C" int ses_create(const ses_config *cfg, ses_handle **out)
     if (cfg->eval_ep_num < 1 || cfg->eval_ep_num > 32) return fail("ses_create: eval_ep_num must be in [1, 32] (got %d)", cfg->eval_ep_num);
     if (cfg->population < 2) return fail("ses_create: population must be >= 2");
     if (cfg->group < 1 || cfg->n_head < 0 || cfg->n_parents < 1) return fail("ses_create: bad population layout");
+    if (cfg->antithetic != 0 && cfg->antithetic != 1) return fail("ses_create: antithetic must be 0 or 1");
     if (cfg->id_begin < 0 || cfg->id_end > cfg->population || cfg->id_begin > cfg->id_end) return fail("ses_create: bad slice [%d, %d)", cfg->id_begin, cfg->id_end);
     if ((cfg->population - 1) / cfg->group >= cfg->n_parents) return fail("ses_create: layout needs %d parents, table has %d", (cfg->population - 1) / cfg->group + 1, cfg->n_parents);
 
@@ -241,7 +242,7 @@ extern "C" int ses_rollout(ses_handle *h, uint32_t generation, float sigma, cons
     rp.fitness = fitness_dev; rp.steps = reinterpret_cast<long long *>(steps_dev);
     rp.trace = trace_dev; rp.trace_actions = trace_actions_dev; rp.work_counter = h->work_counter;
     rp.sigma = sigma; rp.seed = c.seed; rp.gen = generation;
-    rp.layout.group = c.group; rp.layout.n_head = c.n_head;
+    rp.layout.group = c.group; rp.layout.n_head = c.n_head; rp.layout.antithetic = c.antithetic;
     rp.id_begin = c.id_begin; rp.id_end = c.id_end;
     rp.E = c.eval_ep_num; rp.max_step = h->eff_max_step; rp.pomdp = c.pomdp; rp.init_mode = c.init_mode;
     rp.n_trace = n_trace; rp.slots_cap = 0; rp.lanes_used = 32; rp.n_agents = c.n_agents;
@@ -435,7 +436,7 @@ extern "C" int ses_update_openai(ses_handle *h, uint32_t generation, const doubl
     CU(cudaSetDevice(h->cfg.device));
     cudaStream_t st = S(stream);
     const int P = h->cfg.population;
-    Layout lay{h->cfg.group, h->cfg.n_head};
+    Layout lay{h->cfg.group, h->cfg.n_head, h->cfg.antithetic};
     // levels 0+1 of the gradient: all groups here, or -- with peers attached -- this rank's share of the groups,
     // each row stored into every peer's table over NVLink, then the flag barrier
     const bool shard = h->peer_world > 1 && h->xbuf && !eps_override_dev;
@@ -472,7 +473,7 @@ extern "C" int ses_materialize(ses_handle *h, uint32_t generation, float sigma, 
     if ((!parents_dev && !w_override_dev) || !ids_dev || !out_dev) return fail("ses_materialize: null buffer");
     if (n < 1) return 0;
     CU(cudaSetDevice(h->cfg.device));
-    Layout lay{h->cfg.group, h->cfg.n_head};
+    Layout lay{h->cfg.group, h->cfg.n_head, h->cfg.antithetic};
     const int t = n * h->NQ;
     k_materialize<<<(t + 255) / 256, 256, 0, S(stream)>>>(parents_dev, w_override_dev, h->cfg.id_begin, h->D, h->NQ, sigma, h->cfg.seed,
                                                           generation, lay, ids_dev, n, out_dev);
@@ -489,7 +490,7 @@ extern "C" int ses_update_elite_mean(ses_handle *h, uint32_t generation, float s
     if ((!parents_dev && !w_override_dev) || !order_dev || !mu_out_dev) return fail("ses_update_elite_mean: null buffer");
     if (k < 1 || k > h->cfg.population) return fail("ses_update_elite_mean: k=%d out of range", k);
     CU(cudaSetDevice(h->cfg.device));
-    Layout lay{h->cfg.group, h->cfg.n_head};
+    Layout lay{h->cfg.group, h->cfg.n_head, h->cfg.antithetic};
     k_elite_mean<<<(h->NQ + 63) / 64, 64, 0, S(stream)>>>(parents_dev, w_override_dev, h->cfg.id_begin, h->D, h->NQ, sigma, h->cfg.seed,
                                                           generation, lay, order_dev, k, mu_out_dev);
     h->launches += 1;

@@ -50,7 +50,10 @@ __global__ void __launch_bounds__(GB1 * GQC) k_grad_partial(const double *__rest
                 e.w = d + 3 < D ? row[d + 3] : 0.0f;
             } else {
                 if (!layout.perturbed(j)) continue;           // eps == 0 (offspring_strategies.py:302-308)
-                e = normal4(seed, (uint32_t)q, (uint32_t)j, gen);
+                float sg;
+                const uint32_t nid = layout.noise_id(j, sg);
+                e = normal4(seed, (uint32_t)q, nid, gen);
+                e.x = __fmul_rn(e.x, sg); e.y = __fmul_rn(e.y, sg); e.z = __fmul_rn(e.z, sg); e.w = __fmul_rn(e.w, sg);
             }
             const double f = shaped[j];
             a0 = fma((double)e.x, f, a0);
@@ -113,7 +116,8 @@ __global__ void __launch_bounds__(256) k_materialize(const float *__restrict__ p
         w.z = d + 2 < D ? row[d + 2] : 0.0f;
         w.w = d + 3 < D ? row[d + 3] : 0.0f;
     } else {
-        w = offspring_quad(parents + (size_t)layout.parent(id) * D, D, q, layout.perturbed(id), sigma, seed, (uint32_t)id, gen);
+        { float sg; const uint32_t nid = layout.noise_id(id, sg);
+              w = offspring_quad(parents + (size_t)layout.parent(id) * D, D, q, layout.perturbed(id), __fmul_rn(sigma, sg), seed, nid, gen); }
     }
     float *o = out + (size_t)j * D + 4 * q;
     const int d = 4 * q;
@@ -142,7 +146,8 @@ __global__ void __launch_bounds__(64) k_elite_mean(const float *__restrict__ par
             w.z = d + 2 < D ? row[d + 2] : 0.0f;
             w.w = d + 3 < D ? row[d + 3] : 0.0f;
         } else {
-            w = offspring_quad(parents + (size_t)layout.parent(id) * D, D, q, layout.perturbed(id), sigma, seed, (uint32_t)id, gen);
+            { float sg; const uint32_t nid = layout.noise_id(id, sg);
+              w = offspring_quad(parents + (size_t)layout.parent(id) * D, D, q, layout.perturbed(id), __fmul_rn(sigma, sg), seed, nid, gen); }
         }
         if (e == 0) acc = w;
         else {

@@ -68,7 +68,7 @@ class RolloutEngine:
     """One engine instance == one ses_handle == one GPU's slice of the population."""
 
     def __init__(self, env_name, obs_dim, act_dim, gru, pomdp, max_step, eval_ep_num, population, group, n_head,
-                 n_parents, seed=0, init_mode="shared", n_agents=2, id_begin=0, id_end=None, device=0):
+                 n_parents, seed=0, init_mode="shared", n_agents=2, id_begin=0, id_end=None, device=0, antithetic=False):
         if env_name not in ENV_IDS:
             raise ValueError(
                 "env %r is not supported by the B200 engine (%s; Box2D, PyBullet and "
@@ -94,7 +94,8 @@ class RolloutEngine:
             env=ENV_IDS[env_name], obs_dim=obs_dim, act_dim=act_dim, gru=int(bool(gru)), pomdp=int(bool(pomdp)),
             n_agents=self.n_agents, max_step=self.max_step, eval_ep_num=self.E, population=self.P, group=int(group),
             n_head=int(n_head), n_parents=int(n_parents), seed=int(seed) & 0xFFFFFFFF,
-            init_mode={"shared": 0, "fresh": 1}[init_mode], id_begin=self.id_begin, id_end=self.id_end, device=device)
+            init_mode={"shared": 0, "fresh": 1}[init_mode], id_begin=self.id_begin, id_end=self.id_end, device=device,
+            antithetic=int(bool(antithetic)))
         h = C.c_void_p()
         _lib.check(self.lib.ses_create(C.byref(self.cfg), C.byref(h)))
         self._h = h

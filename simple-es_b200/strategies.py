@@ -30,7 +30,7 @@ class _Base:
             name, int(network_cfg["num_state"]), int(network_cfg["num_action"]), bool(network_cfg["gru"]),
             bool(env_cfg.get("pomdp", False)), env_cfg.get("max_step"), eval_ep_num, self.P, group, n_head, n_par,
             seed=seed, init_mode=engine_cfg.get("init_states", "shared"), n_agents=int(engine_cfg.get("n_agents", 2)),
-            id_begin=self.lo, id_end=self.hi, device=device)
+            id_begin=self.lo, id_end=self.hi, device=device, antithetic=bool(engine_cfg.get("antithetic", False)))
         self.D = self.engine.D
         dev = self.engine.device
         self.parents = torch.zeros(n_par, self.D, dtype=torch.float32, device=dev)   # network.zero_init() (loop.py:31)

@@ -324,6 +324,46 @@ def test_generation_openai_host_matches_twin_composition(twin):
         sigma *= 0.999
 
 
+# ------------------------------------------------------------------------------------- opt-in: antithetic sampling
+@pytest.mark.parametrize("strategy,n,k,gru", [("openai_es", 1025, None, False), ("simple_genetic", 1000, 8, False), ("simple_evolution", 300, 10, True)])
+def test_antithetic_sampling_bit_exact_and_mirrored(twin, strategy, n, k, gru):
+    """engine.antithetic (not in the reference): the perturbed offspring of a group come in (+eps, -eps) pairs.  K1, the
+    materialiser and the openai_es gradient re-derive the same mirrored noise as the oracle, bit for bit; with a zero
+    parent the two members of a pair are exact negatives of each other."""
+    from simple_es_b200.engine import population_layout
+    P, group, n_head, n_par = population_layout(strategy, n, k)
+    Dn = 6562 if gru else D
+    eng = _engine(population=P, group=group, n_head=n_head, n_parents=n_par, gru=gru, seed=17, antithetic=True)
+    rng = np.random.default_rng(1)
+    parents = rng.normal(0, 0.3, (n_par, Dn)).astype(np.float32)
+    twin.set_antithetic(True)
+    try:
+        ids = np.arange(P, dtype=np.int32)
+        got = eng.materialize(5, 0.7, _cuda(parents), _cuda(ids)).cpu().numpy()
+        want = twin.materialize(parents, 0.7, 17, 5, group, n_head, ids)
+        assert np.array_equal(got, want)
+        zero = eng.materialize(5, 0.7, _cuda(np.zeros_like(parents)), _cuda(ids)).cpu().numpy()
+        for g0 in range(0, P, group):
+            pert = zero[g0 + n_head:g0 + group]
+            m = (pert.shape[0] // 2) * 2
+            assert np.array_equal(pert[0:m:2], -pert[1:m:2]) and np.any(pert[0] != 0)
+        fit, steps = eng.rollout(5, 0.7, _cuda(parents))
+        tf, ts = twin.population_cartpole(parents, gru=gru, sigma=0.7, seed=17, gen=5, group=group, n_head=n_head, n=P, E=5, nthreads=8)
+        assert np.array_equal(steps.cpu().numpy(), ts) and np.array_equal(fit.cpu().numpy(), tf)
+        if strategy == "openai_es":
+            order, shaped = eng.rank_desc(fit, shaped=True)
+            mu = _cuda(parents[0].copy()); m_ = torch.zeros(Dn, device="cuda"); v_ = torch.zeros(Dn, device="cuda")
+            gout = torch.zeros(Dn, device="cuda")
+            eng.update_openai(5, 0.7, 0.1, 1, shaped, mu, m_, v_, grad_out=gout)
+            g = twin.grad_openai(twin.centered_rank(twin.rank_desc(tf)), Dn, 17, 5, group, n_head, -(0.1 / (P * 0.7)))
+            assert np.array_equal(gout.cpu().numpy(), g)
+    finally:
+        twin.set_antithetic(False)
+    # and the switch really changes the population
+    plain = _engine(population=P, group=group, n_head=n_head, n_parents=n_par, gru=gru, seed=17)
+    assert not np.array_equal(plain.materialize(5, 0.7, _cuda(parents), _cuda(ids)).cpu().numpy(), got)
+
+
 # ------------------------------------------------------------------------------------- K1: GRU policy (BASELINE config 2)
 DG = 6562
 

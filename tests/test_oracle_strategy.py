@@ -116,3 +116,20 @@ def test_strategy_port_replays_reference(golden, name):
             np.testing.assert_allclose(s.mu, g["mu_after_%d" % gen], rtol=1e-6, atol=1e-7)
     if name != "openai_es":
         assert np.array_equal(pop, g["pop_final"])
+
+
+def test_twin_antithetic_pairs_are_mirrored(twin):
+    """Opt-in mirrored sampling of the oracle: offspring (n_head + 2k, n_head + 2k + 1) of a group use +eps / -eps of one
+    Philox counter; unperturbed heads and the default mode are unaffected."""
+    D, P, n_head = 226, 64, 2
+    zero = np.zeros((1, D), np.float32)
+    ids = np.arange(P, dtype=np.int32)
+    plain = twin.materialize(zero, 1.0, 3, 7, P, n_head, ids)
+    twin.set_antithetic(True)
+    try:
+        anti = twin.materialize(zero, 1.0, 3, 7, P, n_head, ids)
+    finally:
+        twin.set_antithetic(False)
+    assert np.all(anti[:n_head] == 0) and np.array_equal(anti[n_head::2], plain[n_head::2])
+    assert np.array_equal(anti[n_head + 1::2], -anti[n_head::2])
+    assert np.array_equal(twin.materialize(zero, 1.0, 3, 7, P, n_head, ids), plain)
