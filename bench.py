@@ -185,7 +185,8 @@ def run_reference(args):
 def workload_config(args, world):
     return {"workload": "CartPole-v1 MLP(4-32-2, D=226) openai_es pop=%d eval_ep_num=%d max_step=500 "
                         "(BASELINE configs[2]; conf/cartpole_openai.yaml)" % (args.pop, E_DEFAULT),
-            "population": args.pop, "eval_ep_num": E_DEFAULT, "strategy": STRATEGY, "parallelism": "pop-shard x%d" % world, "fitness_exchange": (args.exchange if world > 1 else "local"),
+            "population": args.pop, "eval_ep_num": E_DEFAULT, "strategy": STRATEGY,
+            "parallelism": "pop-shard x%d (%s)" % (world, args.shard if world > 1 else "single"), "fitness_exchange": (args.exchange if world > 1 else "local"),
             "init_states": "shared [E] table (reference mp.Pool semantics)",
             "l2": "flushed between timed generations (256 MiB write); the hot path itself reads 904 B of parameters per generation"}
 
@@ -206,7 +207,7 @@ def run_b200(args):
     config = {"env": {"name": "CartPole-v1", "max_step": 500, "pomdp": False},
               "network": {"name": "gym_model", "num_state": 4, "num_action": 2, "discrete_action": True, "gru": False},
               "strategy": dict(STRATEGY, offspring_num=args.pop),
-              "engine": {"name": "b200", "fitness_exchange": args.exchange}}
+              "engine": {"name": "b200", "fitness_exchange": args.exchange, "shard": args.shard}}
     loop = B200Loop(config, args.steps + args.warmup, 1, E_DEFAULT, log=False, save_model_period=0, seed=0, device=local, quiet=True)
     s = loop.strategy
     eng = s.engine
@@ -236,10 +237,7 @@ def run_b200(args):
         s.fitness = s._fit[s.generation & 1]
         e.rollout(s.generation, s.sigma, s.parents, fitness=s.fitness, steps=s.steps)
         ev[k][1].record()
-        if s.exchange == "peer":
-            e.peer_barrier()
-        elif s.exchange == "nccl":
-            sdist.exchange_fitness(s.fitness, s.lo, s.hi)
+        s.exchange_fitness()
         e.rank_desc(s.fitness, shaped=True, order=s.order, shaped_out=s.shaped)
         s.t += 1
         e.update_openai(s.generation, s.sigma, s.lr, s.t, s.shaped, s.parents.view(-1), s.m, s.v)
@@ -383,6 +381,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--exchange", default=os.environ.get("SES_FITNESS_EXCHANGE", "peer"), choices=["peer", "nccl"],
                     help="N > 1: fitness exchange fused into K1 over NVLink peer memory (default) or an NCCL all-gather")
+    ap.add_argument("--shard", default="cyclic", choices=["cyclic", "contiguous"],
+                    help="N > 1: block-cyclic (default) or contiguous offspring-id ranges per rank")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

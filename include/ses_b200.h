@@ -56,7 +56,11 @@ typedef struct ses_config {
     int32_t device;       /* CUDA device ordinal                                                   */
     int32_t antithetic;   /* opt-in, not in the reference: perturbed offspring of a group come in  */
                           /* mirrored pairs (+eps, -eps) sharing one Philox counter; 0 = off       */
-    int32_t reserved[6];
+    int32_t shard_block;  /* 0: this handle owns the contiguous ids [id_begin, id_end); B > 0: block-cyclic   */
+    int32_t shard_rank;   /* sharding -- blocks of B consecutive ids are dealt round robin to shard_world    */
+    int32_t shard_world;  /* handles, this one owns blocks b with b % shard_world == shard_rank (id_begin = 0, */
+                          /* id_end = population); w_override rows / traces are in local order               */
+    int32_t reserved[3];
 } ses_config;
 
 typedef struct ses_handle ses_handle;

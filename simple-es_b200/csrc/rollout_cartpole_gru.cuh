@@ -73,12 +73,14 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_rollout_cartpole_gru(const Ro
         // ---------------------------------------------------------------- next offspring
         int id = 0;
         if (lane == 0) id = atomicAdd(p.work_counter, 1);
-        id = __shfl_sync(FULL, id, 0) + p.id_begin;
-        if (id >= p.id_end) break;
+        id = __shfl_sync(FULL, id, 0);
+        if (id >= p.shard.n_local) break;
+        const int local_idx = id;
+        id = p.shard.local_to_id(local_idx);
         __syncwarp();
         // weights: flat quad q -> shared memory (big matrices tiled, the rest in flat order)
         {
-            const float *prow = p.w_override ? p.w_override + (size_t)(id - p.id_begin) * GRU_D
+            const float *prow = p.w_override ? p.w_override + (size_t)local_idx * GRU_D
                                              : p.parents + (size_t)p.layout.parent(id) * GRU_D;
             const bool pert = p.w_override ? false : p.layout.perturbed(id);
             float sg;
@@ -225,7 +227,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_rollout_cartpole_gru(const Ro
                     ++nstep;
                     if (nstep >= p.max_step) done = true;
                     if constexpr (TRACE) {
-                        const int local = id - p.id_begin;
+                        const int local = local_idx;
                         if (e0 + lane == 0 && local < p.n_trace && nstep <= 200) {
                             double *t = p.trace + ((size_t)local * 200 + (nstep - 1)) * 4;
                             t[0] = x; t[1] = xd; t[2] = th; t[3] = thd;
@@ -266,7 +268,7 @@ static int launch_rollout_cartpole_gru_ec(int num_sms, int ctas_per_sm, const Ro
         return -1;
     }
     if (ctas_per_sm > 0 && ctas_per_sm < per_sm) per_sm = ctas_per_sm;
-    const int n_local = rp.id_end - rp.id_begin;
+    const int n_local = rp.shard.n_local;
     int grid = per_sm * num_sms;
     const int need = (n_local + WARPS - 1) / WARPS;
     if (grid > need) grid = need;

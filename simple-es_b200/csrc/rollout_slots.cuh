@@ -51,7 +51,7 @@ struct RolloutParams {
     uint32_t seed;
     uint32_t gen;
     Layout layout;
-    int id_begin, id_end;
+    Shard shard;                 // this rank's slice: local index (work queue) <-> global offspring id
     int E;
     int max_step;
     int pomdp;
@@ -160,13 +160,13 @@ __global__ void __launch_bounds__(WARPS * 32) k_rollout_slots(const RolloutParam
             if (want > 0 && more) {
                 int base = 0;
                 if (lane == 0) base = atomicAdd(p.work_counter, want);
-                base = __shfl_sync(FULL, base, 0) + p.id_begin;
-                if (base + want >= p.id_end) more = false;
-                const int got = max(0, min(want, p.id_end - base));
+                base = __shfl_sync(FULL, base, 0);                 // local index of the first new offspring
+                if (base + want >= p.shard.n_local) more = false;
+                const int got = max(0, min(want, p.shard.n_local - base));
                 const int my_rank = __popc(empty_mask & lt);       // rank of this lane's slot among the empty ones
                 const bool fill = ((empty_mask >> lane) & 1u) && my_rank < got;
                 if (fill) {
-                    sm.off_id[lane] = base + my_rank;
+                    sm.off_id[lane] = p.shard.local_to_id(base + my_rank);
                     sm.ep_next[lane] = 0;
                     sm.ep_done[lane] = 0;
                     sm.steps[lane] = 0;
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_rollout_slots(const RolloutParam
                     const int id = sm.off_id[s];
                     float4 wq;
                     if (p.w_override) {
-                        const float *row = p.w_override + (size_t)(id - p.id_begin) * D;
+                        const float *row = p.w_override + (size_t)p.shard.id_to_local(id) * D;
                         const int d = 4 * q;
                         wq.x = row[d];
                         wq.y = d + 1 < D ? row[d + 1] : 0.0f;
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_rollout_slots(const RolloutParam
             ++nstep;                                               // gym_wrapper.py:33 / pettingzoo_wrapper.py:34
             if (nstep >= p.max_step) done = true;                  // gym_wrapper.py:37-39, TimeLimit / max_cycles
             if constexpr (TRACE) {
-                const int local = sm.off_id[slot] - p.id_begin;
+                const int local = p.shard.id_to_local(sm.off_id[slot]);
                 if (ep == 0 && local < p.n_trace && nstep <= 200) {
                     Env::store_trace(st, p.trace + ((size_t)local * 200 + (nstep - 1)) * Env::STATE_DIM);
 #pragma unroll

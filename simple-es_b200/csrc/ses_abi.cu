@@ -51,6 +51,7 @@ extern "C" int ses_param_count(int32_t obs, int32_t act, int32_t gru) { return p
 struct ses_handle {
     ses_config cfg;
     int D, NQ, DP;
+    Shard shard;
     int state_dim;
     int num_sms;
     int eff_max_step;
@@ -119,6 +120,10 @@ extern "C" int ses_create(const ses_config *cfg, ses_handle **out)
     if (cfg->group < 1 || cfg->n_head < 0 || cfg->n_parents < 1) return fail("ses_create: bad population layout");
     if (cfg->antithetic != 0 && cfg->antithetic != 1) return fail("ses_create: antithetic must be 0 or 1");
     if (cfg->id_begin < 0 || cfg->id_end > cfg->population || cfg->id_begin > cfg->id_end) return fail("ses_create: bad slice [%d, %d)", cfg->id_begin, cfg->id_end);
+    if (cfg->shard_block < 0 || (cfg->shard_block > 0 && (cfg->shard_world < 1 || cfg->shard_rank < 0 || cfg->shard_rank >= cfg->shard_world)))
+        return fail("ses_create: bad block-cyclic shard (block %d, rank %d of %d)", cfg->shard_block, cfg->shard_rank, cfg->shard_world);
+    if (cfg->shard_block > 0 && (cfg->id_begin != 0 || cfg->id_end != cfg->population))
+        return fail("ses_create: a block-cyclic shard needs id_begin = 0 and id_end = population");
     if ((cfg->population - 1) / cfg->group >= cfg->n_parents) return fail("ses_create: layout needs %d parents, table has %d", (cfg->population - 1) / cfg->group + 1, cfg->n_parents);
 
     CU(cudaSetDevice(cfg->device));
@@ -129,6 +134,16 @@ extern "C" int ses_create(const ses_config *cfg, ses_handle **out)
     ses_handle *h = new ses_handle();
     h->cfg = *cfg;
     h->D = param_count(cfg->obs_dim, cfg->act_dim, cfg->gru);
+    h->shard.id_begin = cfg->id_begin; h->shard.block = cfg->shard_block; h->shard.rank = cfg->shard_rank; h->shard.world = cfg->shard_world;
+    if (cfg->shard_block > 0) {
+        // ids owned: full blocks b = rank, rank + world, ... plus the part of the last (partial) block below P
+        const long long B = cfg->shard_block, W = cfg->shard_world, Pn = cfg->population;
+        long long n = 0;
+        for (long long b = cfg->shard_rank; b * B < Pn; b += W) n += (b + 1) * B <= Pn ? B : Pn - b * B;
+        h->shard.n_local = (int)n;
+    } else {
+        h->shard.n_local = cfg->id_end - cfg->id_begin;
+    }
     h->NQ = (h->D + 3) / 4;
     h->DP = h->NQ * 4;
     h->state_dim = cfg->env == SES_ENV_SIMPLE_SPREAD ? 4 * cfg->n_agents : (cfg->env == SES_ENV_MOUNTAINCAR ? 2 : 4);
@@ -230,7 +245,7 @@ extern "C" int ses_rollout(ses_handle *h, uint32_t generation, float sigma, cons
     if (!parents_dev && !w_override_dev) return fail("ses_rollout: need parents_dev or w_override_dev");
     if (n_trace > 0 && (!trace_dev || !trace_actions_dev)) return fail("ses_rollout: n_trace > 0 needs trace buffers");
     const ses_config &c = h->cfg;
-    const int n_local = c.id_end - c.id_begin;
+    const int n_local = h->shard.n_local;
     if (n_local == 0) return 0;
     if (n_trace > n_local) n_trace = n_local;
     CU(cudaSetDevice(c.device));
@@ -243,7 +258,7 @@ extern "C" int ses_rollout(ses_handle *h, uint32_t generation, float sigma, cons
     rp.trace = trace_dev; rp.trace_actions = trace_actions_dev; rp.work_counter = h->work_counter;
     rp.sigma = sigma; rp.seed = c.seed; rp.gen = generation;
     rp.layout.group = c.group; rp.layout.n_head = c.n_head; rp.layout.antithetic = c.antithetic;
-    rp.id_begin = c.id_begin; rp.id_end = c.id_end;
+    rp.shard = h->shard;
     rp.E = c.eval_ep_num; rp.max_step = h->eff_max_step; rp.pomdp = c.pomdp; rp.init_mode = c.init_mode;
     rp.n_trace = n_trace; rp.slots_cap = 0; rp.lanes_used = 32; rp.n_agents = c.n_agents;
     rp.total_steps = h->step_counter;
@@ -475,7 +490,7 @@ extern "C" int ses_materialize(ses_handle *h, uint32_t generation, float sigma, 
     CU(cudaSetDevice(h->cfg.device));
     Layout lay{h->cfg.group, h->cfg.n_head, h->cfg.antithetic};
     const int t = n * h->NQ;
-    k_materialize<<<(t + 255) / 256, 256, 0, S(stream)>>>(parents_dev, w_override_dev, h->cfg.id_begin, h->D, h->NQ, sigma, h->cfg.seed,
+    k_materialize<<<(t + 255) / 256, 256, 0, S(stream)>>>(parents_dev, w_override_dev, h->shard, h->D, h->NQ, sigma, h->cfg.seed,
                                                           generation, lay, ids_dev, n, out_dev);
     h->launches += 1;
     CU(cudaGetLastError());
@@ -491,7 +506,7 @@ extern "C" int ses_update_elite_mean(ses_handle *h, uint32_t generation, float s
     if (k < 1 || k > h->cfg.population) return fail("ses_update_elite_mean: k=%d out of range", k);
     CU(cudaSetDevice(h->cfg.device));
     Layout lay{h->cfg.group, h->cfg.n_head, h->cfg.antithetic};
-    k_elite_mean<<<(h->NQ + 63) / 64, 64, 0, S(stream)>>>(parents_dev, w_override_dev, h->cfg.id_begin, h->D, h->NQ, sigma, h->cfg.seed,
+    k_elite_mean<<<(h->NQ + 63) / 64, 64, 0, S(stream)>>>(parents_dev, w_override_dev, h->shard, h->D, h->NQ, sigma, h->cfg.seed,
                                                           generation, lay, order_dev, k, mu_out_dev);
     h->launches += 1;
     CU(cudaGetLastError());
@@ -508,7 +523,7 @@ extern "C" int ses_generation_openai_host(ses_handle *h, uint32_t generation, fl
     if (!h) return fail("ses_generation_openai_host: null handle");
     const ses_config &c = h->cfg;
     const int P = c.population;
-    if (c.id_begin != 0 || c.id_end != P) return fail("ses_generation_openai_host: needs a single-slice handle");
+    if (h->shard.n_local != P) return fail("ses_generation_openai_host: needs a single-slice handle");
     if (c.n_parents != 1) return fail("ses_generation_openai_host: openai_es has one parent (mu)");
     if (!mu_host || !m_host || !v_host || !fitness_host || !total_steps_host) return fail("ses_generation_openai_host: null buffer");
     CU(cudaSetDevice(c.device));

@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256) k_grad_final_adam(const double *__restric
 
 // weights of selected offspring: out[j][D] = parent(ids[j]) + sigma * eps(gen, ids[j])
 __global__ void __launch_bounds__(256) k_materialize(const float *__restrict__ parents, const float *__restrict__ w_override,
-                                                     int id_begin, int D, int NQ, float sigma, uint32_t seed, uint32_t gen,
+                                                     Shard shard, int D, int NQ, float sigma, uint32_t seed, uint32_t gen,
                                                      Layout layout, const int *__restrict__ ids, int n, float *__restrict__ out)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(256) k_materialize(const float *__restrict__ p
     const int id = ids[j];
     float4 w;
     if (w_override) {
-        const float *row = w_override + (size_t)(id - id_begin) * D;
+        const float *row = w_override + (size_t)shard.id_to_local(id) * D;
         const int d = 4 * q;
         w.x = d + 0 < D ? row[d + 0] : 0.0f;
         w.y = d + 1 < D ? row[d + 1] : 0.0f;
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) k_materialize(const float *__restrict__ p
 }
 
 // simple_evolution: float32 running sum of the k best in rank order, then / k
-__global__ void __launch_bounds__(64) k_elite_mean(const float *__restrict__ parents, const float *__restrict__ w_override, int id_begin,
+__global__ void __launch_bounds__(64) k_elite_mean(const float *__restrict__ parents, const float *__restrict__ w_override, Shard shard,
                                                    int D, int NQ, float sigma, uint32_t seed, uint32_t gen, Layout layout,
                                                    const int *__restrict__ order, int k, float *__restrict__ mu_out)
 {
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(64) k_elite_mean(const float *__restrict__ par
         const int id = order[e];
         float4 w;
         if (w_override) {
-            const float *row = w_override + (size_t)(id - id_begin) * D;
+            const float *row = w_override + (size_t)shard.id_to_local(id) * D;
             const int d = 4 * q;
             w.x = d + 0 < D ? row[d + 0] : 0.0f;
             w.y = d + 1 < D ? row[d + 1] : 0.0f;

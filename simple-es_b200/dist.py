@@ -1,6 +1,7 @@
 """Population sharding across ranks (one process per GPU).
 
-The population shards by contiguous offspring-id ranges (engine.shard_bounds); the only exchange of
+The population shards block-cyclically (engine.owned_ids; default) or by contiguous offspring-id ranges
+(engine.shard_bounds); the only exchange of
 a generation is the fitness vector (P float64 = 512 kB at P = 65536).  Every rank then ranks and
 updates redundantly from identical inputs and identical Philox seeds, so parameters never travel.
 Replaces the reference's only "distribution": multiprocessing.Pool.map over pickled
@@ -45,6 +46,17 @@ def exchange_fitness(fitness, lo, hi):
         fitness[:lo].zero_()
         fitness[hi:].zero_()
         dist.all_reduce(fitness, op=dist.ReduceOp.SUM)
+    return fitness
+
+
+def exchange_fitness_masked(fitness, not_mine):
+    """The same for a non-contiguous (block-cyclic) slice: `not_mine` is a bool mask of the entries other ranks own.
+    all_reduce(SUM) of the vector with those entries zeroed -- exact, every entry has exactly one non-zero contributor."""
+    rank, ws = world()
+    if ws == 1:
+        return fitness
+    fitness.masked_fill_(not_mine, 0.0)
+    dist.all_reduce(fitness, op=dist.ReduceOp.SUM)
     return fitness
 
 

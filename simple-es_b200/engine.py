@@ -51,6 +51,19 @@ def shard_bounds(P, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def cyclic_block(P, world):
+    """Block size of the block-cyclic sharding: small enough that every rank gets >= 8 blocks, at most 256 ids."""
+    return max(1, min(256, int(P) // (8 * int(world))))
+
+
+def owned_ids(P, rank, world, block):
+    """Global offspring ids of `rank` under block-cyclic sharding, in local (work-queue) order -- the host-side mirror
+    of `Shard::local_to_id` (csrc/ses_common.cuh)."""
+    blocks = np.arange(rank, (P + block - 1) // block, world, dtype=np.int64)
+    ids = (blocks[:, None] * block + np.arange(block, dtype=np.int64)[None, :]).reshape(-1)
+    return ids[ids < P]
+
+
 def _ptr(t):
     if t is None:
         return None
@@ -68,7 +81,9 @@ class RolloutEngine:
     """One engine instance == one ses_handle == one GPU's slice of the population."""
 
     def __init__(self, env_name, obs_dim, act_dim, gru, pomdp, max_step, eval_ep_num, population, group, n_head,
-                 n_parents, seed=0, init_mode="shared", n_agents=2, id_begin=0, id_end=None, device=0, antithetic=False):
+                 n_parents, seed=0, init_mode="shared", n_agents=2, id_begin=0, id_end=None, device=0, antithetic=False,
+                 shard=None):
+        """`shard` = (rank, world, block): block-cyclic slice instead of the contiguous [id_begin, id_end)."""
         if env_name not in ENV_IDS:
             raise ValueError(
                 "env %r is not supported by the B200 engine (%s; Box2D, PyBullet and "
@@ -80,6 +95,9 @@ class RolloutEngine:
         self.P = int(population)
         self.id_begin = int(id_begin)
         self.id_end = self.P if id_end is None else int(id_end)
+        self.shard = None if shard is None else tuple(int(x) for x in shard)
+        if self.shard is not None and (self.id_begin, self.id_end) != (0, self.P):
+            raise ValueError("a block-cyclic shard covers the whole population: leave id_begin / id_end at their defaults")
         self.E = int(eval_ep_num)
         self.env_name = env_name
         self.n_agents = int(n_agents) if env_name == "simple_spread" else 1
@@ -95,7 +113,8 @@ class RolloutEngine:
             n_agents=self.n_agents, max_step=self.max_step, eval_ep_num=self.E, population=self.P, group=int(group),
             n_head=int(n_head), n_parents=int(n_parents), seed=int(seed) & 0xFFFFFFFF,
             init_mode={"shared": 0, "fresh": 1}[init_mode], id_begin=self.id_begin, id_end=self.id_end, device=device,
-            antithetic=int(bool(antithetic)))
+            antithetic=int(bool(antithetic)), shard_block=self.shard[2] if self.shard else 0,
+            shard_rank=self.shard[0] if self.shard else 0, shard_world=self.shard[1] if self.shard else 0)
         h = C.c_void_p()
         _lib.check(self.lib.ses_create(C.byref(self.cfg), C.byref(h)))
         self._h = h
@@ -133,6 +152,8 @@ class RolloutEngine:
 
     @property
     def n_local(self):
+        if self.shard is not None:
+            return int(owned_ids(self.P, *self.shard).size)
         return self.id_end - self.id_begin
 
     @property

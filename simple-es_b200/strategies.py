@@ -9,7 +9,7 @@ generation: K1 rollout of this rank's slice, fitness exchange, K2 rank, K3 updat
 import torch
 
 from . import dist as sdist
-from .engine import RolloutEngine, population_layout, shard_bounds
+from .engine import RolloutEngine, cyclic_block, owned_ids, population_layout, shard_bounds
 
 
 class _Base:
@@ -25,12 +25,20 @@ class _Base:
         self.k = int(strategy_cfg.get("elite_num", 1))
         self.P, group, n_head, n_par = population_layout(self.name, self.n, self.k)
         self.lo, self.hi = shard_bounds(self.P, rank, ws)
+        # engine.shard: "cyclic" (default with several ranks: blocks of <= 256 consecutive ids dealt round robin, so that
+        # ranks stay balanced when neighbouring offspring behave alike -- simple_genetic keeps each elite's offspring
+        # together) or "contiguous" (one id range per rank)
+        mode = engine_cfg.get("shard", "cyclic") if ws > 1 else "contiguous"
+        if mode not in ("cyclic", "contiguous"):
+            raise ValueError("engine.shard must be 'cyclic' or 'contiguous'")
+        self.shard = (rank, ws, cyclic_block(self.P, ws)) if mode == "cyclic" else None
         name = env_cfg["name"]
         self.engine = RolloutEngine(
             name, int(network_cfg["num_state"]), int(network_cfg["num_action"]), bool(network_cfg["gru"]),
             bool(env_cfg.get("pomdp", False)), env_cfg.get("max_step"), eval_ep_num, self.P, group, n_head, n_par,
             seed=seed, init_mode=engine_cfg.get("init_states", "shared"), n_agents=int(engine_cfg.get("n_agents", 2)),
-            id_begin=self.lo, id_end=self.hi, device=device, antithetic=bool(engine_cfg.get("antithetic", False)))
+            id_begin=0 if self.shard else self.lo, id_end=None if self.shard else self.hi, device=device,
+            antithetic=bool(engine_cfg.get("antithetic", False)), shard=self.shard)
         self.D = self.engine.D
         dev = self.engine.device
         self.parents = torch.zeros(n_par, self.D, dtype=torch.float32, device=dev)   # network.zero_init() (loop.py:31)
@@ -50,6 +58,10 @@ class _Base:
             self._fit = [torch.zeros(self.P, dtype=torch.float64, device=dev)] * 2
         else:
             raise ValueError("engine.fitness_exchange must be 'peer' or 'nccl'")
+        if self.shard and self.exchange == "nccl":
+            mask = torch.ones(self.P, dtype=torch.bool)
+            mask[torch.from_numpy(owned_ids(self.P, *self.shard))] = False
+            self._not_mine = mask.to(dev)
         self.fitness = self._fit[0]
         self.steps = torch.zeros(self.P, dtype=torch.int64, device=dev)
         self.order = torch.empty(self.P, dtype=torch.int32, device=dev)
@@ -62,10 +74,17 @@ class _Base:
         e = self.engine
         self.fitness = self._fit[self.generation & 1]
         e.rollout(self.generation, self.sigma, self.parents, fitness=self.fitness, steps=self.steps)
+        self.exchange_fitness()
+
+    def exchange_fitness(self):
+        """After K1: make the full fitness vector visible on every rank."""
         if self.exchange == "peer":
-            e.peer_barrier()
+            self.engine.peer_barrier()                 # the values were stored into every peer's buffer by K1 itself
         elif self.exchange == "nccl":
-            sdist.exchange_fitness(self.fitness, self.lo, self.hi)
+            if self.shard:
+                sdist.exchange_fitness_masked(self.fitness, self._not_mine)
+            else:
+                sdist.exchange_fitness(self.fitness, self.lo, self.hi)
 
     def _rollout_and_rank(self, shaped=False):
         self._rollout_and_exchange()

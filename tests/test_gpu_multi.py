@@ -13,7 +13,7 @@ torch = pytest.importorskip("torch")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, strategy, exchange, q):
+def _worker(rank, world, port, strategy, exchange, q, shard="cyclic"):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     import yaml
@@ -22,6 +22,7 @@ def _worker(rank, world, port, strategy, exchange, q):
                     Loader=yaml.FullLoader)
     cfg["strategy"]["offspring_num"] = 6000 if strategy == "openai_es" else 3000     # evolution: P = 3001 (ragged shards)
     cfg["engine"]["fitness_exchange"] = exchange
+    cfg["engine"]["shard"] = shard
     loop = B200Loop(cfg, 4, 1, 5, save_model_period=0, seed=3, quiet=True)
     for _ in range(4):
         loop.strategy.step()
@@ -47,13 +48,15 @@ def _single(strategy):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("strategy,exchange", [("openai_es", "nccl"), ("simple_evolution", "nccl"), ("openai_es", "peer"), ("simple_evolution", "peer")])
-def test_two_rank_run_equals_single_gpu(strategy, exchange):
+@pytest.mark.parametrize("strategy,exchange,shard", [("openai_es", "nccl", "cyclic"), ("simple_evolution", "nccl", "cyclic"),
+                                                     ("openai_es", "peer", "cyclic"), ("simple_evolution", "peer", "cyclic"),
+                                                     ("openai_es", "nccl", "contiguous"), ("simple_evolution", "peer", "contiguous")])
+def test_two_rank_run_equals_single_gpu(strategy, exchange, shard):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29700 + (os.getpid() % 200) + (7 if exchange == "peer" else 0) + (13 if strategy == "openai_es" else 0)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, strategy, exchange, q)) for r in range(2)]
+    port = 29700 + (os.getpid() % 200) + (7 if exchange == "peer" else 0) + (13 if strategy == "openai_es" else 0) + (29 if shard == "cyclic" else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, strategy, exchange, q, shard)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted((q.get(timeout=300) for _ in procs), key=lambda t: t[0])

@@ -324,6 +324,36 @@ def test_generation_openai_host_matches_twin_composition(twin):
         sigma *= 0.999
 
 
+# ------------------------------------------------------------------------------------- block-cyclic sharding
+@pytest.mark.parametrize("env,obs,act,gru,P,world", [("CartPole-v1", 4, 2, False, 3001, 2), ("CartPole-v1", 4, 2, True, 301, 3),
+                                                     ("simple_spread", 12, 5, False, 1000, 8), ("Acrobot-v1", 6, 3, False, 777, 2)])
+def test_block_cyclic_shards_reproduce_the_whole_population(twin, env, obs, act, gru, P, world):
+    """The ranks' block-cyclic slices (engine.owned_ids / Shard::local_to_id) together give exactly the fitness vector
+    of one engine rolling out everything; verification-mode weights and traces are addressed in local order."""
+    from simple_es_b200.engine import cyclic_block, owned_ids
+    kw = dict(env_name=env, obs_dim=obs, act_dim=act, gru=gru, population=P, group=P, n_head=1, eval_ep_num=3, seed=8,
+              max_step=None, init_mode="fresh")
+    whole = _engine(**kw)
+    rng = np.random.default_rng(2)
+    mu = rng.normal(0, 0.4, (1, whole.D)).astype(np.float32)
+    fit1, steps1 = whole.rollout(2, 0.9, _cuda(mu))
+    B = cyclic_block(P, world)
+    fit = torch.full((P,), float("nan"), dtype=torch.float64, device="cuda"); steps = torch.full((P,), -1, dtype=torch.int64, device="cuda")
+    for r in range(world):
+        eng = _engine(shard=(r, world, B), **kw)
+        assert eng.n_local == owned_ids(P, r, world, B).size
+        eng.rollout(2, 0.9, _cuda(mu), fitness=fit, steps=steps)
+        eng.close()
+    assert torch.equal(fit, fit1) and torch.equal(steps, steps1)
+    # verification mode on rank 1's slice: explicit weights row l belong to offspring owned_ids[l]
+    ids = owned_ids(P, 1, world, B)
+    W = whole.materialize(2, 0.9, _cuda(mu), _cuda(ids.astype(np.int32)))
+    eng = _engine(shard=(1, world, B), **kw)
+    f2 = torch.zeros(P, dtype=torch.float64, device="cuda"); s2 = torch.zeros(P, dtype=torch.int64, device="cuda")
+    out = eng.rollout(2, 0.0, None, fitness=f2, steps=s2, w_override=W.contiguous(), n_trace=min(4, ids.size))
+    assert torch.equal(f2[torch.from_numpy(ids).cuda()], fit1[torch.from_numpy(ids).cuda()])
+
+
 # ------------------------------------------------------------------------------------- opt-in: antithetic sampling
 @pytest.mark.parametrize("strategy,n,k,gru", [("openai_es", 1025, None, False), ("simple_genetic", 1000, 8, False), ("simple_evolution", 300, 10, True)])
 def test_antithetic_sampling_bit_exact_and_mirrored(twin, strategy, n, k, gru):
