@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--elite-num", type=int, default=None)
     ap.add_argument("--generations", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--shard", default="cyclic", choices=["cyclic", "contiguous"])
     args = ap.parse_args()
     rank, world = sdist.init_from_env()
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -34,6 +35,7 @@ def main():
     cfg["strategy"]["offspring_num"] = args.offspring_num
     if args.elite_num is not None:
         cfg["strategy"]["elite_num"] = args.elite_num
+    cfg["engine"]["shard"] = args.shard
     loop = B200Loop(cfg, args.generations, 1, 5, save_model_period=0, seed=0, device=local, quiet=True)
     s = loop.strategy
     for _ in range(args.warmup):
@@ -61,7 +63,7 @@ def main():
         torch.distributed.destroy_process_group()
     if rank == 0:
         ms = float(t[0])
-        print(json.dumps({"conf": args.conf, "strategy": cfg["strategy"]["name"], "population": s.P, "n_gpus": world,
+        print(json.dumps({"conf": args.conf, "strategy": cfg["strategy"]["name"], "population": s.P, "n_gpus": world, "shard": args.shard,
                           "generations": args.generations, "ms_per_generation": ms / args.generations,
                           "generations_per_s": args.generations / (ms * 1e-3), "env_steps_per_s": int(n[0]) / (ms * 1e-3),
                           "best_reward": best}))
