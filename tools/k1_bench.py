@@ -4,7 +4,7 @@
   gen0      : mu = 0, sigma = 2  (mean return ~ 20 steps, ragged episode lengths)
   converged : a parent that balances the pole, sigma = 0.05 (nearly every episode runs 500 steps)
 
-Launch-shape knobs come from the environment (SES_ROLLOUT_CTA_WARPS, SES_ROLLOUT_LANES, SES_ROLLOUT_CTAS_PER_SM).
+Knobs come from the environment (SES_K1_VARIANT, SES_ROLLOUT_LANES, SES_ROLLOUT_CTAS_PER_SM).
 """
 import argparse
 import json
@@ -36,7 +36,7 @@ def main():
     ap.add_argument("--regime", default="both")
     args = ap.parse_args()
     P = args.pop
-    out = {"cta_warps": os.environ.get("SES_ROLLOUT_CTA_WARPS", "4"), "lanes": os.environ.get("SES_ROLLOUT_LANES", "auto"), "ctas_per_sm": os.environ.get("SES_ROLLOUT_CTAS_PER_SM", "auto"), "pop": P}
+    out = {"variant": os.environ.get("SES_K1_VARIANT", "4"), "lanes": os.environ.get("SES_ROLLOUT_LANES", "auto"), "ctas_per_sm": os.environ.get("SES_ROLLOUT_CTAS_PER_SM", "auto"), "pop": P}
     for regime in (["gen0", "converged"] if args.regime == "both" else [args.regime]):
         eng = RolloutEngine("CartPole-v1", 4, 2, False, False, 500, args.E, P, P, 1, 1, seed=0)
         mu = torch.from_numpy(np.zeros((1, D), np.float32) if regime == "gen0" else balancing_parent()).cuda()
