@@ -254,27 +254,40 @@ struct SpreadEnv {
                 s.apos[i][d] = __dadd_rn(s.apos[i][d], __dmul_rn(v, 0.1));
             }
         // rewards (Scenario.global_reward / reward; the 2021 sources count the agent's own "collision")
+        // The oracle takes min_a sqrt(d2) per landmark and tests sqrt(d2) < 0.3 for every ordered agent pair.  sqrt is
+        // monotone and correctly rounded, so (same bits, 6 instead of 21 square roots at N = 3):
+        //   min_a sqrt(d2_a) == sqrt(min_a d2_a);   sqrt(d2) < 0.3  <=>  d2 < D2_COLLIDE, the smallest double whose root
+        //   is >= 0.3 (0x3fb70a3d70a3d709);   d2(a, i) == d2(i, a) bit for bit;   d2(i, i) == 0 always collides.
         double glob = 0.0;
 #pragma unroll
         for (int l = 0; l < N; ++l) {
-            double best = 0.0;
+            double best2 = 0.0;
 #pragma unroll
             for (int a = 0; a < N; ++a) {
                 const double dx = __dsub_rn(s.apos[a][0], s.lpos[l][0]), dy = __dsub_rn(s.apos[a][1], s.lpos[l][1]);
-                const double d = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
-                if (a == 0 || d < best) best = d;
+                const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                if (a == 0 || d2 < best2) best2 = d2;
             }
-            glob = __dsub_rn(glob, best);
+            glob = __dsub_rn(glob, __dsqrt_rn(best2));
+        }
+        const double D2_COLLIDE = __longlong_as_double(0x3fb70a3d70a3d709ll);
+        bool hit[N][N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            hit[i][i] = true;
+#pragma unroll
+            for (int a = i + 1; a < N; ++a) {
+                const double dx = __dsub_rn(s.apos[a][0], s.apos[i][0]), dy = __dsub_rn(s.apos[a][1], s.apos[i][1]);
+                hit[i][a] = hit[a][i] = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < D2_COLLIDE;
+            }
         }
         double total = 0.0;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             double local = 0.0;
 #pragma unroll
-            for (int a = 0; a < N; ++a) {
-                const double dx = __dsub_rn(s.apos[a][0], s.apos[i][0]), dy = __dsub_rn(s.apos[a][1], s.apos[i][1]);
-                if (__dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))) < 0.3) local = __dsub_rn(local, 1.0);
-            }
+            for (int a = 0; a < N; ++a)
+                if (hit[i][a]) local = __dsub_rn(local, 1.0);
             total = __dadd_rn(total, __dadd_rn(__dmul_rn(glob, 0.5), __dmul_rn(local, 0.5)));
         }
         s.ret = __dadd_rn(s.ret, total);

@@ -551,7 +551,7 @@ extern "C" int ses_generation_openai_host(ses_handle *h, uint32_t generation, fl
     if (rc_roll) return -1;
     int key_bits = 0;
     double key_scale = 1.0;
-    if (c.env == SES_ENV_CARTPOLE) {          // fitness = steps / E with integer steps <= E * max_step
+    if (c.env != SES_ENV_SIMPLE_SPREAD) {     // fitness = +-steps / E with integer |steps| <= E * max_step
         const long long vmax = (long long)c.eval_ep_num * h->eff_max_step;
         while ((1ll << key_bits) <= vmax) ++key_bits;
         key_scale = (double)c.eval_ep_num;
