@@ -29,6 +29,23 @@ def test_library_exports_every_declared_symbol():
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_ctypes_struct_matches_the_c_header(tmp_path):
+    """simple-es_b200/_lib.py::ses_config must have the layout of include/ses_b200.h's struct (size and every field
+    offset), checked with a C program compiled against the header."""
+    import ctypes as C
+    import subprocess
+    from simple_es_b200 import _lib
+    names = [n for n, _ in _lib.ses_config._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "ses_b200.h"\nint main(void){printf("%zu\\n", sizeof(ses_config));'
+                   + "".join('printf("%%zu\\n", offsetof(ses_config, %s));' % n for n in names) + "return 0;}\n")
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    out = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert out[0] == C.sizeof(_lib.ses_config) == 96
+    assert out[1:] == [getattr(_lib.ses_config, n).offset for n in names]
+
+
 def test_no_cpu_fallback():
     from simple_es_b200 import _lib
     from simple_es_b200.engine import RolloutEngine
