@@ -98,6 +98,7 @@ class RolloutEngine:
         self.shard = None if shard is None else tuple(int(x) for x in shard)
         if self.shard is not None and (self.id_begin, self.id_end) != (0, self.P):
             raise ValueError("a block-cyclic shard covers the whole population: leave id_begin / id_end at their defaults")
+        self._n_local = int(owned_ids(self.P, *self.shard).size) if self.shard is not None else self.id_end - self.id_begin
         self.E = int(eval_ep_num)
         self.env_name = env_name
         self.n_agents = int(n_agents) if env_name == "simple_spread" else 1
@@ -152,9 +153,7 @@ class RolloutEngine:
 
     @property
     def n_local(self):
-        if self.shard is not None:
-            return int(owned_ids(self.P, *self.shard).size)
-        return self.id_end - self.id_begin
+        return self._n_local
 
     @property
     def launches(self):
