@@ -80,6 +80,7 @@ struct ses_handle {
     int lanes_used_override = 0;
     int ctas_per_sm = 0;
     int k1_variant = 4;
+    int spread_slots8 = 0;
 
     int64_t launches = 0;
 };
@@ -157,6 +158,7 @@ extern "C" int ses_create(const ses_config *cfg, ses_handle **out)
     h->lanes_used_override = env_int("SES_ROLLOUT_LANES", 0);
     h->ctas_per_sm = env_int("SES_ROLLOUT_CTAS_PER_SM", 0);
     h->k1_variant = env_int("SES_K1_VARIANT", 4);
+    h->spread_slots8 = env_int("SES_SPREAD_SLOTS8", 0);
     if (h->k1_variant < 0 || h->k1_variant > 5) h->k1_variant = 4;
 
     const int P = cfg->population;
@@ -203,10 +205,9 @@ extern "C" int ses_set_step_counter(ses_handle *h, uint64_t *counter_dev)
 // ------------------------------------------------------------------------------------------------
 // K1
 // ------------------------------------------------------------------------------------------------
-template <class Env, int SL>
+template <class Env, int SL, int WARPS = 4>
 static int launch_slots(ses_handle *h, RolloutParams &rp, int need_warps, bool trace, cudaStream_t st)
 {
-    constexpr int WARPS = 4;
     using Smem = SlotSmem<Env, SL, !Env::UNIT_REWARD>;
     auto kernel = trace ? k_rollout_slots<Env, SL, WARPS, true> : k_rollout_slots<Env, SL, WARPS, false>;
     const size_t smem = WARPS * sizeof(Smem);
@@ -296,6 +297,13 @@ extern "C" int ses_rollout(ses_handle *h, uint32_t generation, float sigma, cons
     if (c.env == SES_ENV_CARTPOLE && c.gru) return launch_rollout_cartpole_gru(h->num_sms, h->ctas_per_sm, rp, tr, st, &h->launches, g_err, sizeof(g_err));
     if (c.env == SES_ENV_MOUNTAINCAR) return launch_slots_by_E<MountainCarEnv>(h, rp, need_warps, tr, st);
     if (c.env == SES_ENV_ACROBOT) return launch_slots_by_E<AcrobotEnv>(h, rp, need_warps, tr, st);
+    // simple_spread episodes all last max_cycles steps, so a warp never holds more than ceil(lanes_used / E) offspring at
+    // once: 6 slots instead of 8 for E >= 5 (and 2-warp CTAs for N = 3) put 12 / 10 warps on an SM instead of 8
+    // (shared-memory capacity is what limits this kernel)
+    if (c.eval_ep_num >= 5 && !h->spread_slots8) {
+        if (c.n_agents == 2) return launch_slots<SpreadEnv<2>, 6>(h, rp, need_warps, tr, st);
+        return launch_slots<SpreadEnv<3>, 6, 2>(h, rp, need_warps, tr, st);
+    }
     if (c.n_agents == 2) return launch_slots<SpreadEnv<2>, 8>(h, rp, need_warps, tr, st);
     return launch_slots<SpreadEnv<3>, 8>(h, rp, need_warps, tr, st);
 }
