@@ -23,6 +23,11 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# One OpenMP thread per process (what torchrun sets for N > 1 anyway): the CPU legs run one forked worker per
+# core, and torch's intra-op pool inside each of them only oversubscribes the box (measured here: 116 k -> 180 k
+# env-steps/s for the reference path on 8 cores).  The GPU arm does no CPU compute.
+os.environ.setdefault("OMP_NUM_THREADS", "1")
+os.environ.setdefault("MKL_NUM_THREADS", "1")
 
 P_DEFAULT = 65536
 E_DEFAULT = 5
@@ -113,10 +118,23 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # CPU legs (oracle; allowed importers of oracle/: tests, smoke, and these two functions)
 # ----------------------------------------------------------------------------------------------
-def cpu_reference_generation(n_offspring, cores, gen_seed, eval_ep_num=E_DEFAULT):
+STATE_FIXTURE = os.path.join(ROOT, "tests", "golden", "bench_state_gen30.npz")
+REGIME = ("population drawn around the generation-30 state of this very workload (tests/golden/bench_state_gen30.npz, "
+          "tools/make_bench_fixture.py): episodes of ~500 steps, the regime the GPU arm's timed generations run in")
+CPU_SEC_PER_OFFSPRING = 0.21   # 5 episodes x 500 steps x ~85 us per reference policy-forward + env step on one core
+
+
+def bench_state():
+    """The trained openai_es state the CPU legs start from (a committed fixture; not an oracle import)."""
+    import numpy as np
+    z = np.load(STATE_FIXTURE)
+    return {"mu": z["mu"], "m": z["m"], "v": z["v"], "sigma": float(z["sigma"]), "t": int(z["t"])}
+
+
+def cpu_reference_generation(n_offspring, cores, gen_seed, eval_ep_num=E_DEFAULT, state=None):
     """One generation of the reference's CPU path (port: oracle/pyref.py -- torch-CPU policy per
-    offspring, Python CartPole, a fresh mp.Pool(cores), strategy.evaluate) on a gen-0 population
-    sample of n_offspring.  Returns (env_steps, seconds)."""
+    offspring, Python CartPole, a fresh mp.Pool(cores), strategy.evaluate) on a population sample of
+    n_offspring drawn around `state` (None: the all-zero generation-0 network).  Returns (env_steps, seconds)."""
     import numpy as np
     import torch
     from oracle import pyref
@@ -126,28 +144,30 @@ def cpu_reference_generation(n_offspring, cores, gen_seed, eval_ep_num=E_DEFAULT
     env = pyref.CartPoleShim(max_step=500, init_states=init)
     cfg = dict(STRATEGY, offspring_num=n_offspring)
     t0 = time.perf_counter()
-    rec = pyref.es_loop_port(env, (4, 2, False), cfg, 1, cores, eval_ep_num, seed=gen_seed)
+    rec = pyref.es_loop_port(env, (4, 2, False), cfg, 1, cores, eval_ep_num, seed=gen_seed, state=state)
     return rec[0]["env_steps"], time.perf_counter() - t0
 
 
 def cpu_baseline_block(cores):
     """Bounded CPU baseline reported beside the GPU number (rank 0, N = 1)."""
-    n = max(64, min(P_DEFAULT, 1536 * cores))          # ~10-20 s of CPU work on the box's cores
-    steps, dt = cpu_reference_generation(n, cores, 12345)
+    n = max(64, min(P_DEFAULT, 96 * cores))            # 10-20 s of CPU work on the box's cores
+    steps, dt = cpu_reference_generation(n, cores, 12345, state=bench_state())
     out = {"value": steps / dt, "unit": "env-steps/s", "cores": cores, "kind": "port",
            "sample": "1 generation of the reference CPU path (oracle/pyref.py port: torch-CPU policy, Python CartPole, "
-                     "mp.Pool(%d), evaluate) on %d gen-0 offspring x %d episodes = %d env steps in %.1f s"
-                     % (cores, n, E_DEFAULT, steps, dt)}
-    try:  # a much stronger CPU number for context: the C bit-twin on every host thread
+                     "mp.Pool(%d), evaluate) on %d offspring x %d episodes = %d env steps in %.1f s; %s"
+                     % (cores, n, E_DEFAULT, steps, dt, REGIME)}
+    try:  # a much stronger CPU number for context: the C bit-twin on every host thread, same regime
         import numpy as np
         from oracle import twin
-        n2 = 8192
+        st = bench_state()
+        n2 = 512 * cores
         t0 = time.perf_counter()
-        _, ts = twin.population_cartpole(np.zeros((1, D), np.float32), sigma=2.0, seed=0, gen=0, group=P_DEFAULT, n_head=1,
+        _, ts = twin.population_cartpole(st["mu"][None], sigma=st["sigma"], seed=0, gen=30, group=P_DEFAULT, n_head=1,
                                          n=n2, E=E_DEFAULT, nthreads=cores)
         dt2 = time.perf_counter() - t0
         out["c_twin"] = {"value": float(ts.sum()) / dt2, "unit": "env-steps/s", "cores": cores,
-                         "sample": "%d gen-0 offspring (sigma 2) x %d episodes, oracle/ses_twin.c, %d pthreads" % (n2, E_DEFAULT, cores)}
+                         "sample": "%d offspring of generation 30 x %d episodes = %d env steps, oracle/ses_twin.c, %d pthreads"
+                                   % (n2, E_DEFAULT, int(ts.sum()), cores)}
     except Exception as exc:  # pragma: no cover
         out["c_twin"] = {"error": str(exc)}
     return out
@@ -159,16 +179,19 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    n = max(64, min(4096, 64 * cores))
+    # per-step sample: the whole run (K timed + W warm-up steps) should take about two minutes on this box
+    per_step_s = 120.0 / max(1, args.steps + args.warmup)
+    n = int(max(2 * cores, min(64 * cores, per_step_s * cores / CPU_SEC_PER_OFFSPRING)))
+    state = bench_state()
     for w in range(args.warmup):
-        cpu_reference_generation(max(16, cores), cores, 100 + w)
+        cpu_reference_generation(n, cores, 100 + w, state=state)
     tot_steps, tot_t = 0, 0.0
     for k in range(args.steps):
-        s, dt = cpu_reference_generation(n, cores, 1000 + k)
+        s, dt = cpu_reference_generation(n, cores, 1000 + k, state=state)
         tot_steps += s; tot_t += dt
     v = tot_steps / tot_t
-    sample = ("each step = 1 generation of the reference CPU path (oracle/pyref.py port, mp.Pool(%d)) on %d gen-0 "
-              "offspring x %d episodes (bounded sample of the 65536 population)" % (cores, n, E_DEFAULT))
+    sample = ("each step = 1 generation of the reference CPU path (oracle/pyref.py port, mp.Pool(%d)) on %d offspring x %d "
+              "episodes (bounded sample of the 65536 population); %s" % (cores, n, E_DEFAULT, REGIME))
     line = {
         "impl": "reference", "metric": "env-steps/sec", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, args.steps),

@@ -536,12 +536,22 @@ class StrategyPort:
         return pop, best, self.sigma
 
 
-def es_loop_port(env, net_cfg, strategy_cfg, generation_num, process_num, eval_ep_num, seed=0, verbose=False):
+def es_loop_port(env, net_cfg, strategy_cfg, generation_num, process_num, eval_ep_num, seed=0, verbose=False, state=None):
     """Port of ESLoop.run (loop.py:52-104): a fresh mp.Pool every generation, one task per
-    offspring carrying (env, weights, eval_ep_num).  Returns per-generation records."""
+    offspring carrying (env, weights, eval_ep_num).  Returns per-generation records.
+    `state` (optional dict: mu, sigma and, for openai_es, m / v / t) starts the run from a trained
+    strategy state instead of the reference's all-zero network (loop.py:31) -- used by bench.py to time
+    the reference path in the regime the GPU arm is timed in."""
     np.random.seed(seed)
     D = param_count(*net_cfg)
     strat = StrategyPort(strategy_cfg, D)
+    if state is not None:
+        strat.mu = np.array(state["mu"], dtype=np.float32)
+        strat.sigma = float(state.get("sigma", strat.sigma))
+        if strat.name == "openai_es" and "m" in state:
+            strat.opt.m = np.array(state["m"], dtype=np.float32)
+            strat.opt.v = np.array(state["v"], dtype=np.float32)
+            strat.opt.t = int(state["t"])
     pop = strat.generate()
     out = []
     for g in range(generation_num):
