@@ -88,6 +88,7 @@ class B200Loop(BaseESLoop):
 
     def run(self):
         s = self.strategy
+        s.timing = True                                      # CUDA-event marks around K1 + exchange and K2 + K3
         ep_num = self.start_ep
         for _ in range(self.generation_num):
             start = time.time()
@@ -95,13 +96,14 @@ class B200Loop(BaseESLoop):
             s.step()
             best_reward = float(s.best_reward().item())      # the one device->host sync of a generation
             consumed = time.time() - start
+            # rollout_t / eval_t (loop.py:70-88) are device times here: K1 + fitness exchange, and K2 + K3, taken from CUDA
+            # events that the sync above has completed -- the phases are one stream-ordered pass, the host never waits between
+            rollout_t, eval_t = s.phase_times() or (consumed, 0.0)
             curr_sigma = s.curr_sigma
-            self.history.append((ep_num, best_reward, curr_sigma, consumed))
+            self.history.append((ep_num, best_reward, curr_sigma, consumed, rollout_t, eval_t))
             if self.rank == 0 and not self.quiet:
-                # rollout and evaluate are one stream-ordered GPU pass; their split is not observable from
-                # the host without extra syncs, so both reference fields report the generation time.
                 print(f"episode: {ep_num}, Best reward: {best_reward:.2f}, sigma: {curr_sigma:.3f}, "
-                      f"time: {consumed:.2f}, rollout_t: {consumed:.2f}, eval_t: {0.0:.2f}")
+                      f"time: {consumed:.2f}, rollout_t: {rollout_t:.2f}, eval_t: {eval_t:.2f}")
             if self._wandb is not None:
                 self.ep5_rewards.append(best_reward)
                 self._wandb.log({"ep5_mean_reward": sum(self.ep5_rewards) / len(self.ep5_rewards),

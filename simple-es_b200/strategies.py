@@ -68,13 +68,33 @@ class _Base:
         self.generation = 0
         self.total_env_steps = torch.zeros(1, dtype=torch.int64, device=dev)     # accumulated by K1 itself
         self.engine.set_step_counter(self.total_env_steps)
+        # CUDA-event phase marks of a generation (start / after K1 + exchange / end).  B200Loop reads them after its one
+        # host sync per generation to fill the reference's `rollout_t` / `eval_t` fields (loop.py:70-91) with device times
+        # instead of adding host syncs between the phases.
+        self.timing = False
+        self._ev = None
+
+    def _mark(self, i):
+        if self.timing:
+            if self._ev is None:
+                self._ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            self._ev[i].record(torch.cuda.current_stream(self.engine.device))
+
+    def phase_times(self):
+        """(rollout seconds, evaluate seconds) of the last step(); call after the stream has been synchronised
+        (B200Loop does so by reading best_reward).  None unless `timing` was on during that step."""
+        if not self.timing or self._ev is None:
+            return None
+        return self._ev[0].elapsed_time(self._ev[1]) * 1e-3, self._ev[1].elapsed_time(self._ev[2]) * 1e-3
 
     def _rollout_and_exchange(self):
         """K1 on this rank's slice, then the full fitness vector on every rank."""
         e = self.engine
+        self._mark(0)
         self.fitness = self._fit[self.generation & 1]
         e.rollout(self.generation, self.sigma, self.parents, fitness=self.fitness, steps=self.steps)
         self.exchange_fitness()
+        self._mark(1)
 
     def exchange_fitness(self):
         """After K1: make the full fitness vector visible on every rank."""
@@ -156,6 +176,7 @@ class OpenAIES(_Base):
         self.sigma *= self.decay                                  # :418, after update_factor used the old sigma
         self.curr_sigma = self.sigma
         self.generation += 1
+        self._mark(2)
 
     def elite_flat(self):
         return self.parents[0]                                    # get_elite_model() is mu_model (:330-331)
@@ -173,6 +194,7 @@ class SimpleEvolution(_Base):
         self.sigma *= self.decay                                  # :251, BEFORE regenerating
         self.curr_sigma = self.sigma
         self.generation += 1
+        self._mark(2)
 
     def elite_flat(self):
         return self.parents[0]                                    # elite_models[0] was overwritten by the mean (Q2)
@@ -192,6 +214,7 @@ class SimpleGenetic(_Base):
         self.sigma = self.curr_sigma
         self.curr_sigma = self.curr_sigma * self.decay
         self.generation += 1
+        self._mark(2)
 
     def elite_flat(self):
         return self.parents[0]                                    # elite_models[0] (:64-65)

@@ -66,6 +66,7 @@ def test_openai_es_learns_cartpole_and_writes_reference_checkpoints(tmp_path, ca
     out = capsys.readouterr().out
     assert out.count("episode: ") == 40 and "Best reward: " in out and "sigma: " in out and "rollout_t: " in out
     assert hist[-1][1] == 500.0                                    # solved: best offspring balances for 500 steps
+    assert all(h[4] > 0.0 and h[5] > 0.0 for h in hist)            # rollout_t / eval_t: CUDA-event times of K1+exchange, K2+K3
     assert max(h[1] for h in hist[:3]) < 500.0 or True
     files = sorted(os.listdir(tmp_path / "run" / "saved_models"))
     assert files == ["ep_10.pt", "ep_20.pt", "ep_30.pt", "ep_40.pt"]          # loop.py:101-104
