@@ -1,0 +1,446 @@
+// simt_emu.h -- TEST INFRASTRUCTURE ONLY: a minimal single-threaded SIMT emulator that lets g++ compile the
+// engine's CUDA sources (simple-es_b200/csrc/*.cu, *.cuh) for the HOST, so that the kernels' logic -- warp
+// schedulers, ballots / shuffles / match_any, shared-memory layouts, Philox streams, the numerical contract's
+// operation order -- can be checked bit for bit against the CPU oracle in a container without a GPU
+// (tests/test_simt_emu.py).  It is NOT a CPU fallback of the product: the package never loads this library,
+// simple_es_b200._lib.load() knows only libses_b200.so, and every product entry point fails without a CUDA device
+// (tests/test_host_logic.py::test_no_cpu_fallback).  It says nothing about performance, races between warps or the
+// memory model: every CUDA thread is a ucontext fiber, a warp's lanes run one after the other up to their next warp
+// collective, CTAs run one after the other.
+//
+// What is emulated: __global__ functions called through simt::launch (the build script rewrites <<< >>>), threadIdx /
+// blockIdx / blockDim / gridDim (x only), static and dynamic __shared__, __syncthreads, __syncwarp, __ballot_sync,
+// __shfl_sync, __shfl_xor_sync, __match_any_sync, atomicAdd / atomicExch, the *_rn arithmetic intrinsics (plain IEEE
+// operations: the translation unit is compiled with -ffp-contract=off), packed float2 intrinsics, bit casts, and the part
+// of the runtime API ses_abi.cu uses (device memory == host memory, one synchronous stream).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <time.h>
+#include <ucontext.h>
+
+#include <vector>
+
+#define SES_SIMT_EMU 1
+#define __host__
+#define __device__
+#define __global__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __constant__ static const
+#define __align__(n) alignas(n)
+
+// ------------------------------------------------------------------------------------------------ vector types
+struct alignas(8) float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(16) double2 { double x, y; };
+struct alignas(8) uint2 { unsigned x, y; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+struct alignas(8) int2 { int x, y; };
+struct alignas(16) int4 { int x, y, z, w; };
+struct uint3 { unsigned x, y, z; };
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+static inline double2 make_double2(double x, double y) { return double2{x, y}; }
+static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
+static inline int2 make_int2(int x, int y) { return int2{x, y}; }
+static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
+
+// ------------------------------------------------------------------------------------------------ fibers
+namespace simt {
+
+enum { READY = 0, WAIT_WARP = 1, WAIT_CTA = 2, DONE = 3 };
+enum { K_SYNCWARP = 1, K_BALLOT, K_SHFL, K_MATCH };
+
+struct Warp {
+    uint64_t opnd[2][32];
+    uint32_t arrived[2];
+    int kind[2];
+    int alive, waiting;
+};
+
+struct Fiber {
+    ucontext_t ctx;
+    uint3 tid;
+    int state, lane;
+    unsigned wseq;          // number of warp collectives this lane has completed
+    Warp *warp;
+};
+
+inline Fiber *g_cur = nullptr;
+inline ucontext_t g_sched;
+inline uint3 g_blockIdx = {0, 0, 0};
+inline dim3 g_blockDim, g_gridDim;
+inline unsigned char *g_dyn_smem = nullptr;
+inline int g_cta_waiting = 0;
+inline unsigned long long g_switches = 0, g_launches = 0;
+
+inline unsigned char *dyn_smem() { return g_dyn_smem; }
+
+[[noreturn]] inline void die(const char *msg)
+{
+    fprintf(stderr, "simt_emu: %s (block %u, thread %u)\n", msg, g_blockIdx.x, g_cur ? g_cur->tid.x : 0u);
+    abort();
+}
+
+inline void yield()
+{
+    Fiber *f = g_cur;
+    ++g_switches;
+    swapcontext(&f->ctx, &g_sched);
+}
+
+// a lane arrives at a warp collective with its operand; returns the parity of the exchange buffer holding the results
+inline int warp_collective(int kind, uint64_t v)
+{
+    Fiber *f = g_cur;
+    if (!f) die("warp collective outside a kernel");
+    Warp &w = *f->warp;
+    const int par = (int)(f->wseq & 1u);
+    if (w.arrived[par] && w.kind[par] != kind) die("lanes of one warp wait at different warp collectives");
+    w.kind[par] = kind;
+    w.opnd[par][f->lane] = v;
+    w.arrived[par] |= 1u << f->lane;
+    w.waiting += 1;
+    f->state = WAIT_WARP;
+    yield();
+    f->wseq += 1;
+    return par;
+}
+
+template <class T>
+inline uint64_t to_bits(T v)
+{
+    static_assert(sizeof(T) <= 8, "warp collectives move at most 64 bits");
+    uint64_t b = 0;
+    memcpy(&b, &v, sizeof(T));
+    return b;
+}
+template <class T>
+inline T from_bits(uint64_t b)
+{
+    T v;
+    memcpy(&v, &b, sizeof(T));
+    return v;
+}
+
+struct Stacks {
+    char *base = nullptr;
+    size_t n = 0;
+    static constexpr size_t SZ = 256 << 10;
+    char *get(size_t nthreads)
+    {
+        if (nthreads > n) {
+            if (base) munmap(base, n * SZ);
+            base = (char *)mmap(nullptr, nthreads * SZ, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+            if (base == MAP_FAILED) die("mmap of fiber stacks failed");
+            n = nthreads;
+        }
+        return base;
+    }
+};
+inline Stacks g_stacks;
+
+template <class F>
+void fiber_entry(unsigned lo, unsigned hi)
+{
+    F *body = reinterpret_cast<F *>(((uintptr_t)hi << 32) | (uintptr_t)lo);
+    (*body)();
+    g_cur->state = DONE;
+    // returning switches to uc_link (the scheduler)
+}
+
+// run one CTA: fibers round robin, warp by warp; a warp collective resolves when every live lane of the warp waits at it,
+// __syncthreads when every live thread of the CTA does (exited threads count as arrived, as on the hardware)
+template <class F>
+void run_cta(unsigned nthreads, F &body)
+{
+    const unsigned nwarps = (nthreads + 31) / 32;
+    std::vector<Fiber> fibers(nthreads);
+    std::vector<Warp> warps(nwarps);
+    char *stacks = g_stacks.get(nthreads);
+    for (unsigned w = 0; w < nwarps; ++w) {
+        memset(&warps[w], 0, sizeof(Warp));
+        warps[w].alive = (int)((w + 1) * 32 <= nthreads ? 32 : nthreads - w * 32);
+    }
+    const uintptr_t bp = reinterpret_cast<uintptr_t>(&body);
+    for (unsigned t = 0; t < nthreads; ++t) {
+        Fiber &f = fibers[t];
+        f.tid = uint3{t, 0, 0};
+        f.state = READY;
+        f.lane = (int)(t & 31);
+        f.wseq = 0;
+        f.warp = &warps[t >> 5];
+        getcontext(&f.ctx);
+        f.ctx.uc_stack.ss_sp = stacks + (size_t)t * Stacks::SZ;
+        f.ctx.uc_stack.ss_size = Stacks::SZ;
+        f.ctx.uc_link = &g_sched;
+        makecontext(&f.ctx, (void (*)())fiber_entry<F>, 2, (unsigned)(bp & 0xffffffffu), (unsigned)(bp >> 32));
+    }
+    int alive = (int)nthreads;
+    g_cta_waiting = 0;
+    while (alive > 0) {
+        bool progress = false;
+        for (unsigned w = 0; w < nwarps; ++w) {
+            Warp &wp = warps[w];
+            const unsigned t0 = w * 32, t1 = t0 + 32 < nthreads ? t0 + 32 : nthreads;
+            for (unsigned t = t0; t < t1; ++t) {
+                Fiber &f = fibers[t];
+                if (f.state != READY) continue;
+                g_cur = &f;
+                swapcontext(&g_sched, &f.ctx);
+                g_cur = nullptr;
+                progress = true;
+                if (f.state == DONE) { alive -= 1; wp.alive -= 1; }
+            }
+            if (wp.alive > 0 && wp.waiting == wp.alive) {
+                // resolve: the results stay readable in opnd[par] / arrived[par]; the other buffer is recycled
+                int par = -1;
+                for (unsigned t = t0; t < t1; ++t)
+                    if (fibers[t].state == WAIT_WARP) {
+                        const int pp = (int)(fibers[t].wseq & 1u);
+                        if (par >= 0 && pp != par) die("lanes of one warp are at different collective counts");
+                        par = pp;
+                        fibers[t].state = READY;
+                    }
+                wp.arrived[par ^ 1] = 0;
+                wp.waiting = 0;
+                progress = true;
+            }
+        }
+        if (alive > 0 && g_cta_waiting == alive) {
+            for (unsigned t = 0; t < nthreads; ++t)
+                if (fibers[t].state == WAIT_CTA) fibers[t].state = READY;
+            g_cta_waiting = 0;
+            progress = true;
+        }
+        if (!progress) die("deadlock: no thread of the CTA can run (divergent barrier?)");
+    }
+}
+
+template <class F>
+void launch(dim3 grid, dim3 block, size_t smem, F &&body)
+{
+    if (grid.y != 1 || grid.z != 1 || block.y != 1 || block.z != 1) die("only 1-D launches are emulated");
+    if (block.x < 1 || block.x > 1024) die("bad block size");
+    ++g_launches;
+    g_gridDim = grid;
+    g_blockDim = block;
+    void *dyn = nullptr;
+    if (smem && posix_memalign(&dyn, 128, smem)) die("out of memory (dynamic shared memory)");
+    g_dyn_smem = static_cast<unsigned char *>(dyn);
+    for (unsigned b = 0; b < grid.x; ++b) {
+        g_blockIdx = uint3{b, 0, 0};
+        if (dyn) memset(dyn, 0xA5, smem);          // shared memory starts undefined on the device
+        run_cta(block.x, body);
+    }
+    g_dyn_smem = nullptr;
+    free(dyn);
+}
+
+inline float rcp_approx(float x) { return 1.0f / x; }      // MUFU.RCP stand-in (the device value is within 1 ulp of this)
+inline float min_xorsign_abs(float a, float b)
+{
+    // min(|a|, |b|) with sign(a) ^ sign(b)
+    const float m = fminf(fabsf(a), fabsf(b));
+    return (signbit(a) != signbit(b)) ? -m : m;
+}
+inline unsigned lanemask_lt() { return (1u << g_cur->lane) - 1u; }
+
+}  // namespace simt
+
+#define threadIdx (simt::g_cur->tid)
+#define blockIdx (simt::g_blockIdx)
+#define blockDim (simt::g_blockDim)
+#define gridDim (simt::g_gridDim)
+
+// ------------------------------------------------------------------------------------------------ barriers, collectives
+inline void __syncthreads()
+{
+    simt::Fiber *f = simt::g_cur;
+    simt::g_cta_waiting += 1;
+    f->state = simt::WAIT_CTA;
+    simt::yield();
+}
+inline void __syncwarp(unsigned = 0xffffffffu) { simt::warp_collective(simt::K_SYNCWARP, 0); }
+inline void __threadfence_system() {}
+inline void __threadfence() {}
+
+inline unsigned __ballot_sync(unsigned mask, int pred)
+{
+    const int par = simt::warp_collective(simt::K_BALLOT, pred ? 1u : 0u);
+    const simt::Warp &w = *simt::g_cur->warp;
+    unsigned r = 0;
+    for (int l = 0; l < 32; ++l)
+        if (((w.arrived[par] >> l) & 1u) && w.opnd[par][l]) r |= 1u << l;
+    return r & mask;
+}
+template <class T>
+inline T __shfl_sync(unsigned, T v, int src, int width = 32)
+{
+    const int par = simt::warp_collective(simt::K_SHFL, simt::to_bits(v));
+    const simt::Warp &w = *simt::g_cur->warp;
+    const int lane = simt::g_cur->lane;
+    const int s = (lane & ~(width - 1)) | (src & (width - 1));
+    if (!((w.arrived[par] >> s) & 1u)) return v;
+    return simt::from_bits<T>(w.opnd[par][s]);
+}
+template <class T>
+inline T __shfl_xor_sync(unsigned, T v, int lanemask, int width = 32)
+{
+    const int par = simt::warp_collective(simt::K_SHFL, simt::to_bits(v));
+    const simt::Warp &w = *simt::g_cur->warp;
+    const int lane = simt::g_cur->lane;
+    const int s = lane ^ lanemask;
+    if ((s & ~(width - 1)) != (lane & ~(width - 1)) || !((w.arrived[par] >> s) & 1u)) return v;
+    return simt::from_bits<T>(w.opnd[par][s]);
+}
+template <class T>
+inline unsigned __match_any_sync(unsigned mask, T v)
+{
+    const uint64_t mine = simt::to_bits(v);
+    const int par = simt::warp_collective(simt::K_MATCH, mine);
+    const simt::Warp &w = *simt::g_cur->warp;
+    unsigned r = 0;
+    for (int l = 0; l < 32; ++l)
+        if (((w.arrived[par] >> l) & 1u) && w.opnd[par][l] == mine) r |= 1u << l;
+    return r & mask;
+}
+
+template <class T, class U>
+inline T atomicAdd(T *p, U v) { const T o = *p; *p = (T)(o + (T)v); return o; }
+template <class T, class U>
+inline T atomicExch(T *p, U v) { const T o = *p; *p = (T)v; return o; }
+template <class T, class U>
+inline T atomicMax(T *p, U v) { const T o = *p; if ((T)v > o) *p = (T)v; return o; }
+
+inline long long clock64()
+{
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (long long)ts.tv_sec * 1000000000ll + ts.tv_nsec;
+}
+
+// ------------------------------------------------------------------------------------------------ integer intrinsics
+inline int __popc(unsigned x) { return __builtin_popcount(x); }
+inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
+inline int __ffs(int x) { return __builtin_ffs(x); }
+inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
+inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
+inline unsigned __fns(unsigned mask, unsigned base, int offset)
+{
+    // position of the offset-th set bit of mask at or above `base` (offset >= 1), 0xffffffff if there is none
+    if (offset == 0) return ((mask >> base) & 1u) ? base : 0xffffffffu;
+    if (offset > 0) {
+        for (unsigned b = base; b < 32; ++b)
+            if ((mask >> b) & 1u) { if (--offset == 0) return b; }
+        return 0xffffffffu;
+    }
+    for (int b = (int)base; b >= 0; --b)
+        if ((mask >> b) & 1u) { if (++offset == 0) return (unsigned)b; }
+    return 0xffffffffu;
+}
+inline int min(int a, int b) { return a < b ? a : b; }
+inline int max(int a, int b) { return a > b ? a : b; }
+inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
+inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
+inline long long min(long long a, long long b) { return a < b ? a : b; }
+inline long long max(long long a, long long b) { return a > b ? a : b; }
+inline unsigned long long min(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
+inline unsigned long long max(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
+
+// ------------------------------------------------------------------------------------------------ floating point
+// Separately rounded IEEE operations; the translation unit is compiled with -ffp-contract=off -mfma, so fmaf / fma are
+// the only fused operations -- the numerical contract of DESIGN.md section 4.
+inline float __uint_as_float(unsigned b) { return simt::from_bits<float>(b); }
+inline unsigned __float_as_uint(float f) { return (unsigned)simt::to_bits(f); }
+inline int __float_as_int(float f) { return (int)simt::to_bits(f); }
+inline float __int_as_float(int b) { return simt::from_bits<float>((uint64_t)(unsigned)b); }
+inline double __longlong_as_double(long long b) { return simt::from_bits<double>((uint64_t)b); }
+inline long long __double_as_longlong(double d) { return (long long)simt::to_bits(d); }
+inline float __fadd_rn(float a, float b) { return a + b; }
+inline float __fsub_rn(float a, float b) { return a - b; }
+inline float __fmul_rn(float a, float b) { return a * b; }
+inline float __fdiv_rn(float a, float b) { return a / b; }
+inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+inline float __fsqrt_rn(float a) { return sqrtf(a); }
+inline double __dadd_rn(double a, double b) { return a + b; }
+inline double __dsub_rn(double a, double b) { return a - b; }
+inline double __dmul_rn(double a, double b) { return a * b; }
+inline double __ddiv_rn(double a, double b) { return a / b; }
+inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
+inline double __dsqrt_rn(double a) { return sqrt(a); }
+inline float2 __fadd2_rn(float2 a, float2 b) { return float2{a.x + b.x, a.y + b.y}; }
+inline float2 __fmul2_rn(float2 a, float2 b) { return float2{a.x * b.x, a.y * b.y}; }
+inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return float2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }
+inline long long __double2ll_rn(double a) { return llrint(a); }       // default rounding mode: to nearest even
+inline int __double2int_rn(double a) { return (int)lrint(a); }
+inline int __double2int_rz(double a) { return (int)a; }
+inline int __float2int_rn(float a) { return (int)lrintf(a); }
+inline int __float2int_rz(float a) { return (int)a; }
+
+// ------------------------------------------------------------------------------------------------ runtime API subset
+typedef int cudaError_t;
+enum { cudaSuccess = 0, cudaErrorNotSupported = 801, cudaErrorMemoryAllocation = 2 };
+typedef struct simt_stream *cudaStream_t;
+typedef struct simt_event { double t; } *cudaEvent_t;
+enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum { cudaIpcMemLazyEnablePeerAccess = 1 };
+struct cudaIpcMemHandle_t { char reserved[64]; };
+struct cudaDeviceProp { int major, minor, multiProcessorCount; char name[64]; };
+
+inline const char *cudaGetErrorString(cudaError_t e)
+{
+    return e == cudaSuccess ? "no error" : e == cudaErrorNotSupported ? "not supported by the SIMT emulator" : "emulator error";
+}
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
+inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int)
+{
+    memset(p, 0, sizeof(*p));
+    p->major = 10; p->minor = 0;
+    const char *v = getenv("SES_SIMT_EMU_SMS");
+    p->multiProcessorCount = v && *v ? atoi(v) : 2;
+    snprintf(p->name, sizeof(p->name), "SIMT emulator (host)");
+    return cudaSuccess;
+}
+template <class T>
+inline cudaError_t cudaMalloc(T **p, size_t n)
+{
+    void *q = nullptr;
+    if (posix_memalign(&q, 256, n ? n : 1)) return cudaErrorMemoryAllocation;
+    memset(q, 0xCD, n);                        // device memory starts undefined
+    *p = static_cast<T *>(q);
+    return cudaSuccess;
+}
+inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+inline cudaError_t cudaMemset(void *p, int v, size_t n) { memset(p, v, n); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t = nullptr) { memset(p, v, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+template <class K>
+inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return cudaSuccess; }
+template <class K>
+inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, K, int, size_t) { *n = 2; return cudaSuccess; }
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return cudaErrorNotSupported; }
+inline cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
+inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaErrorNotSupported; }
+inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new simt_event{0.0}; return cudaSuccess; }
+inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) { e->t = (double)clock64() * 1e-6; return cudaSuccess; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)(b->t - a->t); return cudaSuccess; }

@@ -1,0 +1,445 @@
+"""The engine's CUDA sources, compiled for the HOST on the SIMT emulator of tests/simt_emu (every CUDA thread a fiber;
+see tests/simt_emu/include/simt_emu.h), against the CPU oracle and the reference-generated golden vectors.
+
+Purpose: the dev container has no GPU, so without this the kernels' logic (warp schedulers, ballots / shuffles /
+match_any, shared-memory layouts, Philox counters, operation order of the numerical contract) could only be checked on
+the B200 box.  These tests run the SAME kernel source through the SAME C ABI entry points (ses_abi.cu) at small sizes and
+demand what the GPU parity tests (tests/test_gpu_*.py, -m gpu) demand at full size: bit equality with the oracle.
+The emulated library is test infrastructure only -- the product never loads it and has no CPU fallback
+(test_host_logic.py::test_no_cpu_fallback); performance, inter-warp races and the memory model remain GPU-only questions
+(compute-sanitizer: profiles/r01_sanitizer.txt)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+D = 226
+DG = 6562
+
+
+@pytest.fixture(scope="module")
+def emu():
+    from simt_emu import emu_engine
+    emu_engine.load()
+    return emu_engine.EmuEngine
+
+
+def _trained_mu():
+    """A parent that balances the pole (bang-bang on theta + theta_dot): 500-step episodes with small sigma."""
+    mu = np.zeros((1, D), np.float32)
+    w1 = mu[0, :128].reshape(32, 4); w2 = mu[0, 160:224].reshape(2, 32)
+    w1[0] = [0.0, 0.5, 10.0, 3.0]; w2[1, 0] = 5.0; w2[0, 0] = -5.0
+    return mu
+
+
+# ------------------------------------------------------------------------------------- contract
+def test_emu_math_contract_bit_exact(emu, twin):
+    eng = emu()
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-10, 10, 200_000), rng.normal(0, 1, 200_000), [0.0, -0.0, 50, -50]]).astype(np.float32)
+    assert np.array_equal(eng.test_math("tanh", x), twin.tanhf(x))
+    assert np.array_equal(eng.test_math("sigmoid", x), twin.sigmf(x))
+    assert np.array_equal(eng.test_math("tanh_fast", x), twin.tanhf(x))
+    # packed / scalar fast-path tanh == the contract's tanh on a slice of the float32 line (the GPU test walks all of it;
+    # here the reciprocal seed is the correctly rounded 1/q instead of MUFU.RCP, so this checks the algebra, not the seed)
+    assert eng.test_tanh_x2_exhaustive(False, 0.25, 0.2500305) == 0
+    assert eng.test_tanh_x2_exhaustive(True, 3.0, 3.0002441) == 0
+    u = ((rng.integers(0, 2 ** 24, 200_000) + 0.5) * 2.0 ** -24).astype(np.float32)
+    assert np.array_equal(eng.test_math("ln", u), twin.lnf(u))
+    v = (rng.integers(0, 2 ** 24, 200_000) * 2.0 ** -24).astype(np.float32)
+    s, c = twin.sincos2pif(v)
+    assert np.array_equal(eng.test_math("sin2pi", v), s) and np.array_equal(eng.test_math("cos2pi", v), c)
+    th = rng.uniform(-0.5, 0.5, 200_000)
+    s, c = twin.sincos(th)
+    assert np.array_equal(eng.test_math("sin64", th), s) and np.array_equal(eng.test_math("cos64", th), c)
+    xf = np.concatenate([rng.uniform(-100, 100, 200_000), np.arange(-80, 81) * (np.pi / 4), [0.0, -0.0]])
+    s, c = twin.sincos_full(xf)
+    assert np.array_equal(eng.test_math("sin64_full", xf), s) and np.array_equal(eng.test_math("cos64_full", xf), c)
+
+
+def test_emu_philox_normals_bit_exact(emu, twin):
+    eng = emu(seed=1234)
+    for gen, idx in [(0, 0), (0, 1), (3, 77), (1000, 65535), (2 ** 31, 2 ** 20 - 1)]:
+        assert np.array_equal(eng.test_normals(gen, idx), twin.normals(1234, gen, idx, D))
+
+
+@pytest.mark.parametrize("strategy,n,k", [("simple_evolution", 96, 10), ("openai_es", 128, None), ("simple_genetic", 100, 8)])
+def test_emu_materialize_layouts_bit_exact(emu, twin, strategy, n, k):
+    from simple_es_b200.engine import population_layout
+    P, group, n_head, n_par = population_layout(strategy, n, k)
+    eng = emu(population=P, group=group, n_head=n_head, n_parents=n_par, seed=5)
+    parents = np.random.default_rng(1).normal(0, 1, (n_par, D)).astype(np.float32)
+    ids = np.arange(P, dtype=np.int32)
+    got = eng.materialize(7, 0.37, parents, ids)
+    assert np.array_equal(got, twin.materialize(parents, 0.37, 5, 7, group, n_head, ids))
+    assert all(np.array_equal(got[i], parents[i // group]) for i in range(P) if i % group < n_head)
+
+
+# ------------------------------------------------------------------------------------- K1: CartPole MLP (slot kernel)
+@pytest.mark.parametrize("init_mode,pomdp,E", [("shared", False, 5), ("fresh", False, 3), ("shared", True, 5), ("shared", False, 1),
+                                               ("fresh", False, 7)])
+def test_emu_rollout_philox_bit_exact(emu, twin, init_mode, pomdp, E):
+    P = 333
+    eng = emu(population=P, group=P, n_head=1, eval_ep_num=E, pomdp=pomdp, init_mode=init_mode, seed=11)
+    mu = np.zeros((1, D), np.float32)
+    fit, steps = eng.rollout(2, 2.0, mu)
+    tf, ts = twin.population_cartpole(mu, pomdp=pomdp, sigma=2.0, seed=11, gen=2, group=P, n_head=1, n=P, E=E,
+                                      init_mode=0 if init_mode == "shared" else 1, nthreads=4)
+    assert np.array_equal(steps, ts) and np.array_equal(fit, tf)
+    assert ts.max() > 3 * ts.min()                          # ragged episode lengths: the warp scheduler re-arms lanes
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
+def test_emu_rollout_k1_variants_bit_exact(emu, twin, variant, monkeypatch):
+    """Every K1 code path (scalar / packed FFMA2, permuted slot table, weights of the lane's slot in registers) is the
+    same function: ragged and 500-step episodes, Philox and verification (w_override) inputs."""
+    monkeypatch.setenv("SES_K1_VARIANT", str(variant))
+    for P, sigma, seed, pomdp, mu in [(160, 2.0, 21, False, np.zeros((1, D), np.float32)), (40, 0.05, 22, False, _trained_mu()),
+                                      (96, 1.0, 23, True, np.zeros((1, D), np.float32))]:
+        eng = emu(population=P, group=P, n_head=1, eval_ep_num=5, seed=seed, pomdp=pomdp)
+        fit, steps = eng.rollout(1, sigma, mu)
+        tf, ts = twin.population_cartpole(mu, pomdp=pomdp, sigma=sigma, seed=seed, gen=1, group=P, n_head=1, n=P, E=5, nthreads=4)
+        assert np.array_equal(steps, ts) and np.array_equal(fit, tf)
+        if sigma < 1.0:
+            assert (ts == 2500).mean() > 0.5               # most episodes hit the 500-step truncation
+        eng.close()
+    rng = np.random.default_rng(5)
+    W = rng.normal(0, 1.5, (64, D)).astype(np.float32)
+    init = rng.uniform(-0.05, 0.05, (5, 4))
+    eng = emu(population=64, group=64, n_head=1, eval_ep_num=5)
+    fit, steps = eng.rollout(0, 0.0, None, w_override=W, init_states=init)
+    tf, ts = twin.population_cartpole(np.zeros((1, D), np.float32), n=64, group=64, E=5, W_override=W, init=init, nthreads=4)
+    assert np.array_equal(steps, ts) and np.array_equal(fit, tf)
+
+
+@pytest.mark.parametrize("E", [3, 1])
+def test_emu_rollout_16_and_32_slots_per_warp(emu, twin, E):
+    P = 200
+    eng = emu(population=P, group=P, n_head=1, eval_ep_num=E, seed=31)
+    mu = np.zeros((1, D), np.float32)
+    fit, steps = eng.rollout(4, 1.5, mu)
+    tf, ts = twin.population_cartpole(mu, sigma=1.5, seed=31, gen=4, group=P, n_head=1, n=P, E=E, nthreads=4)
+    assert np.array_equal(steps, ts) and np.array_equal(fit, tf)
+
+
+def test_emu_rollout_verification_mode_matches_reference(emu, twin, golden):
+    """The kernel source consumes the reference's own weight arrays and initial states (north_star verification mode).
+    Golden = reference RolloutWorker + GymEnvModel (torch CPU) over the float64 CartPole restatement."""
+    g = golden("rollout_cartpole_mlp")
+    W, init = g["W"], g["init"]
+    tid = [int(i) for i in g["trace_ids"]]
+    perm = np.array(tid + [i for i in range(W.shape[0]) if i not in tid])
+    P = W.shape[0]
+    eng = emu(population=P, group=P, n_head=1, eval_ep_num=int(g["E"]))
+    fit, steps, trace, actions = eng.rollout(0, 0.0, None, w_override=W[perm], init_states=init, n_trace=len(tid))
+    assert (fit == g["fitness"][perm]).mean() >= 0.999
+    actions = actions[:, :, 0]
+    for j in range(len(tid)):
+        ref = g["traces"][j]
+        n = int(np.isfinite(ref[:, 0]).sum())
+        assert np.array_equal(actions[j, :n], g["trace_actions"][j, :n])
+        assert np.abs(trace[j, :n] - ref[:n]).max() <= 1e-9      # north_star: 1e-9 over the first 200 steps
+        _, ttr, tac = twin.rollout_cartpole(W[perm][j], E=int(g["E"]), init=init, trace_steps=200)
+        m = int(np.isfinite(ttr[:, 0]).sum())
+        assert np.array_equal(trace[j, :m], ttr[:m]) and np.array_equal(actions[j, :m], tac[:m])
+
+
+def test_emu_rollout_edge_cases(emu, twin):
+    mu = np.zeros((1, D), np.float32)
+    eng = emu(population=64, group=64, max_step=1, eval_ep_num=4)            # every episode truncated after one step
+    fit, steps = eng.rollout(0, 1.0, mu)
+    assert np.all(steps == 4) and np.all(fit == 1.0)
+    eng = emu(population=2, group=2, eval_ep_num=32, seed=9)                 # smallest population, largest E
+    fit, steps = eng.rollout(5, 2.0, mu)
+    tf, ts = twin.population_cartpole(mu, sigma=2.0, seed=9, gen=5, group=2, n_head=1, n=2, E=32)
+    assert np.array_equal(steps, ts)
+    eng = emu(population=64, group=64, id_begin=10, id_end=10)               # empty slice: nothing written
+    fit, steps = eng.rollout(0, 1.0, mu)
+    assert np.all(steps == -1) and np.isnan(fit).all()
+    eng = emu(population=64, group=64, id_begin=5, id_end=38, seed=2)        # ragged slice writes only its own range
+    fit, steps = eng.rollout(1, 2.0, mu)
+    tf, ts = twin.population_cartpole(mu, sigma=2.0, seed=2, gen=1, group=64, n_head=1, id0=5, n=33)
+    assert np.array_equal(steps[5:38], ts) and np.all(steps[:5] == -1) and np.all(steps[38:] == -1)
+    eng = emu(population=50, group=50, seed=3)                               # CartPole-v0 = the 200-step limit
+    v0 = emu(env_name="CartPole-v0", population=50, group=50, seed=3, max_step=None)
+    _, s500 = eng.rollout(0, 0.05, _trained_mu())
+    _, s200 = v0.rollout(0, 0.05, _trained_mu())
+    assert s200.max() == 1000 and np.array_equal(s200, np.minimum(s200, 1000)) and s500.max() == 2500
+
+
+def test_emu_engine_rejects_bad_configs(emu):
+    with pytest.raises(RuntimeError, match="num_state=4"):
+        emu(obs_dim=5)
+    with pytest.raises(RuntimeError, match="eval_ep_num"):
+        emu(eval_ep_num=33)
+    with pytest.raises(RuntimeError, match="population"):
+        emu(population=1, group=1)
+    with pytest.raises(RuntimeError, match="parents"):
+        emu(population=64, group=16, n_parents=3)
+    with pytest.raises(RuntimeError, match="N=2 or N=3"):
+        emu(env_name="simple_spread", obs_dim=24, act_dim=5, n_agents=4)
+
+
+# ------------------------------------------------------------------------------------- K2
+@pytest.mark.parametrize("n", [2, 97, 4097, 65536 + 3, (1 << 18) + 5])
+def test_emu_rank_desc_bit_exact(emu, n):
+    eng = emu(population=n, group=n)
+    rng = np.random.default_rng(n)
+    kinds = ("float", "ties", "cartpole") if n <= 4097 else ("cartpole",)
+    for kind in kinds:
+        if kind == "float":
+            r = rng.normal(0, 100, n)
+        elif kind == "ties":
+            r = np.round(rng.normal(0, 3, n))                      # negative values, -0.0 / +0.0 and many ties
+            r[::7] = -0.0
+        else:
+            r = rng.integers(40, 2501, n) / 5.0
+        want = np.flip(np.argsort(r, kind="stable")).astype(np.int32)
+        if n <= 4097:
+            assert np.array_equal(eng.rank_desc(r, full_key=True), want), kind
+        if kind == "cartpole":                                     # integer-key fast path (2 radix passes)
+            assert np.array_equal(eng.rank_desc(r), want)
+            neg = emu(env_name="MountainCar-v0", obs_dim=2, act_dim=3, population=n, group=n, max_step=None)
+            assert np.array_equal(neg.rank_desc(-r), np.flip(np.argsort(-r, kind="stable")).astype(np.int32))
+
+
+def test_emu_rank_and_shaping_match_reference(emu, twin, golden):
+    g = golden("strategy_openai_es")
+    P = int(g["P"])
+    eng = emu(population=P, group=P)
+    for gen in range(3):
+        order, shaped = eng.rank_desc(g["rewards_%d" % gen], shaped=True, full_key=True)
+        assert np.array_equal(order, g["order_%d" % gen])                          # bit-exact indices
+        assert np.array_equal(shaped, twin.centered_rank(g["order_%d" % gen].astype(np.int32)))
+        np.testing.assert_allclose(shaped, g["shaped_%d" % gen], rtol=1e-12, atol=1e-15)
+    for name in ("strategy_simple_evolution", "strategy_simple_genetic"):
+        g = golden(name)
+        P, k = int(g["P"]), int(g["cfg_elite_num"])
+        eng = emu(population=P, group=P)
+        for gen in range(3):
+            assert np.array_equal(eng.rank_desc(g["rewards_%d" % gen], full_key=True)[:k], g["elite_ids_%d" % gen])
+
+
+# ------------------------------------------------------------------------------------- K3
+def test_emu_update_openai_regenerated_noise_bit_exact(emu, twin):
+    P = 4096 + 37                                                   # 130 level-0 blocks -> 3 level-1 groups (one ragged)
+    eng = emu(population=P, group=P, n_head=1, seed=21)
+    rng = np.random.default_rng(2)
+    shaped = twin.centered_rank(rng.permutation(P).astype(np.int32))
+    mu = rng.normal(0, 1, D).astype(np.float32); m = rng.normal(0, .01, D).astype(np.float32)
+    v = np.abs(rng.normal(0, .01, D)).astype(np.float32)
+    lr, sigma, t, gen = 0.1, 0.2, 4, 9
+    mu_d, m_d, v_d = mu.copy(), m.copy(), v.copy()
+    grad = eng.update_openai(gen, sigma, lr, t, shaped, mu_d, m_d, v_d)
+    g = twin.grad_openai(shaped, D, 21, gen, P, 1, -(lr / (P * sigma)))
+    assert np.array_equal(grad, g)
+    th, mm, vv = twin.adam(mu, m, v, g, eng.adam_a(lr, t))
+    assert np.array_equal(mu_d, th) and np.array_equal(m_d, mm) and np.array_equal(v_d, vv)
+
+
+def test_emu_update_openai_matches_reference_with_its_noise(emu, golden):
+    g = golden("strategy_openai_es")
+    P, lr = int(g["P"]), float(g["cfg_learning_rate"])
+    eng = emu(population=P, group=P, n_head=1)
+    m_d = np.zeros(D, np.float32); v_d = np.zeros(D, np.float32)
+    for gen in range(3):
+        sigma = float(g["sigma_before_%d" % gen])
+        mu_d = g["mu_before_%d" % gen].astype(np.float32).copy()
+        grad = eng.update_openai(gen, sigma, lr, gen + 1, g["shaped_%d" % gen], mu_d, m_d, v_d, eps_override=g["eps_%d" % gen])
+        np.testing.assert_allclose(grad, g["grad_%d" % gen], rtol=1e-4, atol=1e-7)
+        np.testing.assert_allclose(mu_d, g["mu_after_%d" % gen], rtol=1e-4, atol=1e-6)      # north_star rtol
+        np.testing.assert_allclose(m_d, g["adam_m_%d" % gen], rtol=1e-4, atol=1e-9)
+        np.testing.assert_allclose(v_d, g["adam_v_%d" % gen], rtol=2e-4, atol=1e-12)
+
+
+def test_emu_elite_mean_and_genetic_carry_over(emu, twin, golden):
+    g = golden("strategy_simple_evolution")
+    P, k = int(g["P"]), int(g["cfg_elite_num"])
+    eng = emu(population=P, group=P, n_head=2)
+    for gen in range(3):                                           # verification mode: the reference's populations
+        order = eng.rank_desc(g["rewards_%d" % gen], full_key=True)
+        assert np.array_equal(eng.elite_mean(gen, 0.0, None, order, k, w_override=g["pop_%d" % gen]), g["mu_after_%d" % gen])
+    rng = np.random.default_rng(4)
+    parent = rng.normal(0, 1, (1, D)).astype(np.float32)
+    eng = emu(population=97, group=97, n_head=2, seed=8)
+    order = rng.permutation(97).astype(np.int32)
+    assert np.array_equal(eng.elite_mean(3, 1.5, parent, order, 10),
+                          twin.elite_mean(twin.materialize(parent, 1.5, 8, 3, 97, 2, order[:10])))
+    g = golden("strategy_simple_genetic")
+    P, k = int(g["P"]), int(g["cfg_elite_num"])
+    eng = emu(population=P, group=P // k, n_head=1, n_parents=k)
+    for gen in range(3):
+        order = eng.rank_desc(g["rewards_%d" % gen], full_key=True)
+        assert np.array_equal(eng.materialize(gen, 0.0, None, order[:k], w_override=g["pop_%d" % gen]), g["elites_after_%d" % gen])
+
+
+def test_emu_generation_openai_host_matches_twin_composition(emu, twin):
+    """ses_generation_openai_host (bench.py's e2e entry point): K1 -> K2 (integer keys) -> K3 composed inside the library."""
+    P, E, lr, sigma, seed = 300, 5, 0.1, 0.5, 17
+    eng = emu(population=P, group=P, n_head=1, eval_ep_num=E, seed=seed)
+    mu = np.zeros(D, np.float32); m = np.zeros(D, np.float32); v = np.zeros(D, np.float32)
+    fit = np.zeros(P, np.float64)
+    tmu, tm, tv = mu.copy(), m.copy(), v.copy()
+    for gen in range(3):
+        total = eng.generation_openai_host(gen, sigma, lr, gen + 1, mu, m, v, fit)
+        tf, ts = twin.population_cartpole(tmu[None], sigma=sigma, seed=seed, gen=gen, group=P, n_head=1, n=P, E=E, nthreads=4)
+        assert total == ts.sum() and np.array_equal(fit, tf)
+        shaped = twin.centered_rank(twin.rank_desc(tf))
+        g = twin.grad_openai(shaped, D, seed, gen, P, 1, -(lr / (P * sigma)))
+        tmu, tm, tv = twin.adam(tmu, tm, tv, g, eng.adam_a(lr, gen + 1))
+        assert np.array_equal(mu, tmu) and np.array_equal(m, tm) and np.array_equal(v, tv)
+        sigma *= 0.999
+    assert eng.launches == 3 * 9                                    # K1 + sort init + 2 x (hist, scatter) + shape + 2 x K3
+
+
+# ------------------------------------------------------------------------------------- sharding, antithetic
+@pytest.mark.parametrize("env,obs,act,gru,P,world", [("CartPole-v1", 4, 2, False, 301, 2), ("CartPole-v1", 4, 2, True, 41, 3),
+                                                     ("simple_spread", 12, 5, False, 100, 8), ("Acrobot-v1", 6, 3, False, 77, 2)])
+def test_emu_block_cyclic_shards_reproduce_the_whole_population(emu, env, obs, act, gru, P, world):
+    from simple_es_b200.engine import cyclic_block, owned_ids
+    kw = dict(env_name=env, obs_dim=obs, act_dim=act, gru=gru, population=P, group=P, n_head=1, eval_ep_num=3, seed=8,
+              max_step=60 if env == "Acrobot-v1" else None, init_mode="fresh")
+    whole = emu(**kw)
+    mu = np.random.default_rng(2).normal(0, 0.4, (1, whole.D)).astype(np.float32)
+    fit1, steps1 = whole.rollout(2, 0.9, mu)
+    B = cyclic_block(P, world)
+    fit = np.full(P, np.nan); steps = np.full(P, -1, dtype=np.int64)
+    for r in range(world):
+        eng = emu(shard=(r, world, B), **kw)
+        assert eng.n_local == owned_ids(P, r, world, B).size
+        eng.rollout(2, 0.9, mu, fitness=fit, steps=steps)
+        eng.close()
+    assert np.array_equal(fit, fit1) and np.array_equal(steps, steps1)
+    ids = owned_ids(P, 1, world, B)                                # verification mode: rows in local (work-queue) order
+    W = whole.materialize(2, 0.9, mu, ids.astype(np.int32))
+    eng = emu(shard=(1, world, B), **kw)
+    f2 = np.zeros(P); s2 = np.zeros(P, dtype=np.int64)
+    eng.rollout(2, 0.0, None, fitness=f2, steps=s2, w_override=W, n_trace=min(4, ids.size))
+    assert np.array_equal(f2[ids], fit1[ids])
+
+
+@pytest.mark.parametrize("strategy,n,k,gru", [("openai_es", 257, None, False), ("simple_genetic", 120, 8, False), ("simple_evolution", 24, 10, True)])
+def test_emu_antithetic_sampling_bit_exact_and_mirrored(emu, twin, strategy, n, k, gru):
+    from simple_es_b200.engine import population_layout
+    P, group, n_head, n_par = population_layout(strategy, n, k)
+    Dn = DG if gru else D
+    eng = emu(population=P, group=group, n_head=n_head, n_parents=n_par, gru=gru, seed=17, antithetic=True)
+    parents = np.random.default_rng(1).normal(0, 0.3, (n_par, Dn)).astype(np.float32)
+    twin.set_antithetic(True)
+    try:
+        ids = np.arange(P, dtype=np.int32)
+        got = eng.materialize(5, 0.7, parents, ids)
+        assert np.array_equal(got, twin.materialize(parents, 0.7, 17, 5, group, n_head, ids))
+        zero = eng.materialize(5, 0.7, np.zeros_like(parents), ids)
+        for g0 in range(0, P, group):
+            pert = zero[g0 + n_head:g0 + group]
+            m = (pert.shape[0] // 2) * 2
+            assert np.array_equal(pert[0:m:2], -pert[1:m:2]) and np.any(pert[0] != 0)
+        fit, steps = eng.rollout(5, 0.7, parents)
+        tf, ts = twin.population_cartpole(parents, gru=gru, sigma=0.7, seed=17, gen=5, group=group, n_head=n_head, n=P, E=5, nthreads=4)
+        assert np.array_equal(steps, ts) and np.array_equal(fit, tf)
+        if strategy == "openai_es":
+            order, shaped = eng.rank_desc(fit, shaped=True)
+            mu = parents[0].copy(); m_ = np.zeros(Dn, np.float32); v_ = np.zeros(Dn, np.float32)
+            gout = eng.update_openai(5, 0.7, 0.1, 1, shaped, mu, m_, v_)
+            g = twin.grad_openai(twin.centered_rank(twin.rank_desc(tf)), Dn, 17, 5, group, n_head, -(0.1 / (P * 0.7)))
+            assert np.array_equal(gout, g)
+    finally:
+        twin.set_antithetic(False)
+
+
+# ------------------------------------------------------------------------------------- K1: GRU policy (warp per offspring)
+@pytest.mark.parametrize("pomdp,E,sigma", [(True, 5, 0.7), (False, 3, 0.3), (True, 7, 0.7), (False, 1, 0.5)])
+def test_emu_rollout_gru_philox_bit_exact(emu, twin, pomdp, E, sigma):
+    P = 40
+    eng = emu(population=P, group=P, n_head=2, eval_ep_num=E, gru=True, pomdp=pomdp, seed=13)
+    mu = np.random.default_rng(7).normal(0, 0.3, (1, DG)).astype(np.float32)
+    fit, steps = eng.rollout(4, sigma, mu)
+    tf, ts = twin.population_cartpole(mu, gru=True, pomdp=pomdp, sigma=sigma, seed=13, gen=4, group=P, n_head=2, n=P, E=E, nthreads=4)
+    assert np.array_equal(steps, ts) and np.array_equal(fit, tf)
+    assert ts[0] == ts[1]                                   # simple_evolution layout: offspring 0 and 1 are both mu
+
+
+def test_emu_rollout_gru_verification_mode_matches_reference(emu, golden):
+    g = golden("rollout_cartpole_gru_pomdp")
+    W, init, E = g["W"], g["init"], int(g["E"])
+    tid = [int(i) for i in g["trace_ids"]]
+    perm = np.array(tid + [i for i in range(W.shape[0]) if i not in tid])
+    P = W.shape[0]
+    eng = emu(population=P, group=P, n_head=1, eval_ep_num=E, gru=True, pomdp=True)
+    fit, steps, trace, actions = eng.rollout(0, 0.0, None, w_override=W[perm], init_states=init, n_trace=len(tid))
+    assert (fit == g["fitness"][perm]).mean() >= 0.999
+    actions = actions[:, :, 0]
+    for j in range(len(tid)):
+        ref = g["traces"][j]
+        n = int(np.isfinite(ref[:, 0]).sum())
+        assert np.array_equal(actions[j, :n], g["trace_actions"][j, :n])
+        assert np.abs(trace[j, :n] - ref[:n]).max() <= 1e-9
+
+
+# ------------------------------------------------------------------------------------- K1: simple_spread
+@pytest.mark.parametrize("N,E,init_mode", [(2, 5, "shared"), (3, 5, "shared"), (2, 4, "fresh"), (3, 2, "fresh")])
+def test_emu_rollout_spread_philox_bit_exact(emu, twin, N, E, init_mode):
+    P = 150
+    Dn = 6 * N * 32 + 32 + 5 * 32 + 5
+    eng = emu(env_name="simple_spread", obs_dim=6 * N, act_dim=5, n_agents=N, max_step="None", population=P, group=P,
+              n_head=1, eval_ep_num=E, seed=19, init_mode=init_mode)
+    assert eng.D == Dn
+    mu = np.random.default_rng(3).normal(0, 0.5, (1, Dn)).astype(np.float32)
+    fit, steps = eng.rollout(6, 0.8, mu)
+    tf, ts = twin.population_mpe(mu, N=N, sigma=0.8, seed=19, gen=6, group=P, n_head=1, n=P, E=E,
+                                 init_mode=0 if init_mode == "shared" else 1)
+    assert np.array_equal(steps, ts) and np.all(ts == 25 * E)
+    assert np.array_equal(fit, tf)                          # float64 returns under the contract: bit-exact
+
+
+@pytest.mark.parametrize("name", ["rollout_spread_n2", "rollout_spread_n3"])
+def test_emu_rollout_spread_verification_mode_matches_reference(emu, golden, name):
+    g = golden(name)
+    W, init, N, E = g["W"], g["init"], int(g["N"]), int(g["E"])
+    P = W.shape[0]
+    eng = emu(env_name="simple_spread", obs_dim=6 * N, act_dim=5, n_agents=N, max_step="None", population=P, group=P,
+              n_head=1, eval_ep_num=E)
+    nt = g["traces"].shape[0]
+    fit, steps, trace, actions = eng.rollout(0, 0.0, None, w_override=W, init_states=init, n_trace=nt)
+    np.testing.assert_allclose(fit, g["fitness"], rtol=1e-12)
+    assert np.array_equal(actions[:, :25], g["trace_actions"])
+    assert np.abs(trace[:, :25] - g["traces"]).max() <= 1e-9
+
+
+# ------------------------------------------------------------------------------------- K1: MountainCar-v0, Acrobot-v1
+CLASSIC = {"MountainCar-v0": (2, 3, 195, "rollout_mountaincar"), "Acrobot-v1": (6, 3, 323, "rollout_acrobot")}
+
+
+@pytest.mark.parametrize("env", list(CLASSIC))
+@pytest.mark.parametrize("E,init_mode,sigma", [(5, "shared", 2.0), (3, "fresh", 1.0), (1, "fresh", 3.0)])
+def test_emu_rollout_classic_philox_bit_exact(emu, twin, env, E, init_mode, sigma):
+    P = 64 if env == "Acrobot-v1" else 120
+    obs, act, Dn, _ = CLASSIC[env]
+    eng = emu(env_name=env, obs_dim=obs, act_dim=act, max_step=None, population=P, group=P, eval_ep_num=E, seed=23, init_mode=init_mode)
+    assert eng.D == Dn
+    mu = np.random.default_rng(4).normal(0, 0.5, (1, Dn)).astype(np.float32)
+    fit, steps = eng.rollout(3, sigma, mu)
+    tf, ts = twin.population_classic(env, mu, sigma=sigma, seed=23, gen=3, group=P, n_head=1, n=P, E=E,
+                                     init_mode=0 if init_mode == "shared" else 1)
+    assert np.array_equal(steps, ts) and np.array_equal(fit, tf)
+
+
+@pytest.mark.parametrize("env", list(CLASSIC))
+def test_emu_rollout_classic_traces_equal_the_twin(emu, twin, golden, env):
+    """Verification mode on the reference-driven golden inputs: the emulated kernel's traces are the twin's, bit for bit
+    (how far the twin is from the reference's libm path is the subject of tests/test_oracle_classic.py)."""
+    obs, act, Dn, name = CLASSIC[env]
+    g = golden(name)
+    W, init, E = g["W"][:12], g["init"], int(g["E"])
+    eng = emu(env_name=env, obs_dim=obs, act_dim=act, max_step=None, population=12, group=12, eval_ep_num=E)
+    fit, steps, trace, actions = eng.rollout(0, 0.0, None, w_override=W, init_states=init, n_trace=12)
+    for j in range(12):
+        tf, tsteps, ttr, tac = twin.rollout_classic(env, W[j], E=E, init=init, trace_steps=200)
+        m = int(np.isfinite(ttr[:, 0]).sum())
+        assert m > 0 and np.array_equal(trace[j, :m], ttr[:m]) and np.array_equal(actions[j, :m, 0], tac[:m])
+        assert fit[j] == tf and steps[j] == tsteps
