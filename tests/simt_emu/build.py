@@ -95,9 +95,9 @@ ASM = [
      r"\1 = simt::min_xorsign_abs(\2, \3);"),
     (re.compile(r'asm volatile\("mov\.u32 %0, %%lanemask_lt;"\s*:\s*"=r"\((.+?)\)\);'), r"\1 = simt::lanemask_lt();"),
     (re.compile(r'asm volatile\("st\.release\.sys\.global\.u64 \[%0\], %1;"\s*::\s*"l"\((.+?)\),\s*"l"\((.+?)\)\s*:\s*"memory"\);'),
-     r"*(\1) = (\2);"),
+     r"__atomic_store_n((unsigned long long *)(\1), (unsigned long long)(\2), __ATOMIC_RELEASE);"),
     (re.compile(r'asm volatile\("ld\.acquire\.sys\.global\.u64 %0, \[%1\];"\s*:\s*"=l"\((.+?)\)\s*:\s*"l"\((.+?)\)\s*:\s*"memory"\);'),
-     r"\1 = *(\2);"),
+     r"\1 = __atomic_load_n((unsigned long long *)(\2), __ATOMIC_ACQUIRE);"),
 ]
 DYN_SMEM = re.compile(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?unsigned char (\w+)\[\];")
 

@@ -148,6 +148,29 @@ class EmuEngine:
                                                         _p(v), _p(fitness), _p(total), None))
         return int(total[0])
 
+    # ------------------------------------------------------------------ peer exchange (emulated ranks = threads of this process)
+    def peer_export(self):
+        mine = C.create_string_buffer(64)
+        self._check(self.lib.ses_peer_export(self._h, mine))
+        return mine.raw
+
+    def peer_attach(self, handles, rank, world):
+        """-> the two [P] float64 exchange buffers (views of library-owned memory), by generation parity."""
+        blob = C.create_string_buffer(b"".join(handles), 64 * world)
+        self._check(self.lib.ses_peer_attach(self._h, blob, int(rank), int(world)))
+        bufs = []
+        for parity in (0, 1):
+            ptr = C.c_void_p()
+            self._check(self.lib.ses_peer_fitness_ptr(self._h, parity, C.byref(ptr)))
+            bufs.append(np.ctypeslib.as_array((C.c_double * self.P).from_address(ptr.value)))
+        return bufs
+
+    def peer_barrier(self):
+        self._check(self.lib.ses_peer_barrier(self._h, None))
+
+    def peer_check(self):
+        self._check(self.lib.ses_peer_check(self._h))
+
     def test_math(self, kind, x):
         kinds = {"tanh": 0, "sigmoid": 1, "ln": 2, "sin2pi": 3, "cos2pi": 4, "sin64": 5, "cos64": 6, "tanh_fast": 7,
                  "sin64_full": 8, "cos64_full": 9}

@@ -6,7 +6,8 @@
 // simple_es_b200._lib.load() knows only libses_b200.so, and every product entry point fails without a CUDA device
 // (tests/test_host_logic.py::test_no_cpu_fallback).  It says nothing about performance, races between warps or the
 // memory model: every CUDA thread is a ucontext fiber, a warp's lanes run one after the other up to their next warp
-// collective, CTAs run one after the other.
+// collective, CTAs run one after the other.  All emulator state is thread_local: a multi-GPU test runs one emulated
+// rank per OS thread of one process (peer "IPC" mappings are plain pointers, the flag barrier spins across threads).
 //
 // What is emulated: __global__ functions called through simt::launch (the build script rewrites <<< >>>), threadIdx /
 // blockIdx / blockDim / gridDim (x only), static and dynamic __shared__, __syncthreads, __syncwarp, __ballot_sync,
@@ -31,7 +32,7 @@
 #define __global__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
-#define __shared__ static
+#define __shared__ static thread_local
 #define __constant__ static const
 #define __align__(n) alignas(n)
 
@@ -77,13 +78,13 @@ struct Fiber {
     Warp *warp;
 };
 
-inline Fiber *g_cur = nullptr;
-inline ucontext_t g_sched;
-inline uint3 g_blockIdx = {0, 0, 0};
-inline dim3 g_blockDim, g_gridDim;
-inline unsigned char *g_dyn_smem = nullptr;
-inline int g_cta_waiting = 0;
-inline unsigned long long g_switches = 0, g_launches = 0;
+inline thread_local Fiber *g_cur = nullptr;
+inline thread_local ucontext_t g_sched;
+inline thread_local uint3 g_blockIdx = {0, 0, 0};
+inline thread_local dim3 g_blockDim, g_gridDim;
+inline thread_local unsigned char *g_dyn_smem = nullptr;
+inline thread_local int g_cta_waiting = 0;
+inline thread_local unsigned long long g_switches = 0, g_launches = 0;
 
 inline unsigned char *dyn_smem() { return g_dyn_smem; }
 
@@ -149,7 +150,7 @@ struct Stacks {
         return base;
     }
 };
-inline Stacks g_stacks;
+inline thread_local Stacks g_stacks;
 
 template <class F>
 void fiber_entry(unsigned lo, unsigned hi)
@@ -436,9 +437,11 @@ template <class K>
 inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return cudaSuccess; }
 template <class K>
 inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, K, int, size_t) { *n = 2; return cudaSuccess; }
-inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return cudaErrorNotSupported; }
-inline cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
-inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaErrorNotSupported; }
+// "IPC": the emulated ranks of a multi-GPU test live in ONE process (one OS thread per rank), so a memory handle is just
+// the pointer and a peer mapping is the buffer itself
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) { memset(h, 0, sizeof(*h)); memcpy(h->reserved, &p, sizeof(p)); return cudaSuccess; }
+inline cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, h.reserved, sizeof(*p)); return cudaSuccess; }
+inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
 inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new simt_event{0.0}; return cudaSuccess; }
 inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
 inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) { e->t = (double)clock64() * 1e-6; return cudaSuccess; }

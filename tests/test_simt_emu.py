@@ -443,3 +443,67 @@ def test_emu_rollout_classic_traces_equal_the_twin(emu, twin, golden, env):
         m = int(np.isfinite(ttr[:, 0]).sum())
         assert m > 0 and np.array_equal(trace[j, :m], ttr[:m]) and np.array_equal(actions[j, :m, 0], tac[:m])
         assert fit[j] == tf and steps[j] == tsteps
+
+
+# ------------------------------------------------------------------------------------- multi-GPU: peer exchange fused into K1
+def _openai_rank(emu, rank, world, P, gens, seed, barrier, handles, out, shard_mode):
+    """One emulated rank (an OS thread): the steps of strategies.OpenAIES.step() with the peer exchange."""
+    from simple_es_b200.engine import cyclic_block, shard_bounds
+    try:
+        if world == 1:
+            eng = emu(population=P, group=P, n_head=1, seed=seed)
+            bufs = [np.zeros(P), np.zeros(P)]
+        else:
+            if shard_mode == "cyclic":
+                eng = emu(population=P, group=P, n_head=1, seed=seed, shard=(rank, world, cyclic_block(P, world)))
+            else:
+                lo, hi = shard_bounds(P, rank, world)
+                eng = emu(population=P, group=P, n_head=1, seed=seed, id_begin=lo, id_end=hi)
+            handles[rank] = eng.peer_export()
+            barrier.wait()
+            bufs = eng.peer_attach(handles, rank, world)
+            barrier.wait()
+        mu = np.zeros((1, D), np.float32); m = np.zeros(D, np.float32); v = np.zeros(D, np.float32)
+        steps = np.zeros(P, dtype=np.int64)
+        sigma, lr, hist = 0.5, 0.1, []
+        for gen in range(gens):
+            fit = bufs[gen & 1]
+            eng.rollout(gen, sigma, mu, fitness=fit, steps=steps)        # K1 stores each fitness into every peer's buffer
+            if world > 1:
+                eng.peer_barrier()
+            order, shaped = eng.rank_desc(fit, shaped=True)
+            eng.update_openai(gen, sigma, lr, gen + 1, shaped, mu[0], m, v)   # gradient rows sharded over the ranks + barrier
+            sigma *= 0.999
+            hist.append((fit.copy(), order.copy(), mu.copy(), m.copy(), v.copy()))
+        if world > 1:
+            eng.peer_check()
+            barrier.wait()                                               # nobody frees its buffer while a peer may still write
+        out[rank] = hist
+    except BaseException as exc:                                         # pragma: no cover
+        out[rank] = exc
+        barrier.abort()
+        raise
+
+
+@pytest.mark.parametrize("world,shard_mode,P", [(2, "cyclic", 301), (3, "contiguous", 200), (8, "cyclic", 2200)])
+def test_emu_peer_exchange_ranks_equal_single_rank(emu, world, shard_mode, P):
+    """SURVEY 8e on the emulator: W ranks (threads), each rolling out its shard with the fitness exchange fused into K1
+    (stores into every peer's buffer + flag barrier, double buffered by generation parity) and its share of the gradient's
+    level-1 rows, finish every generation with the SAME fitness vector, rank order and (mu, m, v) as one rank doing it all."""
+    import threading
+    gens, seed = 3, 29
+    ref = {}
+    _openai_rank(emu, 0, 1, P, gens, seed, None, None, ref, None)
+    barrier = threading.Barrier(world, timeout=120)
+    handles, out = [None] * world, {}
+    threads = [threading.Thread(target=_openai_rank, args=(emu, r, world, P, gens, seed, barrier, handles, out, shard_mode))
+               for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    for r in range(world):
+        assert not isinstance(out.get(r), BaseException) and out.get(r) is not None, out.get(r)
+        for gen in range(gens):
+            for a, b in zip(out[r][gen], ref[0][gen]):
+                assert np.array_equal(a, b), (r, gen)
