@@ -116,6 +116,43 @@ def test_emu_rollout_k1_variants_bit_exact(emu, twin, variant, monkeypatch):
     assert np.array_equal(steps, ts) and np.array_equal(fit, tf)
 
 
+@pytest.mark.parametrize("case", range(8))
+def test_emu_rollout_scheduler_random_shapes(emu, twin, case, monkeypatch):
+    """The warp scheduler's result does not depend on how work is laid out: random population sizes, episode counts, lanes
+    taking work (SES_ROLLOUT_LANES), grid limits (SES_ROLLOUT_CTAS_PER_SM, emulated SM count) and slices -- same bits."""
+    rng = np.random.default_rng(100 + case)
+    E = int(rng.choice([1, 2, 3, 4, 5, 6, 8, 11, 32]))
+    P = int(rng.integers(2, 260))
+    lo = int(rng.integers(0, P)); hi = int(rng.integers(lo, P + 1))
+    if rng.random() < 0.5:
+        monkeypatch.setenv("SES_ROLLOUT_LANES", str(int(rng.integers(1, 33))))
+    monkeypatch.setenv("SES_ROLLOUT_CTAS_PER_SM", str(int(rng.integers(1, 3))))
+    monkeypatch.setenv("SES_SIMT_EMU_SMS", str(int(rng.integers(1, 4))))
+    init_mode = "fresh" if rng.random() < 0.5 else "shared"
+    n_head = int(rng.integers(0, 3))
+    eng = emu(population=P, group=P, n_head=n_head, eval_ep_num=E, seed=case, init_mode=init_mode, id_begin=lo, id_end=hi,
+              max_step=int(rng.choice([500, 37])))
+    mu = rng.normal(0, 0.2, (1, D)).astype(np.float32)
+    fit, steps = eng.rollout(case, 1.0, mu)
+    tf, ts = twin.population_cartpole(mu, sigma=1.0, seed=case, gen=case, group=P, n_head=n_head, id0=lo, n=hi - lo, E=E,
+                                      max_step=eng.max_step, init_mode=0 if init_mode == "shared" else 1, nthreads=2)
+    assert np.array_equal(steps[lo:hi], ts) and np.array_equal(fit[lo:hi], tf)
+    assert np.all(steps[:lo] == -1) and np.all(steps[hi:] == -1)
+
+
+def test_emu_spread_eight_slot_build(emu, twin, monkeypatch):
+    """SES_SPREAD_SLOTS8=1 selects the 8-slot simple_spread instantiations (the default for E >= 5 is 6 slots): same bits."""
+    monkeypatch.setenv("SES_SPREAD_SLOTS8", "1")
+    for N in (2, 3):
+        P, Dn = 70, 6 * N * 32 + 32 + 165
+        eng = emu(env_name="simple_spread", obs_dim=6 * N, act_dim=5, n_agents=N, max_step="None", population=P, group=P,
+                  n_head=1, eval_ep_num=5, seed=5)
+        mu = np.random.default_rng(N).normal(0, 0.5, (1, Dn)).astype(np.float32)
+        fit, steps = eng.rollout(1, 0.6, mu)
+        tf, ts = twin.population_mpe(mu, N=N, sigma=0.6, seed=5, gen=1, group=P, n_head=1, n=P, E=5)
+        assert np.array_equal(steps, ts) and np.array_equal(fit, tf)
+
+
 @pytest.mark.parametrize("E", [3, 1])
 def test_emu_rollout_16_and_32_slots_per_warp(emu, twin, E):
     P = 200
