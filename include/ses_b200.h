@@ -114,6 +114,14 @@ int ses_update_openai(ses_handle *h, uint32_t generation, const double *shaped_d
                       double beta2, double adam_eps, float *mu_dev, float *m_dev, float *v_dev,
                       float *grad_out_dev, void *stream);
 
+/* K3a' -- the same gradient followed by SGD with momentum instead of Adam.  Opt-in (engine.optimizer: sgd): the reference's
+ * optimizers.py ships Adam only; this is the SGD of the file it names as its source (OpenAI es_distributed/optimizers.py):
+ * v = momentum*v + (1-momentum)*g; theta += -stepsize*v, all float32 (numpy >= 2 dtypes of the reference's list-of-arrays idiom).
+ *   mu/v [D] f32 updated in place; update_factor = -lr/(P*sigma); stepsize = learning_rate; momentum in [0, 1). */
+int ses_update_openai_sgd(ses_handle *h, uint32_t generation, const double *shaped_dev,
+                          const float *eps_override_dev, double update_factor, double stepsize, double momentum,
+                          float *mu_dev, float *v_dev, float *grad_out_dev, void *stream);
+
 /* K3b -- replaces _gen_offsprings' materialisation for selected ids: rows of out_dev [n][D] are the
  * weights offspring ids_dev[j] had in `generation` (parent + sigma*Philox noise).  Used for the
  * simple_genetic elite carry-over (offspring_strategies.py:114-116) and for checkpoints. */

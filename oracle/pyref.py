@@ -460,6 +460,24 @@ class AdamPort:
         return theta
 
 
+class SGDPort:
+    """SGD with momentum in the reference's idiom.  optimizers.py ships Adam only; its header names OpenAI's
+    es_distributed/optimizers.py as the source, whose SGD._compute_step is restated here on one flat float32 vector
+    (numpy >= 2: the Python floats are weak scalars, every product and sum is float32)."""
+
+    def __init__(self, D, stepsize, momentum=0.9):
+        self.stepsize, self.momentum = stepsize, momentum
+        self.t = 0
+        self.v = np.zeros(D, dtype=np.float32)
+
+    def update(self, theta, g):
+        self.t += 1
+        self.v = self.momentum * self.v + (1. - self.momentum) * g
+        step = -self.stepsize * self.v
+        theta += step
+        return theta
+
+
 class StrategyPort:
     """The three offspring strategies on a flat parameter vector, with the reference's
     population layouts, update arithmetic and sigma-decay ordering."""

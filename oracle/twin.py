@@ -212,6 +212,13 @@ def adam(theta, m, v, g, a, beta1=0.99, beta2=0.999, epsilon=1e-8):
     return theta, m, v
 
 
+def sgd(theta, v, g, stepsize, momentum=0.9):
+    """In-place on copies; returns (theta, v)."""
+    theta = _f32(theta).copy(); v = _f32(v).copy(); g = _f32(g)
+    lib().tw_sgd(_p(theta), _p(v), _p(g), C.c_int(theta.size), C.c_double(stepsize), C.c_double(momentum))
+    return theta, v
+
+
 def elite_mean(elites):
     elites = _f32(elites)
     k, D = elites.shape

@@ -449,19 +449,16 @@ extern "C" int ses_rank_desc(ses_handle *h, const double *fitness_dev, int32_t n
 // ------------------------------------------------------------------------------------------------
 // K3
 // ------------------------------------------------------------------------------------------------
-extern "C" int ses_update_openai(ses_handle *h, uint32_t generation, const double *shaped_dev,
-                                 const float *eps_override_dev, double update_factor, double adam_a, double beta1,
-                                 double beta2, double adam_eps, float *mu_dev, float *m_dev, float *v_dev,
-                                 float *grad_out_dev, void *stream)
+// levels 0 + 1 of the gradient (k_grad_partial, and the peer barrier when the rows are sharded over ranks);
+// *part1_out is the [nb1][DP] table the level-2 kernels read
+static int grad_levels01(ses_handle *h, uint32_t generation, const double *shaped_dev, const float *eps_override_dev,
+                         void *stream, double **part1_out)
 {
-    if (!h) return fail("ses_update_openai: null handle");
-    if (!shaped_dev || !mu_dev || !m_dev || !v_dev) return fail("ses_update_openai: null buffer");
-    CU(cudaSetDevice(h->cfg.device));
     cudaStream_t st = S(stream);
     const int P = h->cfg.population;
     Layout lay{h->cfg.group, h->cfg.n_head, h->cfg.antithetic};
-    // levels 0+1 of the gradient: all groups here, or -- with peers attached -- this rank's share of the groups,
-    // each row stored into every peer's table over NVLink, then the flag barrier
+    // all groups here, or -- with peers attached -- this rank's share of the groups, each row stored into every
+    // peer's table over NVLink, then the flag barrier
     const bool shard = h->peer_world > 1 && h->xbuf && !eps_override_dev;
     double *part1 = shard ? xbuf_part1(h->xbuf, h) : h->part1;
     int g0 = 0, g1 = h->nb1;
@@ -481,9 +478,42 @@ extern "C" int ses_update_openai(ses_handle *h, uint32_t generation, const doubl
         h->launches += 1;
     }
     if (shard && ses_peer_barrier(h, stream)) return -1;
+    *part1_out = part1;
+    return 0;
+}
+
+extern "C" int ses_update_openai(ses_handle *h, uint32_t generation, const double *shaped_dev,
+                                 const float *eps_override_dev, double update_factor, double adam_a, double beta1,
+                                 double beta2, double adam_eps, float *mu_dev, float *m_dev, float *v_dev,
+                                 float *grad_out_dev, void *stream)
+{
+    if (!h) return fail("ses_update_openai: null handle");
+    if (!shaped_dev || !mu_dev || !m_dev || !v_dev) return fail("ses_update_openai: null buffer");
+    CU(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = S(stream);
+    double *part1 = nullptr;
+    if (grad_levels01(h, generation, shaped_dev, eps_override_dev, stream, &part1)) return -1;
     k_grad_final_adam<<<(h->D + 255) / 256, 256, 0, st>>>(part1, h->nb1, h->DP, h->D, (float)update_factor, adam_a, (float)beta1,
                                                          (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)adam_eps,
                                                          mu_dev, m_dev, v_dev, grad_out_dev);
+    h->launches += 1;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ses_update_openai_sgd(ses_handle *h, uint32_t generation, const double *shaped_dev,
+                                     const float *eps_override_dev, double update_factor, double stepsize, double momentum,
+                                     float *mu_dev, float *v_dev, float *grad_out_dev, void *stream)
+{
+    if (!h) return fail("ses_update_openai_sgd: null handle");
+    if (!shaped_dev || !mu_dev || !v_dev) return fail("ses_update_openai_sgd: null buffer");
+    if (!(momentum >= 0.0 && momentum < 1.0)) return fail("ses_update_openai_sgd: momentum must be in [0, 1)");
+    CU(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = S(stream);
+    double *part1 = nullptr;
+    if (grad_levels01(h, generation, shaped_dev, eps_override_dev, stream, &part1)) return -1;
+    k_grad_final_sgd<<<(h->D + 255) / 256, 256, 0, st>>>(part1, h->nb1, h->DP, h->D, (float)update_factor, (float)(-stepsize),
+                                                        (float)momentum, (float)(1.0 - momentum), mu_dev, v_dev, grad_out_dev);
     h->launches += 1;
     CU(cudaGetLastError());
     return 0;

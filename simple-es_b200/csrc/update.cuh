@@ -98,6 +98,25 @@ __global__ void __launch_bounds__(256) k_grad_final_adam(const double *__restric
     mu[d] = (float)__dadd_rn((double)mu[d], step);              // optimizers.py:22-24
 }
 
+// level 2 + scale + SGD with momentum.  optimizers.py has Adam only; its header names OpenAI's es_distributed/optimizers.py
+// as the source, whose SGD is  v = momentum * v + (1 - momentum) * g;  step = -stepsize * v.  With the reference's
+// list-of-float32-arrays idiom under numpy >= 2 every operand is float32 (Python floats are weak scalars): four
+// separately rounded float32 operations and a float32 `theta += step`.  Opt-in (engine.optimizer: sgd).
+__global__ void __launch_bounds__(256) k_grad_final_sgd(const double *__restrict__ part1, int nb1, int DP, int D, float update_factor,
+                                                        float neg_stepsize, float mom, float omm, float *__restrict__ mu,
+                                                        float *__restrict__ v, float *__restrict__ grad_out)
+{
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= D) return;
+    double s = 0.0;
+    for (int g = 0; g < nb1; ++g) s = __dadd_rn(s, part1[(size_t)g * DP + d]);
+    const float gr = __fmul_rn((float)s, update_factor);
+    if (grad_out) grad_out[d] = gr;
+    const float vn = __fadd_rn(__fmul_rn(mom, v[d]), __fmul_rn(omm, gr));
+    v[d] = vn;
+    mu[d] = __fadd_rn(mu[d], __fmul_rn(neg_stepsize, vn));
+}
+
 // weights of selected offspring: out[j][D] = parent(ids[j]) + sigma * eps(gen, ids[j])
 __global__ void __launch_bounds__(256) k_materialize(const float *__restrict__ parents, const float *__restrict__ w_override,
                                                      Shard shard, int D, int NQ, float sigma, uint32_t seed, uint32_t gen,

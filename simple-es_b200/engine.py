@@ -224,6 +224,17 @@ class RolloutEngine:
                                               self.adam_a(lr, t, beta1, beta2), beta1, beta2, eps, _ptr(mu), _ptr(m),
                                               _ptr(v), _ptr(grad_out), self._stream()))
 
+    def update_openai_sgd(self, generation, sigma, lr, shaped, mu, v, momentum=0.9, eps_override=None, grad_out=None):
+        """In-place openai_es step on (mu, v) with SGD + momentum instead of Adam (engine.optimizer: sgd; the reference
+        ships Adam only -- this is the SGD of the OpenAI file optimizers.py names as its source)."""
+        for name, x in (("mu", mu), ("v", v)):
+            self._chk(x, torch.float32, self.D, name)
+        self._chk(shaped, torch.float64, self.P, "shaped")
+        eps_override = self._chk(eps_override, torch.float32, self.P * self.D, "eps_override")
+        uf = -1.0 * (lr / (self.P * sigma))              # offspring_strategies.py:406-408
+        _lib.check(self.lib.ses_update_openai_sgd(self._h, int(generation), _ptr(shaped), _ptr(eps_override), uf, float(lr),
+                                                  float(momentum), _ptr(mu), _ptr(v), _ptr(grad_out), self._stream()))
+
     def materialize(self, generation, sigma, parents, ids, w_override=None, out=None):
         ids = self._chk(ids, torch.int32, name="ids")
         n = ids.numel()

@@ -18,6 +18,7 @@ class _Base:
     def __init__(self, strategy_cfg, env_cfg, network_cfg, eval_ep_num, seed, device, engine_cfg):
         rank, ws = sdist.world()
         self.cfg = strategy_cfg
+        self.engine_cfg = engine_cfg
         self.sigma = float(strategy_cfg["init_sigma"])           # sigma the CURRENT population was drawn with
         self.curr_sigma = self.sigma                              # what the reference reports (post-decay)
         self.decay = float(strategy_cfg["sigma_decay"])
@@ -166,13 +167,22 @@ class OpenAIES(_Base):
         self.v = torch.zeros(self.D, dtype=torch.float32, device=dev)
         self.t = 0
         self.shaped = torch.empty(self.P, dtype=torch.float64, device=dev)
+        # engine.optimizer: "adam" (the reference's only optimizer, optimizers.py:30-57) or, opt-in, "sgd" with
+        # engine.momentum (the SGD of the OpenAI file optimizers.py names as its source; uses v only)
+        self.optimizer = self.engine_cfg.get("optimizer", "adam")
+        if self.optimizer not in ("adam", "sgd"):
+            raise ValueError("engine.optimizer must be 'adam' or 'sgd'")
+        self.momentum = float(self.engine_cfg.get("momentum", 0.9))
 
     def step(self):
         e = self.engine
         self._rollout_and_exchange()
         e.rank_desc(self.fitness, shaped=True, order=self.order, shaped_out=self.shaped)
         self.t += 1
-        e.update_openai(self.generation, self.sigma, self.lr, self.t, self.shaped, self.parents.view(-1), self.m, self.v)
+        if self.optimizer == "sgd":
+            e.update_openai_sgd(self.generation, self.sigma, self.lr, self.shaped, self.parents.view(-1), self.v, self.momentum)
+        else:
+            e.update_openai(self.generation, self.sigma, self.lr, self.t, self.shaped, self.parents.view(-1), self.m, self.v)
         self.sigma *= self.decay                                  # :418, after update_factor used the old sigma
         self.curr_sigma = self.sigma
         self.generation += 1

@@ -129,6 +129,13 @@ class EmuEngine:
                                                _p(grad), None))
         return grad
 
+    def update_openai_sgd(self, generation, sigma, lr, shaped, mu, v, momentum=0.9, eps_override=None):
+        grad = np.full(self.D, np.nan, dtype=np.float32)
+        uf = -1.0 * (lr / (self.P * sigma))
+        self._check(self.lib.ses_update_openai_sgd(self._h, int(generation), _p(_arr(shaped, np.float64)), _p(_arr(eps_override, np.float32)),
+                                                   uf, float(lr), float(momentum), _p(mu), _p(v), _p(grad), None))
+        return grad
+
     def materialize(self, generation, sigma, parents, ids, w_override=None):
         ids = _arr(ids, np.int32)
         out = np.full((ids.size, self.D), np.nan, dtype=np.float32)

@@ -57,6 +57,24 @@ def test_simple_genetic_loop_matches_oracle_composition(twin):
         assert s.curr_sigma == pytest.approx(sig_rep) and s.sigma == pytest.approx(sig_pop)
 
 
+def test_openai_es_sgd_option_matches_oracle_composition(twin):
+    """engine.optimizer: sgd (opt-in): the loop's generations equal rollout -> rank -> gradient -> SGD composed from the twin."""
+    from simple_es_b200.loop import B200Loop
+    cfg = _cfg("cartpole_openai.yaml", offspring_num=600, init_sigma=0.5, sigma_decay=0.99, learning_rate=0.05)
+    cfg["engine"].update(optimizer="sgd", momentum=0.8)
+    loop = B200Loop(cfg, 3, 1, 5, save_model_period=0, seed=5, quiet=True)
+    s = loop.strategy
+    P, sigma, mu, v = 600, 0.5, np.zeros(D, np.float32), np.zeros(D, np.float32)
+    for gen in range(3):
+        s.step()
+        tf, ts = twin.population_cartpole(mu[None], sigma=sigma, seed=5, gen=gen, group=P, n_head=1, n=P, E=5, nthreads=8)
+        assert np.array_equal(s.fitness.cpu().numpy(), tf)
+        g = twin.grad_openai(twin.centered_rank(twin.rank_desc(tf)), D, 5, gen, P, 1, -(0.05 / (P * sigma)))
+        mu, v = twin.sgd(mu, v, g, 0.05, 0.8)
+        assert np.array_equal(s.parents[0].cpu().numpy(), mu) and np.array_equal(s.v.cpu().numpy(), v)
+        sigma *= 0.99
+
+
 def test_openai_es_learns_cartpole_and_writes_reference_checkpoints(tmp_path, capsys):
     from simple_es_b200 import checkpoint
     from simple_es_b200.loop import B200Loop

@@ -264,6 +264,26 @@ def test_update_openai_regenerated_noise_bit_exact(twin):
     assert np.array_equal(mu_d.cpu().numpy(), th) and np.array_equal(m_d.cpu().numpy(), mm) and np.array_equal(v_d.cpu().numpy(), vv)
 
 
+def test_update_openai_sgd_bit_exact(twin):
+    """engine.optimizer: sgd (opt-in; the reference ships Adam only): the fixed-tree gradient followed by
+    v = mom*v + (1-mom)*g, theta += -lr*v in float32, bit-exact against the twin (itself pinned on a numpy restatement of the
+    OpenAI SGD the reference's optimizers.py names as its source, tests/test_oracle_strategy.py)."""
+    P = 4096 + 37
+    eng = _engine(population=P, group=P, n_head=1, seed=4)
+    rng = np.random.default_rng(6)
+    mu = rng.normal(0, 1, D).astype(np.float32); v = rng.normal(0, .01, D).astype(np.float32)
+    mu_d, v_d = _cuda(mu), _cuda(v)
+    grad_d = torch.empty(D, dtype=torch.float32, device="cuda")
+    sigma, lr = 0.3, 0.05
+    for gen, mom in [(0, 0.9), (1, 0.9), (2, 0.0)]:
+        shaped = twin.centered_rank(rng.permutation(P).astype(np.int32))
+        eng.update_openai_sgd(gen, sigma, lr, _cuda(shaped), mu_d, v_d, momentum=mom, grad_out=grad_d)
+        g = twin.grad_openai(shaped, D, 4, gen, P, 1, -(lr / (P * sigma)))
+        assert np.array_equal(grad_d.cpu().numpy(), g)
+        mu, v = twin.sgd(mu, v, g, lr, mom)
+        assert np.array_equal(mu_d.cpu().numpy(), mu) and np.array_equal(v_d.cpu().numpy(), v)
+
+
 def test_update_openai_matches_reference_with_its_noise(golden):
     """Verification mode: the kernel consumes the reference's own epsilon arrays (which hold
     mu+eps from generation 1 on, quirk Q1) and must land on the reference's mu / Adam state."""

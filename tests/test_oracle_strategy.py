@@ -133,3 +133,23 @@ def test_twin_antithetic_pairs_are_mirrored(twin):
     assert np.all(anti[:n_head] == 0) and np.array_equal(anti[n_head::2], plain[n_head::2])
     assert np.array_equal(anti[n_head + 1::2], -anti[n_head::2])
     assert np.array_equal(twin.materialize(zero, 1.0, 3, 7, P, n_head, ids), plain)
+
+
+def test_sgd_twin_matches_numpy_restatement(twin):
+    """Opt-in SGD (engine.optimizer: sgd): the reference ships Adam only, so the pin is the numpy restatement of the
+    OpenAI SGD its optimizers.py names as the source, in the reference's float32 list-of-arrays idiom (pyref.SGDPort)."""
+    from oracle import pyref
+    rng = np.random.default_rng(3)
+    D = 581
+    theta = rng.normal(0, 1, D).astype(np.float32)
+    opt = pyref.SGDPort(D, stepsize=0.05, momentum=0.9)
+    tt, tv = theta.copy(), np.zeros(D, np.float32)
+    for _ in range(5):
+        g = rng.normal(0, 0.02, D).astype(np.float32)
+        theta = opt.update(theta, g)
+        tt, tv = twin.sgd(tt, tv, g, 0.05, 0.9)
+        assert theta.dtype == np.float32 and opt.v.dtype == np.float32
+        assert np.array_equal(theta, tt) and np.array_equal(opt.v, tv)
+    # momentum 0: plain SGD, theta += -stepsize * g
+    t0, v0 = twin.sgd(tt, tv, g, 0.05, 0.0)
+    assert np.array_equal(v0, g) and np.array_equal(t0, tt + np.float32(-0.05) * g)

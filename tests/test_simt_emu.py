@@ -278,6 +278,25 @@ def test_emu_update_openai_regenerated_noise_bit_exact(emu, twin):
     assert np.array_equal(mu_d, th) and np.array_equal(m_d, mm) and np.array_equal(v_d, vv)
 
 
+def test_emu_update_openai_sgd_bit_exact(emu, twin):
+    """engine.optimizer: sgd (opt-in) -- same fixed-tree gradient, then v = mom*v + (1-mom)*g, theta += -lr*v in float32."""
+    P = 1000
+    eng = emu(population=P, group=P, n_head=1, seed=4)
+    rng = np.random.default_rng(6)
+    mu = rng.normal(0, 1, D).astype(np.float32); v = rng.normal(0, .01, D).astype(np.float32)
+    tmu, tv = mu.copy(), v.copy()
+    sigma, lr = 0.3, 0.05
+    for gen, mom in [(0, 0.9), (1, 0.9), (2, 0.0)]:
+        shaped = twin.centered_rank(rng.permutation(P).astype(np.int32))
+        grad = eng.update_openai_sgd(gen, sigma, lr, shaped, mu, v, momentum=mom)
+        g = twin.grad_openai(shaped, D, 4, gen, P, 1, -(lr / (P * sigma)))
+        assert np.array_equal(grad, g)
+        tmu, tv = twin.sgd(tmu, tv, g, lr, mom)
+        assert np.array_equal(mu, tmu) and np.array_equal(v, tv)
+    with pytest.raises(RuntimeError, match="momentum"):
+        eng.update_openai_sgd(0, sigma, lr, shaped, mu, v, momentum=1.0)
+
+
 def test_emu_update_openai_matches_reference_with_its_noise(emu, golden):
     g = golden("strategy_openai_es")
     P, lr = int(g["P"]), float(g["cfg_learning_rate"])
