@@ -372,6 +372,7 @@ def run_b200(args):
                                       "FLOP count no tanh; an accurate float32 tanh costs 14 FMA-pipe operations) x 2 FLOP / measured FFMA peak"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
     }
+    line["roofline"]["hbm_check"] = hbm_check(eng.n_local, k1_ms / args.steps if args.steps else 0.0)
     if world == 1 and not args.no_cpu:
         try:
             line["cpu_baseline"] = cpu_baseline_block(os.cpu_count() or 1)
@@ -379,6 +380,25 @@ def run_b200(args):
             line["cpu_baseline"] = {"error": str(exc)}
     print(json.dumps(line))
     return 0
+
+
+def hbm_check(n_local, k1_ms_per_launch):
+    """Why `roofline.bound` is not "hbm": K1's ALGORITHMIC bytes per launch (904 B of parameters read + 16 B of results
+    written per offspring) over its measured duration, against the measured HBM peak of
+    MEASURED_PEAKS.json (driver-written; fallback 6650 GB/s per B200_PROFILING.md)."""
+    try:
+        alg = D * 4 + 16 * int(n_local)
+        peak, src = 6650.0, "of fallback (B200_PROFILING.md)"
+        path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(path):
+            with open(path) as f:
+                peak, src = float(json.load(f)["hbm_gbs"]), "of measured (MEASURED_PEAKS.json hbm_gbs)"
+        gbs = alg / (k1_ms_per_launch * 1e-3) / 1e9 if k1_ms_per_launch > 0 else 0.0
+        return {"algorithmic_bytes_per_launch": alg, "achieved_gbs": gbs, "peak_gbs": peak, "peak_source": src,
+                "frac": gbs / peak, "note": "K1 is five orders of magnitude below the HBM roofline and uses no tensor-core "
+                "shaped work (per-offspring weights: GEMV only); the FP32 pipe is the bound that applies"}
+    except Exception as exc:  # pragma: no cover
+        return {"error": str(exc)}
 
 
 def measure_fp32_peak(device):
