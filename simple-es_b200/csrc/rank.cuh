@@ -150,6 +150,149 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const unsigned lo
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused variant (SES_K2_FUSED): the same stable LSD sort with the launch count cut from
+// 2 + 2*passes to 1 + passes (integer keys: 3 kernels instead of 6; float64 keys: 9 instead of 18).  K2 is latency
+// bound -- every kernel is a few microseconds of work -- so launches are what it costs.
+//   * sort_key(): the key of position p straight from the fitness vector (k_sort_init fused into the first histogram
+//     and the first scatter: the initial (key, index) arrays are never written);
+//   * every scatter pass also builds the NEXT pass's per-tile digit histograms and digit totals, keyed by the tile the
+//     key lands in (warp-aggregated global atomics), so only pass 0 needs a histogram kernel;
+//   * the last scatter writes the centered rank of each offspring from its final position (k_shape_centered fused).
+// Positions, stability argument and the resulting permutation are exactly those of the unfused kernels above.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long sort_key(const double *__restrict__ fitness, int n, int p, int key_bits, double key_scale)
+{
+    const double f = __dadd_rn(fitness[n - 1 - p], 0.0);   // position p holds offspring n-1-p; -0.0 -> +0.0
+    if (key_bits == 0) {
+        const unsigned long long b = (unsigned long long)__double_as_longlong(f);
+        const unsigned long long asc = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+        return ~asc;
+    }
+    const long long v = __double2ll_rn(__dmul_rn(f, key_scale)) + (1ll << key_bits);
+    return ((2ull << key_bits) - 1ull) - (unsigned long long)v;
+}
+
+// pass-0 histogram straight from the fitness vector
+template <int SORT_ITEMS>
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_hist_first(const double *__restrict__ fitness, int n, int key_bits, double key_scale,
+                                                                  int *__restrict__ hist)
+{
+    constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
+    __shared__ int h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const int base = blockIdx.x * SORT_TILE;
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int it = 0; it < SORT_ITEMS; ++it) {
+        const int p = base + it * SORT_THREADS + threadIdx.x;
+        const int d = p < n ? (int)(sort_key(fitness, n, p, key_bits, key_scale) & 255ull) : 256 + lane;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        if (p < n && lane == __ffs(peers) - 1) atomicAdd(&h[d], __popc(peers));
+    }
+    __syncthreads();
+    hist[blockIdx.x * 256 + threadIdx.x] = h[threadIdx.x];
+}
+
+// one stable scatter pass; `first`: keys come from the fitness vector; `last`: no next pass -- write the permutation
+// (vals_out) and, if shaped != nullptr, the centered ranks; otherwise also accumulate hist_next (zeroed by the host) for
+// the digit at shift + 8.  Digit totals are the column sums of the tile histograms (no separate table).
+template <int SORT_ITEMS>
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter_fused(const double *__restrict__ fitness, int key_bits, double key_scale,
+                                                                     const unsigned long long *__restrict__ keys_in,
+                                                                     const int *__restrict__ vals_in, int n, int shift, int first, int last,
+                                                                     const int *__restrict__ hist, int *__restrict__ hist_next,
+                                                                     unsigned long long *__restrict__ keys_out, int *__restrict__ vals_out,
+                                                                     double stdv, double *__restrict__ shaped)
+{
+    constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS, SORT_WSEG = 32 * SORT_ITEMS;
+    __shared__ int digit_base[256];
+    __shared__ int whist[SORT_WARPS][256];
+    __shared__ int scan_tmp[256];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lt = lanemask_lt();
+
+    {   // (a) global base of digit d for this CTA: sum_{d'<d} tot[d'] + sum_{c<cta} hist[c][d], tot[d] = sum_c hist[c][d]
+        int t = 0, below = 0;
+        for (int c = 0; c < (int)gridDim.x; ++c) {
+            const int v = hist[c * 256 + tid];
+            t += v;
+            if (c < (int)blockIdx.x) below += v;
+        }
+        scan_tmp[tid] = t;
+        __syncthreads();
+        for (int off = 1; off < 256; off <<= 1) {
+            int v = tid >= off ? scan_tmp[tid - off] : 0;
+            __syncthreads();
+            scan_tmp[tid] += v;
+            __syncthreads();
+        }
+        digit_base[tid] = scan_tmp[tid] - t + below;
+    }
+    for (int i = tid; i < SORT_WARPS * 256; i += SORT_THREADS) (&whist[0][0])[i] = 0;
+    __syncthreads();
+
+    // (b) load this warp's segment, count digits
+    unsigned long long key[SORT_ITEMS];
+    int val[SORT_ITEMS];
+    const int seg = blockIdx.x * SORT_TILE + w * SORT_WSEG;
+#pragma unroll
+    for (int it = 0; it < SORT_ITEMS; ++it) {
+        const int p = seg + it * 32 + lane;
+        const bool ok = p < n;
+        if (first) {
+            key[it] = ok ? sort_key(fitness, n, p, key_bits, key_scale) : 0ull;
+            val[it] = ok ? n - 1 - p : -1;
+        } else {
+            key[it] = ok ? keys_in[p] : 0ull;
+            val[it] = ok ? vals_in[p] : -1;
+        }
+        const int d = ok ? (int)((key[it] >> shift) & 255ull) : (256 + lane);
+        const unsigned peers = __match_any_sync(FULL, d);
+        if (ok && lane == __ffs(peers) - 1) whist[w][d] += __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    {   // (c) exclusive scan over warps per digit, seeded with the digit's global base
+        int run = digit_base[tid];
+#pragma unroll
+        for (int ww = 0; ww < SORT_WARPS; ++ww) {
+            const int t = whist[ww][tid];
+            whist[ww][tid] = run;
+            run += t;
+        }
+    }
+    __syncthreads();
+    // (d) second walk: stable positions; next pass's histograms, or the final outputs
+#pragma unroll
+    for (int it = 0; it < SORT_ITEMS; ++it) {
+        const bool ok = val[it] >= 0;
+        const int d = ok ? (int)((key[it] >> shift) & 255ull) : (256 + lane);
+        const unsigned peers = __match_any_sync(FULL, d);
+        const int leader = __ffs(peers) - 1;
+        int b = 0;
+        if (ok && lane == leader) { b = whist[w][d]; whist[w][d] = b + __popc(peers); }
+        b = __shfl_sync(FULL, b, leader);
+        const int pos = b + __popc(peers & lt);
+        if (ok) vals_out[pos] = val[it];
+        if (!last) {
+            if (ok) keys_out[pos] = key[it];
+            // histogram of the next digit, per destination tile: one atomic per distinct (tile, digit) in the warp
+            const int dn = (int)((key[it] >> (shift + 8)) & 255ull);
+            const int bin = ok ? (pos / SORT_TILE) * 256 + dn : -1 - lane;
+            const unsigned same = __match_any_sync(FULL, bin);
+            if (ok && lane == __ffs(same) - 1) atomicAdd(&hist_next[bin], __popc(same));
+        } else if (shaped && ok) {
+            // centered rank of the offspring that ends at rank `pos` (k_shape_centered)
+            const double v = __dsub_rn(__ddiv_rn((double)(n - 1 - pos), (double)(n - 1)), 0.5);
+            shaped[val[it]] = __ddiv_rn(v, stdv);
+        }
+        __syncwarp();
+    }
+}
+
 // centered ranks, standardised with the closed-form mean (0) and population std of the table
 // {i/(P-1) - 0.5} (offspring_strategies.py:392-398).
 __global__ void k_shape_centered(const int *__restrict__ order, int n, double stdv, double *__restrict__ shaped)

@@ -61,6 +61,8 @@ struct ses_handle {
     int *vals_scratch = nullptr;
     int *hist = nullptr;
     int *tot = nullptr;            // [8][256]
+    int *hist_fused = nullptr;     // fused K2: [passes][tiles][256] tile histograms, zeroed per call
+    int k2_fused = 0;
     double *part1 = nullptr;
     int nb0 = 0, nb1 = 0, n_tiles = 0;
     // scratch for the host-buffer generation path
@@ -159,6 +161,7 @@ extern "C" int ses_create(const ses_config *cfg, ses_handle **out)
     h->ctas_per_sm = env_int("SES_ROLLOUT_CTAS_PER_SM", 0);
     h->k1_variant = env_int("SES_K1_VARIANT", 4);
     h->spread_slots8 = env_int("SES_SPREAD_SLOTS8", 0);
+    h->k2_fused = env_int("SES_K2_FUSED", 0);
     if (h->k1_variant < 0 || h->k1_variant > 5) h->k1_variant = 4;
 
     const int P = cfg->population;
@@ -171,6 +174,7 @@ extern "C" int ses_create(const ses_config *cfg, ses_handle **out)
     CU(cudaMalloc(&h->vals_scratch, sizeof(int) * P));
     CU(cudaMalloc(&h->hist, sizeof(int) * h->n_tiles * 256));
     CU(cudaMalloc(&h->tot, sizeof(int) * 8 * 256));
+    CU(cudaMalloc(&h->hist_fused, sizeof(int) * 8 * (size_t)h->n_tiles * 256));
     CU(cudaMalloc(&h->part1, sizeof(double) * (size_t)h->nb1 * h->DP));
     *out = h;
     return 0;
@@ -182,7 +186,7 @@ extern "C" int ses_destroy(ses_handle *h)
     cudaSetDevice(h->cfg.device);
     cudaFree(h->work_counter);
     cudaFree(h->keys[0]); cudaFree(h->keys[1]);
-    cudaFree(h->vals_scratch); cudaFree(h->hist); cudaFree(h->tot);
+    cudaFree(h->vals_scratch); cudaFree(h->hist); cudaFree(h->tot); cudaFree(h->hist_fused);
     cudaFree(h->part1);
     for (int r = 0; r < h->peer_world; ++r)
         if (r != h->peer_rank && h->peer_x[r]) cudaIpcCloseMemHandle(h->peer_x[r]);
@@ -422,6 +426,32 @@ extern "C" int ses_rank_desc(ses_handle *h, const double *fitness_dev, int32_t n
     int *vals[2];
     vals[0] = (passes % 2 == 0) ? order_dev : h->vals_scratch;
     vals[1] = (passes % 2 == 0) ? h->vals_scratch : order_dev;
+    if (h->k2_fused) {
+        // 1 + passes launches: pass-0 histogram from the fitness vector, then one scatter per pass that also builds the next
+        // pass's histograms; the last one writes the permutation and the centered ranks (rank.cuh)
+        if (shaped_dev && n < 2) return fail("ses_rank_desc: centered ranks need n >= 2");
+        const double stdv = n >= 2 ? sqrt((double)(n + 1) / (12.0 * (double)(n - 1))) : 1.0;
+        const size_t per_pass = (size_t)tiles * 256;                      // [tiles][256] tile histograms of one pass
+        CU(cudaMemsetAsync(h->hist_fused, 0, sizeof(int) * per_pass * passes, st));
+        if (small) k_sort_hist_first<SORT_ITEMS_SMALL><<<tiles, SORT_THREADS, 0, st>>>(fitness_dev, n, key_bits, key_scale, h->hist_fused);
+        else k_sort_hist_first<SORT_ITEMS_LARGE><<<tiles, SORT_THREADS, 0, st>>>(fitness_dev, n, key_bits, key_scale, h->hist_fused);
+        h->launches += 1;
+        for (int ps = 0; ps < passes; ++ps) {
+            const int a = ps & 1, b = a ^ 1;
+            const int first = ps == 0, last = ps == passes - 1;
+            int *hp = h->hist_fused + per_pass * ps;
+            int *hn = last ? nullptr : h->hist_fused + per_pass * (ps + 1);
+            if (small)
+                k_sort_scatter_fused<SORT_ITEMS_SMALL><<<tiles, SORT_THREADS, 0, st>>>(fitness_dev, key_bits, key_scale, h->keys[a], vals[a], n, 8 * ps, first, last,
+                                                                                        hp, hn, h->keys[b], vals[b], stdv, shaped_dev);
+            else
+                k_sort_scatter_fused<SORT_ITEMS_LARGE><<<tiles, SORT_THREADS, 0, st>>>(fitness_dev, key_bits, key_scale, h->keys[a], vals[a], n, 8 * ps, first, last,
+                                                                                        hp, hn, h->keys[b], vals[b], stdv, shaped_dev);
+            h->launches += 1;
+        }
+        CU(cudaGetLastError());
+        return 0;
+    }
     CU(cudaMemsetAsync(h->tot, 0, sizeof(int) * 8 * 256, st));
     k_sort_init<<<(n + 255) / 256, 256, 0, st>>>(fitness_dev, n, key_bits, key_scale, h->keys[0], vals[0]);
     h->launches += 1;

@@ -208,8 +208,11 @@ def test_rollout_full_size_properties():
 
 
 # ------------------------------------------------------------------------------------- K2
+@pytest.mark.parametrize("fused", [0, 1])
 @pytest.mark.parametrize("n", [2, 97, 4097, 65536, 1 << 20])
-def test_rank_desc_bit_exact(n):
+def test_rank_desc_bit_exact(n, fused, monkeypatch):
+    """Both K2 builds: separate init / histogram / scatter / shape kernels, and SES_K2_FUSED=1 (1 + passes launches)."""
+    monkeypatch.setenv("SES_K2_FUSED", str(fused))
     eng = _engine(population=max(n, 2), group=max(n, 2))
     rng = np.random.default_rng(n)
     for kind in ("float", "ties", "cartpole"):
@@ -223,8 +226,10 @@ def test_rank_desc_bit_exact(n):
         got = eng.rank_desc(_cuda(r), full_key=True).cpu().numpy()
         assert np.array_equal(got, want), kind
         if kind == "cartpole":                                     # integer-key fast path
-            got = eng.rank_desc(_cuda(r)).cpu().numpy()
-            assert np.array_equal(got, want)
+            got, shaped = eng.rank_desc(_cuda(r), shaped=True)
+            assert np.array_equal(got.cpu().numpy(), want)
+            cr = ((n - 1 - np.arange(n)) / (n - 1) - 0.5) / np.sqrt((n + 1) / (12.0 * (n - 1)))
+            np.testing.assert_allclose(shaped.cpu().numpy()[want], cr, rtol=1e-15, atol=0)
 
 
 def test_rank_and_shaping_match_reference(twin, golden):

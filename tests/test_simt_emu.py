@@ -222,8 +222,12 @@ def test_emu_engine_rejects_bad_configs(emu):
 
 
 # ------------------------------------------------------------------------------------- K2
+@pytest.mark.parametrize("fused", [0, 1])
 @pytest.mark.parametrize("n", [2, 97, 4097, 65536 + 3, (1 << 18) + 5])
-def test_emu_rank_desc_bit_exact(emu, n):
+def test_emu_rank_desc_bit_exact(emu, n, fused, monkeypatch):
+    """Both K2 builds: separate init / histogram / scatter / shape kernels (2 + 2*passes launches) and the fused one
+    (SES_K2_FUSED=1: 1 + passes launches) give the same permutation -- np.flip(np.argsort(kind="stable"))."""
+    monkeypatch.setenv("SES_K2_FUSED", str(fused))
     eng = emu(population=n, group=n)
     rng = np.random.default_rng(n)
     kinds = ("float", "ties", "cartpole") if n <= 4097 else ("cartpole",)
@@ -239,12 +243,18 @@ def test_emu_rank_desc_bit_exact(emu, n):
         if n <= 4097:
             assert np.array_equal(eng.rank_desc(r, full_key=True), want), kind
         if kind == "cartpole":                                     # integer-key fast path (2 radix passes)
-            assert np.array_equal(eng.rank_desc(r), want)
+            l0 = eng.launches
+            order, shaped = eng.rank_desc(r, shaped=True)
+            assert np.array_equal(order, want) and eng.launches - l0 == (3 if fused else 6)
+            cr = ((n - 1 - np.arange(n)) / (n - 1) - 0.5) / np.sqrt((n + 1) / (12.0 * (n - 1)))
+            np.testing.assert_allclose(shaped[want], cr, rtol=1e-15, atol=0)
             neg = emu(env_name="MountainCar-v0", obs_dim=2, act_dim=3, population=n, group=n, max_step=None)
             assert np.array_equal(neg.rank_desc(-r), np.flip(np.argsort(-r, kind="stable")).astype(np.int32))
 
 
-def test_emu_rank_and_shaping_match_reference(emu, twin, golden):
+@pytest.mark.parametrize("fused", [0, 1])
+def test_emu_rank_and_shaping_match_reference(emu, twin, golden, fused, monkeypatch):
+    monkeypatch.setenv("SES_K2_FUSED", str(fused))
     g = golden("strategy_openai_es")
     P = int(g["P"])
     eng = emu(population=P, group=P)
@@ -333,8 +343,10 @@ def test_emu_elite_mean_and_genetic_carry_over(emu, twin, golden):
         assert np.array_equal(eng.materialize(gen, 0.0, None, order[:k], w_override=g["pop_%d" % gen]), g["elites_after_%d" % gen])
 
 
-def test_emu_generation_openai_host_matches_twin_composition(emu, twin):
+@pytest.mark.parametrize("fused", [0, 1])
+def test_emu_generation_openai_host_matches_twin_composition(emu, twin, fused, monkeypatch):
     """ses_generation_openai_host (bench.py's e2e entry point): K1 -> K2 (integer keys) -> K3 composed inside the library."""
+    monkeypatch.setenv("SES_K2_FUSED", str(fused))
     P, E, lr, sigma, seed = 300, 5, 0.1, 0.5, 17
     eng = emu(population=P, group=P, n_head=1, eval_ep_num=E, seed=seed)
     mu = np.zeros(D, np.float32); m = np.zeros(D, np.float32); v = np.zeros(D, np.float32)
@@ -349,7 +361,8 @@ def test_emu_generation_openai_host_matches_twin_composition(emu, twin):
         tmu, tm, tv = twin.adam(tmu, tm, tv, g, eng.adam_a(lr, gen + 1))
         assert np.array_equal(mu, tmu) and np.array_equal(m, tm) and np.array_equal(v, tv)
         sigma *= 0.999
-    assert eng.launches == 3 * 9                                    # K1 + sort init + 2 x (hist, scatter) + shape + 2 x K3
+    # K1 + K2 (sort init + 2 x (hist, scatter) + shape, or fused: first hist + 2 scatters) + 2 x K3
+    assert eng.launches == 3 * (6 if fused else 9)
 
 
 # ------------------------------------------------------------------------------------- sharding, antithetic
