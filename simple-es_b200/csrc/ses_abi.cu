@@ -161,7 +161,7 @@ extern "C" int ses_create(const ses_config *cfg, ses_handle **out)
     h->ctas_per_sm = env_int("SES_ROLLOUT_CTAS_PER_SM", 0);
     h->k1_variant = env_int("SES_K1_VARIANT", 4);
     h->spread_slots8 = env_int("SES_SPREAD_SLOTS8", 0);
-    h->k2_fused = env_int("SES_K2_FUSED", 0);
+    h->k2_fused = env_int("SES_K2_FUSED", 1);     // 1 + passes launches (default); 0: the separate kernels
     if (h->k1_variant < 0 || h->k1_variant > 5) h->k1_variant = 4;
 
     const int P = cfg->population;
