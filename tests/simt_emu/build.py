@@ -118,6 +118,8 @@ def sources():
 
 
 def build(force=False):
+    if os.environ.get("SES_SIMT_EMU_LIB"):             # e.g. a sanitizer build of the same sources (tools/emu_ubsan.sh)
+        return os.environ["SES_SIMT_EMU_LIB"]
     deps = sources() + [os.path.join(HERE, "include", "simt_emu.h"), os.path.abspath(__file__)]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
         return LIB
