@@ -576,3 +576,13 @@ def test_emu_peer_exchange_ranks_equal_single_rank(emu, world, shard_mode, P):
         for gen in range(gens):
             for a, b in zip(out[r][gen], ref[0][gen]):
                 assert np.array_equal(a, b), (r, gen)
+
+
+def test_emu_fuzz_all_envs_against_twin():
+    """A slice of tools/emu_fuzz.py (random env / policy / layout / slice / E / truncation / antithetic / grid limits):
+    emulated kernels == twin, bit for bit."""
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "emu_fuzz.py"), "20000", "40"], capture_output=True, text=True,
+                         timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "cases 40 bad 0" in out.stdout, out.stdout[-2000:]
