@@ -155,6 +155,17 @@ int ses_generation_openai_host(ses_handle *h, uint32_t generation, float sigma, 
                                int64_t adam_t, float *mu_host, float *m_host, float *v_host,
                                double *fitness_host, int64_t *total_steps_host, void *stream);
 
+/* The same for the two elite strategies (one whole ESLoop.run iteration each, loop.py:61-84, with host buffers; single-slice
+ * handle; synchronises `stream`):
+ *   simple_evolution (offspring_strategies.py:213-258): mu_host [D] in -> K1, K2, elite mean of the elite_num best -> mu_host out.
+ *     The caller applies `sigma *= sigma_decay` afterwards (:251), as for ses_update_elite_mean.
+ *   simple_genetic (:94-124): elites_host [n_parents][D] in -> K1, K2, the n_parents best offspring's weights -> elites_host out.
+ * fitness_host [P] f64 and total_steps_host (env steps simulated) as in ses_generation_openai_host. */
+int ses_generation_evolution_host(ses_handle *h, uint32_t generation, float sigma, int32_t elite_num, float *mu_host,
+                                  double *fitness_host, int64_t *total_steps_host, void *stream);
+int ses_generation_genetic_host(ses_handle *h, uint32_t generation, float sigma, float *elites_host,
+                                double *fitness_host, int64_t *total_steps_host, void *stream);
+
 /* Test hook: the numerical-contract functions on the device, elementwise.
  * kind: 0 tanh32, 1 sigmoid32, 2 ln32, 3 sin2pi32, 4 cos2pi32 (in/out f32);
  *       5 sin64, 6 cos64 (in/out f64); 7 tanh32 with the division fast path written out (what K1 runs). */

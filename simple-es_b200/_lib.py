@@ -37,6 +37,8 @@ SYMBOLS = {
     "ses_materialize": (C.c_int, [_vp, _u32, _f32, _vp, _vp, _vp, _i32, _vp, _vp]),
     "ses_update_elite_mean": (C.c_int, [_vp, _u32, _f32, _vp, _vp, _vp, _i32, _vp, _vp]),
     "ses_generation_openai_host": (C.c_int, [_vp, _u32, _f32, _f64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ses_generation_evolution_host": (C.c_int, [_vp, _u32, _f32, _i32, _vp, _vp, _vp, _vp]),
+    "ses_generation_genetic_host": (C.c_int, [_vp, _u32, _f32, _vp, _vp, _vp, _vp]),
     "ses_peer_export": (C.c_int, [_vp, _vp]),
     "ses_peer_attach": (C.c_int, [_vp, _vp, _i32, _i32]),
     "ses_peer_fitness_ptr": (C.c_int, [_vp, _i32, C.POINTER(_vp)]),

@@ -71,6 +71,12 @@ struct ses_handle {
     long long *h_steps = nullptr;
     int *h_order = nullptr;
     unsigned long long *h_total = nullptr;
+    // scratch of the elite strategies' host-buffer generations (ses_generation_evolution_host / _genetic_host)
+    float *e_parents = nullptr, *e_out = nullptr;      // [n_parents][D] each
+    double *e_fitness = nullptr;
+    long long *e_steps = nullptr;
+    int *e_order = nullptr;
+    unsigned long long *e_total = nullptr;
     // peer (NVLink P2P) fitness exchange: [2][P] doubles (double buffered by generation parity) + flags
     double *xbuf = nullptr;
     double *peer_x[MAX_PEERS] = {nullptr};
@@ -193,6 +199,7 @@ extern "C" int ses_destroy(ses_handle *h)
     cudaFree(h->xbuf); cudaFree(h->peer_error);
     cudaFree(h->h_parents); cudaFree(h->h_m); cudaFree(h->h_v);
     cudaFree(h->h_fitness); cudaFree(h->h_shaped); cudaFree(h->h_steps); cudaFree(h->h_order); cudaFree(h->h_total);
+    cudaFree(h->e_parents); cudaFree(h->e_out); cudaFree(h->e_fitness); cudaFree(h->e_steps); cudaFree(h->e_order); cudaFree(h->e_total);
     delete h;
     return 0;
 }
@@ -637,6 +644,80 @@ extern "C" int ses_generation_openai_host(ses_handle *h, uint32_t generation, fl
     CU(cudaMemcpyAsync(total_steps_host, h->h_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// whole simple_evolution / simple_genetic generation with host buffers
+// ------------------------------------------------------------------------------------------------
+// shared part: H2D of the parent table, K1, K2 (permutation only); leaves the order in h->e_order
+static int elite_generation_prologue(ses_handle *h, const char *who, uint32_t generation, float sigma, const float *parents_host,
+                                     void *stream)
+{
+    const ses_config &c = h->cfg;
+    const int P = c.population;
+    if (h->shard.n_local != P) return fail("%s: needs a single-slice handle", who);
+    CU(cudaSetDevice(c.device));
+    cudaStream_t st = S(stream);
+    const size_t pb = sizeof(float) * (size_t)c.n_parents * h->D;
+    if (!h->e_parents) {
+        CU(cudaMalloc(&h->e_parents, pb));
+        CU(cudaMalloc(&h->e_out, pb));
+        CU(cudaMalloc(&h->e_fitness, sizeof(double) * P));
+        CU(cudaMalloc(&h->e_steps, sizeof(long long) * P));
+        CU(cudaMalloc(&h->e_order, sizeof(int) * P));
+        CU(cudaMalloc(&h->e_total, sizeof(unsigned long long)));
+    }
+    CU(cudaMemcpyAsync(h->e_parents, parents_host, pb, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(h->e_total, 0, sizeof(unsigned long long), st));
+    unsigned long long *saved_counter = h->step_counter;
+    h->step_counter = h->e_total;
+    const int rc_roll = ses_rollout(h, generation, sigma, h->e_parents, nullptr, nullptr, h->e_fitness, reinterpret_cast<int64_t *>(h->e_steps),
+                                    nullptr, nullptr, 0, stream);
+    h->step_counter = saved_counter;
+    if (rc_roll) return -1;
+    int key_bits = 0;
+    double key_scale = 1.0;
+    if (c.env != SES_ENV_SIMPLE_SPREAD) {     // fitness = +-steps / E with integer |steps| <= E * max_step
+        const long long vmax = (long long)c.eval_ep_num * h->eff_max_step;
+        while ((1ll << key_bits) <= vmax) ++key_bits;
+        key_scale = (double)c.eval_ep_num;
+    }
+    return ses_rank_desc(h, h->e_fitness, P, key_bits, key_scale, h->e_order, nullptr, stream);
+}
+
+static int elite_generation_epilogue(ses_handle *h, float *parents_host, size_t bytes, double *fitness_host, int64_t *total_steps_host,
+                                     void *stream)
+{
+    cudaStream_t st = S(stream);
+    CU(cudaMemcpyAsync(fitness_host, h->e_fitness, sizeof(double) * h->cfg.population, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(parents_host, h->e_out, bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(total_steps_host, h->e_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int ses_generation_evolution_host(ses_handle *h, uint32_t generation, float sigma, int32_t elite_num, float *mu_host,
+                                             double *fitness_host, int64_t *total_steps_host, void *stream)
+{
+    if (!h) return fail("ses_generation_evolution_host: null handle");
+    if (!mu_host || !fitness_host || !total_steps_host) return fail("ses_generation_evolution_host: null buffer");
+    if (h->cfg.n_parents != 1) return fail("ses_generation_evolution_host: simple_evolution has one parent (mu)");
+    if (elite_num < 1 || elite_num > h->cfg.population) return fail("ses_generation_evolution_host: elite_num=%d out of range", elite_num);
+    if (elite_generation_prologue(h, "ses_generation_evolution_host", generation, sigma, mu_host, stream)) return -1;
+    if (ses_update_elite_mean(h, generation, sigma, h->e_parents, nullptr, h->e_order, elite_num, h->e_out, stream)) return -1;
+    return elite_generation_epilogue(h, mu_host, sizeof(float) * h->D, fitness_host, total_steps_host, stream);
+}
+
+extern "C" int ses_generation_genetic_host(ses_handle *h, uint32_t generation, float sigma, float *elites_host,
+                                           double *fitness_host, int64_t *total_steps_host, void *stream)
+{
+    if (!h) return fail("ses_generation_genetic_host: null handle");
+    if (!elites_host || !fitness_host || !total_steps_host) return fail("ses_generation_genetic_host: null buffer");
+    const int k = h->cfg.n_parents;
+    if (k > h->cfg.population) return fail("ses_generation_genetic_host: more elites than offspring");
+    if (elite_generation_prologue(h, "ses_generation_genetic_host", generation, sigma, elites_host, stream)) return -1;
+    if (ses_materialize(h, generation, sigma, h->e_parents, nullptr, h->e_order, k, h->e_out, stream)) return -1;
+    return elite_generation_epilogue(h, elites_host, sizeof(float) * (size_t)k * h->D, fitness_host, total_steps_host, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -288,6 +288,25 @@ class RolloutEngine:
             C.c_void_p(total.ctypes.data), self._stream()))
         return int(total[0])
 
+    def generation_evolution_host(self, generation, sigma, elite_num, mu, fitness):
+        """Whole simple_evolution generation on HOST numpy buffers: mu [D] float32 in / out (the elite mean), fitness [P]
+        float64 out; returns the env steps simulated.  Synchronous; the caller decays sigma afterwards."""
+        return self._elite_host(self.lib.ses_generation_evolution_host, (int(generation), float(sigma), int(elite_num)), mu, self.D, fitness)
+
+    def generation_genetic_host(self, generation, sigma, elites, fitness):
+        """Whole simple_genetic generation on HOST numpy buffers: elites [n_parents][D] float32 in / out (the weights of the
+        n_parents best offspring), fitness [P] float64 out; returns the env steps simulated.  Synchronous."""
+        return self._elite_host(self.lib.ses_generation_genetic_host, (int(generation), float(sigma)), elites,
+                                int(self.cfg.n_parents) * self.D, fitness)
+
+    def _elite_host(self, fn, head, parents, numel, fitness):
+        total = np.zeros(1, dtype=np.int64)
+        assert isinstance(parents, np.ndarray) and parents.dtype == np.float32 and parents.flags.c_contiguous and parents.size == numel
+        assert isinstance(fitness, np.ndarray) and fitness.dtype == np.float64 and fitness.flags.c_contiguous and fitness.size == self.P
+        _lib.check(fn(self._h, *head, C.c_void_p(parents.ctypes.data), C.c_void_p(fitness.ctypes.data),
+                      C.c_void_p(total.ctypes.data), self._stream()))
+        return int(total[0])
+
     # ------------------------------------------------------------------------------ test hooks
     def test_math(self, kind, x):
         kinds = {"tanh": 0, "sigmoid": 1, "ln": 2, "sin2pi": 3, "cos2pi": 4, "sin64": 5, "cos64": 6, "tanh_fast": 7,

@@ -178,6 +178,17 @@ class EmuEngine:
     def peer_check(self):
         self._check(self.lib.ses_peer_check(self._h))
 
+    def generation_evolution_host(self, generation, sigma, elite_num, mu, fitness):
+        total = np.zeros(1, dtype=np.int64)
+        self._check(self.lib.ses_generation_evolution_host(self._h, int(generation), float(sigma), int(elite_num), _p(mu), _p(fitness),
+                                                           _p(total), None))
+        return int(total[0])
+
+    def generation_genetic_host(self, generation, sigma, elites, fitness):
+        total = np.zeros(1, dtype=np.int64)
+        self._check(self.lib.ses_generation_genetic_host(self._h, int(generation), float(sigma), _p(elites), _p(fitness), _p(total), None))
+        return int(total[0])
+
     def test_math(self, kind, x):
         kinds = {"tanh": 0, "sigmoid": 1, "ln": 2, "sin2pi": 3, "cos2pi": 4, "sin64": 5, "cos64": 6, "tanh_fast": 7,
                  "sin64_full": 8, "cos64_full": 9}

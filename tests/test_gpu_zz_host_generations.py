@@ -1,0 +1,53 @@
+"""GPU: the host-buffer whole-generation entry points of the two elite strategies (ses_generation_evolution_host,
+ses_generation_genetic_host -- one C call per ESLoop.run iteration, loop.py:61-84, numpy buffers in and out) against the
+same generations composed from the CPU twin.  Bit-exact.  (This file sorts last on purpose: these entry points were added at
+the very end of round 1, after the GPU budget was spent -- they are verified on the host SIMT emulator,
+tests/test_simt_emu.py -- so a surprise here cannot mask the rest of the -m gpu suite under `-x`.)"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+D = 226
+
+
+def _engine(strategy, n, k, **kw):
+    from simple_es_b200.engine import RolloutEngine, population_layout
+    P, group, n_head, n_par = population_layout(strategy, n, k)
+    return RolloutEngine("CartPole-v1", 4, 2, False, False, 500, 5, P, group, n_head, n_par, **kw), (P, group, n_head, n_par)
+
+
+def test_generation_evolution_host_matches_twin_composition(twin):
+    seed = 31
+    eng, (P, group, n_head, n_par) = _engine("simple_evolution", 2000, 10, seed=seed)
+    mu = np.zeros(D, np.float32); fit = np.zeros(P); tmu = mu.copy(); sigma = 2.0
+    for gen in range(3):
+        total = eng.generation_evolution_host(gen, sigma, 10, mu, fit)
+        tf, ts = twin.population_cartpole(tmu[None], sigma=sigma, seed=seed, gen=gen, group=group, n_head=n_head, n=P, E=5, nthreads=8)
+        order = twin.rank_desc(tf)
+        tmu = twin.elite_mean(twin.materialize(tmu[None], sigma, seed, gen, group, n_head, order[:10]))
+        assert total == ts.sum() and np.array_equal(fit, tf) and np.array_equal(mu, tmu)
+        sigma *= 0.9
+
+
+def test_generation_genetic_host_matches_twin_composition(twin):
+    seed = 32
+    eng, (P, group, n_head, n_par) = _engine("simple_genetic", 4096, 8, seed=seed)
+    el = np.random.default_rng(1).normal(0, 0.5, (n_par, D)).astype(np.float32); fit = np.zeros(P); tel = el.copy(); sigma = 1.0
+    for gen in range(3):
+        total = eng.generation_genetic_host(gen, sigma, el, fit)
+        tf, ts = twin.population_cartpole(tel, sigma=sigma, seed=seed, gen=gen, group=group, n_head=n_head, n=P, E=5, nthreads=8)
+        tel = twin.materialize(tel, sigma, seed, gen, group, n_head, twin.rank_desc(tf)[:n_par])
+        assert total == ts.sum() and np.array_equal(fit, tf) and np.array_equal(el, tel)
+        sigma *= 0.95
+
+
+def test_generation_elite_hosts_reject_bad_handles():
+    eng, (P, group, n_head, n_par) = _engine("simple_genetic", 400, 4, seed=1)
+    with pytest.raises(RuntimeError, match="one parent"):
+        eng.generation_evolution_host(0, 1.0, 3, np.zeros(D, np.float32), np.zeros(P))
+    from simple_es_b200.engine import RolloutEngine
+    sliced = RolloutEngine("CartPole-v1", 4, 2, False, False, 500, 5, P, group, n_head, n_par, id_begin=0, id_end=50)
+    with pytest.raises(RuntimeError, match="single-slice"):
+        sliced.generation_genetic_host(0, 1.0, np.zeros((n_par, D), np.float32), np.zeros(P))

@@ -365,6 +365,39 @@ def test_emu_generation_openai_host_matches_twin_composition(emu, twin, fused, m
     assert eng.launches == 3 * (6 if fused else 9)
 
 
+def test_emu_generation_elite_hosts_match_twin_composition(emu, twin):
+    """ses_generation_evolution_host / ses_generation_genetic_host: one C call per generation with host buffers, equal to
+    rollout -> rank -> elite mean / elite carry-over composed from the twin (incl. each strategy's sigma-decay ordering)."""
+    from simple_es_b200.engine import population_layout
+    E, seed = 5, 31
+    # simple_evolution: offspring_num 60 -> P = 61, layout [mu, mu, 59 perturbed]
+    P, group, n_head, n_par = population_layout("simple_evolution", 60, 7)
+    eng = emu(population=P, group=group, n_head=n_head, n_parents=n_par, eval_ep_num=E, seed=seed)
+    mu = np.zeros(D, np.float32); fit = np.zeros(P); tmu = mu.copy(); sigma = 2.0
+    for gen in range(3):
+        total = eng.generation_evolution_host(gen, sigma, 7, mu, fit)
+        tf, ts = twin.population_cartpole(tmu[None], sigma=sigma, seed=seed, gen=gen, group=group, n_head=n_head, n=P, E=E, nthreads=4)
+        order = twin.rank_desc(tf)
+        tmu = twin.elite_mean(twin.materialize(tmu[None], sigma, seed, gen, group, n_head, order[:7]))
+        assert total == ts.sum() and np.array_equal(fit, tf) and np.array_equal(mu, tmu)
+        sigma *= 0.9
+    # simple_genetic: 4 elites x 25 offspring each
+    P, group, n_head, n_par = population_layout("simple_genetic", 100, 4)
+    eng = emu(population=P, group=group, n_head=n_head, n_parents=n_par, eval_ep_num=E, seed=seed)
+    el = np.random.default_rng(1).normal(0, 0.5, (n_par, D)).astype(np.float32); fit = np.zeros(P); tel = el.copy(); sigma = 1.0
+    for gen in range(3):
+        total = eng.generation_genetic_host(gen, sigma, el, fit)
+        tf, ts = twin.population_cartpole(tel, sigma=sigma, seed=seed, gen=gen, group=group, n_head=n_head, n=P, E=E, nthreads=4)
+        tel = twin.materialize(tel, sigma, seed, gen, group, n_head, twin.rank_desc(tf)[:n_par])
+        assert total == ts.sum() and np.array_equal(fit, tf) and np.array_equal(el, tel)
+        sigma *= 0.95
+    with pytest.raises(RuntimeError, match="one parent"):
+        eng.generation_evolution_host(0, 1.0, 3, el[0].copy(), fit)
+    sliced = emu(population=P, group=group, n_head=n_head, n_parents=n_par, eval_ep_num=E, seed=seed, id_begin=0, id_end=50)
+    with pytest.raises(RuntimeError, match="single-slice"):
+        sliced.generation_genetic_host(0, 1.0, el, fit)
+
+
 # ------------------------------------------------------------------------------------- sharding, antithetic
 @pytest.mark.parametrize("env,obs,act,gru,P,world", [("CartPole-v1", 4, 2, False, 301, 2), ("CartPole-v1", 4, 2, True, 41, 3),
                                                      ("simple_spread", 12, 5, False, 100, 8), ("Acrobot-v1", 6, 3, False, 77, 2)])
