@@ -173,6 +173,9 @@ int ses_test_math(int32_t kind, const void *in_dev, void *out_dev, int64_t n, vo
 int ses_test_normals(ses_handle *h, uint32_t generation, int32_t id, float *out_dev /* [D] */, void *stream);
 /* counts mismatches between K1's 3-instruction x/1.1 and IEEE division over n pseudo-random doubles */
 int ses_test_div_total_mass(uint64_t n, uint64_t *mismatches_host);
+/* counts mismatches between the branch-free double division of K1 variant 6 (ddiv_fast) and IEEE division over n pseudo-random
+ * operand pairs of the CartPole step's ranges (|a| in [1, 64), b in [0.5, 1)) */
+int ses_test_ddiv_fast(uint64_t n, uint64_t *mismatches_host);
 /* counts float32 inputs x in [lo, hi] (and -x) for which K1's fast-path tanh differs from the contract's tanh32 */
 int ses_test_tanh_fast_exhaustive(float lo, float hi, uint64_t *mismatches_host);
 /* the same for the packed (FFMA2) tanh of K1's hidden-unit pairs, both halves; newton = 0 drops the Newton step on

@@ -168,7 +168,7 @@ extern "C" int ses_create(const ses_config *cfg, ses_handle **out)
     h->k1_variant = env_int("SES_K1_VARIANT", 4);
     h->spread_slots8 = env_int("SES_SPREAD_SLOTS8", 0);
     h->k2_fused = env_int("SES_K2_FUSED", 1);     // 1 + passes launches (default); 0: the separate kernels
-    if (h->k1_variant < 0 || h->k1_variant > 5) h->k1_variant = 4;
+    if (h->k1_variant < 0 || h->k1_variant > 6) h->k1_variant = 4;
 
     const int P = cfg->population;
     h->n_tiles = (P + sort_tile(SORT_ITEMS_SMALL) - 1) / sort_tile(SORT_ITEMS_SMALL);
@@ -300,6 +300,7 @@ extern "C" int ses_rollout(ses_handle *h, uint32_t generation, float sigma, cons
             if (h->k1_variant == 3) return launch_slots<CartpoleMlpEnvT<3>, 8>(h, rp, need_warps, tr, st);
             if (h->k1_variant == 4) return launch_slots<CartpoleMlpEnvT<4>, 8>(h, rp, need_warps, tr, st);
             if (h->k1_variant == 5) return launch_slots<CartpoleMlpEnvT<5>, 8>(h, rp, need_warps, tr, st);
+            if (h->k1_variant == 6) return launch_slots<CartpoleMlpEnvT<6>, 8>(h, rp, need_warps, tr, st);
             return launch_slots<CartpoleMlpEnvT<1>, 8>(h, rp, need_warps, tr, st);
         }
         if (c.eval_ep_num >= 2) return launch_slots<CartpoleMlpEnvT<4>, 16>(h, rp, need_warps, tr, st);
@@ -936,6 +937,40 @@ __global__ void k_div11_check(unsigned long long n, unsigned long long *mismatch
         bad += __double_as_longlong(div_total_mass(x)) != __double_as_longlong(__ddiv_rn(x, 1.1));
     }
     if (bad) atomicAdd(mismatches, bad);
+}
+
+// ddiv_fast(a, b) vs __ddiv_rn(a, b) on n pseudo-random operand pairs of cartpole_step's ranges: |a| in [1, 64) (random sign
+// and mantissa), b in [0.5, 1)
+__global__ void k_ddiv_fast_check(unsigned long long n, unsigned long long *mismatches)
+{
+    unsigned long long bad = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint4 r = philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), 0x52u, 0u, 0xD1Du, 9u);
+        const uint4 t = philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), 0x53u, 0u, 0xD1Du, 9u);
+        const unsigned long long ma = (((unsigned long long)r.x << 32) | r.y) & 0x000FFFFFFFFFFFFFull;
+        const unsigned long long mb = (((unsigned long long)r.z << 32) | r.w) & 0x000FFFFFFFFFFFFFull;
+        const unsigned long long ea = 1023ull + (t.x % 6u);                      // 2^0 .. 2^5
+        const unsigned long long sa = (unsigned long long)(t.y & 1u) << 63;
+        const double a = __longlong_as_double((long long)(sa | (ea << 52) | ma));
+        const double b = __longlong_as_double((long long)((1022ull << 52) | mb));  // [0.5, 1)
+        bad += __double_as_longlong(ddiv_fast(a, b)) != __double_as_longlong(__ddiv_rn(a, b));
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+extern "C" int ses_test_ddiv_fast(uint64_t n, uint64_t *mismatches_host)
+{
+    if (!mismatches_host) return fail("ses_test_ddiv_fast: null argument");
+    unsigned long long *d = nullptr;
+    CU(cudaMalloc(&d, sizeof(unsigned long long)));
+    CU(cudaMemset(d, 0, sizeof(unsigned long long)));
+    k_ddiv_fast_check<<<148 * 16, 256>>>((unsigned long long)n, d);
+    CU(cudaGetLastError());
+    unsigned long long r = 0;
+    CU(cudaMemcpy(&r, d, sizeof(r), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    *mismatches_host = r;
+    return 0;
 }
 
 extern "C" int ses_test_div_total_mass(uint64_t n, uint64_t *mismatches_host)

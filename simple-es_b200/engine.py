@@ -333,6 +333,12 @@ class RolloutEngine:
         _lib.check(self.lib.ses_test_div_total_mass(int(n), C.byref(bad)))
         return int(bad.value)
 
+    def test_ddiv_fast(self, n=1 << 30):
+        """Mismatches between K1 variant 6's branch-free double division and IEEE division on n random in-range operand pairs."""
+        bad = C.c_uint64(0)
+        _lib.check(self.lib.ses_test_ddiv_fast(int(n), C.byref(bad)))
+        return int(bad.value)
+
     def test_normals(self, generation, idx):
         out = torch.empty(self.D, dtype=torch.float32, device=self.device)
         _lib.check(self.lib.ses_test_normals(self._h, int(generation), int(idx), _ptr(out), self._stream()))

@@ -5,7 +5,7 @@ never loads this library.
 The sources are used as they are; three textual rewrites make them C++:
   * kernel<<<grid, block[, smem[, stream]]>>>(args);   ->  simt::launch(grid, block, smem, [&]() { kernel(args); });
   * extern __shared__ ... unsigned char name[];        ->  unsigned char *name = simt::dyn_smem();
-  * the five inline-PTX statements (rcp.approx, min.xorsign.abs, %lanemask_lt, st.release / ld.acquire) -> C++ equivalents
+  * the inline-PTX statements (rcp.approx f32 / f64, min.xorsign.abs, %lanemask_lt, st.release / ld.acquire) -> C++ equivalents
 """
 import os
 import re
@@ -90,6 +90,7 @@ def rewrite_launches(src):
 
 
 ASM = [
+    (re.compile(r'asm\("rcp\.approx\.ftz\.f64 %0, %1;"\s*:\s*"=d"\((.+?)\)\s*:\s*"d"\((.+?)\)\);'), r"\1 = simt::rcp_approx_f64(\2);"),
     (re.compile(r'asm\("rcp\.approx\.ftz\.f32 %0, %1;"\s*:\s*"=f"\((.+?)\)\s*:\s*"f"\((.+?)\)\);'), r"\1 = simt::rcp_approx(\2);"),
     (re.compile(r'asm\("min\.xorsign\.abs\.f32 %0, %1, %2;"\s*:\s*"=f"\((.+?)\)\s*:\s*"f"\((.+?)\),\s*"f"\((.+?)\)\);'),
      r"\1 = simt::min_xorsign_abs(\2, \3);"),

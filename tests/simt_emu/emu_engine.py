@@ -202,6 +202,11 @@ class EmuEngine:
         self._check(self.lib.ses_test_normals(self._h, int(generation), int(idx), _p(out), None))
         return out
 
+    def test_ddiv_fast(self, n):
+        bad = C.c_uint64(0)
+        self._check(self.lib.ses_test_ddiv_fast(int(n), C.byref(bad)))
+        return int(bad.value)
+
     def test_tanh_x2_exhaustive(self, newton, lo, hi):
         bad = C.c_uint64(0)
         self._check(self.lib.ses_test_tanh_x2_exhaustive(int(bool(newton)), float(lo), float(hi), C.byref(bad)))

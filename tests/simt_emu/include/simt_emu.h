@@ -250,6 +250,11 @@ void launch(dim3 grid, dim3 block, size_t smem, F &&body)
 }
 
 inline float rcp_approx(float x) { return 1.0f / x; }      // MUFU.RCP stand-in (the device value is within 1 ulp of this)
+inline double rcp_approx_f64(double x)
+{
+    // MUFU.RCP64H stand-in: a reciprocal good to ~20 bits whose low word is zero
+    return from_bits<double>(to_bits(1.0 / x) & 0xFFFFFFFF00000000ull);
+}
 inline float min_xorsign_abs(float a, float b)
 {
     // min(|a|, |b|) with sign(a) ^ sign(b)

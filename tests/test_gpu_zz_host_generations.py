@@ -51,3 +51,22 @@ def test_generation_elite_hosts_reject_bad_handles():
     sliced = RolloutEngine("CartPole-v1", 4, 2, False, False, 500, 5, P, group, n_head, n_par, id_begin=0, id_end=50)
     with pytest.raises(RuntimeError, match="single-slice"):
         sliced.generation_genetic_host(0, 1.0, np.zeros((n_par, D), np.float32), np.zeros(P))
+
+
+def test_k1_variant6_speculative_physics_bit_exact(twin, monkeypatch):
+    """K1 variant 6 (opt-in, SES_K1_VARIANT=6): the CartPole step's action-dependent tail evaluated for both actions with a
+    branch-free double division, so that the physics overlaps the policy arithmetic.  Same bits as the twin; the division
+    equals IEEE division on 2^30 random in-range operand pairs."""
+    from simple_es_b200.engine import RolloutEngine
+    monkeypatch.setenv("SES_K1_VARIANT", "6")
+    eng = RolloutEngine("CartPole-v1", 4, 2, False, False, 500, 5, 3000, 3000, 1, 1, seed=11)
+    assert eng.test_ddiv_fast(1 << 30) == 0
+    mu = np.zeros((1, D), np.float32)
+    fit, steps = eng.rollout(2, 2.0, torch.from_numpy(mu).cuda())
+    tf, ts = twin.population_cartpole(mu, sigma=2.0, seed=11, gen=2, group=3000, n_head=1, n=3000, E=5, nthreads=8)
+    assert np.array_equal(steps.cpu().numpy(), ts) and np.array_equal(fit.cpu().numpy(), tf)
+    w1 = mu[0, :128].reshape(32, 4); w2 = mu[0, 160:224].reshape(2, 32)
+    w1[0] = [0.0, 0.5, 10.0, 3.0]; w2[1, 0] = 5.0; w2[0, 0] = -5.0       # a policy that balances: 500-step episodes
+    fit, steps = eng.rollout(0, 0.05, torch.from_numpy(mu).cuda())
+    tf, ts = twin.population_cartpole(mu, sigma=0.05, seed=11, gen=0, group=3000, n_head=1, n=3000, E=5, nthreads=8)
+    assert np.array_equal(steps.cpu().numpy(), ts) and (ts == 2500).mean() > 0.5

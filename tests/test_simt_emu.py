@@ -48,6 +48,8 @@ def test_emu_math_contract_bit_exact(emu, twin):
     # here the reciprocal seed is the correctly rounded 1/q instead of MUFU.RCP, so this checks the algebra, not the seed)
     assert eng.test_tanh_x2_exhaustive(False, 0.25, 0.2500305) == 0
     assert eng.test_tanh_x2_exhaustive(True, 3.0, 3.0002441) == 0
+    # K1 variant 6's branch-free double division (Newton / Markstein from a 20-bit reciprocal seed) == IEEE division
+    assert eng.test_ddiv_fast(3_000_000) == 0
     u = ((rng.integers(0, 2 ** 24, 200_000) + 0.5) * 2.0 ** -24).astype(np.float32)
     assert np.array_equal(eng.test_math("ln", u), twin.lnf(u))
     v = (rng.integers(0, 2 ** 24, 200_000) * 2.0 ** -24).astype(np.float32)
@@ -93,7 +95,7 @@ def test_emu_rollout_philox_bit_exact(emu, twin, init_mode, pomdp, E):
     assert ts.max() > 3 * ts.min()                          # ragged episode lengths: the warp scheduler re-arms lanes
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6])
 def test_emu_rollout_k1_variants_bit_exact(emu, twin, variant, monkeypatch):
     """Every K1 code path (scalar / packed FFMA2, permuted slot table, weights of the lane's slot in registers) is the
     same function: ragged and 500-step episodes, Philox and verification (w_override) inputs."""
