@@ -168,7 +168,7 @@ extern "C" int ses_create(const ses_config *cfg, ses_handle **out)
     h->k1_variant = env_int("SES_K1_VARIANT", 4);
     h->spread_slots8 = env_int("SES_SPREAD_SLOTS8", 0);
     h->k2_fused = env_int("SES_K2_FUSED", 1);     // 1 + passes launches (default); 0: the separate kernels
-    if (h->k1_variant < 0 || h->k1_variant > 6) h->k1_variant = 4;
+    if (h->k1_variant < 0 || h->k1_variant > 7) h->k1_variant = 4;
 
     const int P = cfg->population;
     h->n_tiles = (P + sort_tile(SORT_ITEMS_SMALL) - 1) / sort_tile(SORT_ITEMS_SMALL);
@@ -301,6 +301,7 @@ extern "C" int ses_rollout(ses_handle *h, uint32_t generation, float sigma, cons
             if (h->k1_variant == 4) return launch_slots<CartpoleMlpEnvT<4>, 8>(h, rp, need_warps, tr, st);
             if (h->k1_variant == 5) return launch_slots<CartpoleMlpEnvT<5>, 8>(h, rp, need_warps, tr, st);
             if (h->k1_variant == 6) return launch_slots<CartpoleMlpEnvT<6>, 8>(h, rp, need_warps, tr, st);
+            if (h->k1_variant == 7) return launch_slots<CartpoleMlpEnvT<7>, 8>(h, rp, need_warps, tr, st);
             return launch_slots<CartpoleMlpEnvT<1>, 8>(h, rp, need_warps, tr, st);
         }
         if (c.eval_ep_num >= 2) return launch_slots<CartpoleMlpEnvT<4>, 16>(h, rp, need_warps, tr, st);

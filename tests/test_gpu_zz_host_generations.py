@@ -53,12 +53,13 @@ def test_generation_elite_hosts_reject_bad_handles():
         sliced.generation_genetic_host(0, 1.0, np.zeros((n_par, D), np.float32), np.zeros(P))
 
 
-def test_k1_variant6_speculative_physics_bit_exact(twin, monkeypatch):
-    """K1 variant 6 (opt-in, SES_K1_VARIANT=6): the CartPole step's action-dependent tail evaluated for both actions with a
-    branch-free double division, so that the physics overlaps the policy arithmetic.  Same bits as the twin; the division
-    equals IEEE division on 2^30 random in-range operand pairs."""
+@pytest.mark.parametrize("variant", [6, 7])
+def test_k1_variants_6_7_branch_free_division_bit_exact(twin, monkeypatch, variant):
+    """K1 variants 6 / 7 (opt-in, SES_K1_VARIANT): the CartPole step with a branch-free double division (7), and with the
+    action-dependent tail evaluated for both actions as well (6).  Same bits as the twin; the division equals IEEE division
+    on 2^30 random in-range operand pairs."""
     from simple_es_b200.engine import RolloutEngine
-    monkeypatch.setenv("SES_K1_VARIANT", "6")
+    monkeypatch.setenv("SES_K1_VARIANT", str(variant))
     eng = RolloutEngine("CartPole-v1", 4, 2, False, False, 500, 5, 3000, 3000, 1, 1, seed=11)
     assert eng.test_ddiv_fast(1 << 30) == 0
     mu = np.zeros((1, D), np.float32)

@@ -95,7 +95,7 @@ def test_emu_rollout_philox_bit_exact(emu, twin, init_mode, pomdp, E):
     assert ts.max() > 3 * ts.min()                          # ragged episode lengths: the warp scheduler re-arms lanes
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7])
 def test_emu_rollout_k1_variants_bit_exact(emu, twin, variant, monkeypatch):
     """Every K1 code path (scalar / packed FFMA2, permuted slot table, weights of the lane's slot in registers) is the
     same function: ragged and 500-step episodes, Philox and verification (w_override) inputs."""
