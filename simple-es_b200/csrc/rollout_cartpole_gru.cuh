@@ -18,6 +18,7 @@
 // (offspring) are resident per SM -- shared-memory capacity is what bounds this variant.
 #pragma once
 #include <cstdio>
+#include <cstdlib>
 #include "rollout_cartpole_mlp.cuh"
 
 namespace ses {
@@ -59,7 +60,16 @@ __device__ __forceinline__ void gru_store_gate_quad(GruWarpSmem<EC> &sm, int hh,
 // index into `small` (floats) of flat parameter d outside the two big matrices
 __device__ __forceinline__ int gru_small_index(int d) { return d < GO_WIH ? d : d - 2 * G3 * HID; }
 
-template <int EC, int WARPS, bool TRACE>
+// SPEC (opt-in, SES_GRU_VARIANT=1; written at the end of round 1, bit-exact on the emulator, NOT yet timed on a B200): the
+// float64 physics leaves the serial tail of the step.  In the default kernel the <= 5 lanes that own an episode run, after
+// the cell, 32 dependent FFMA2 (logits) and then the whole cart-pole chain while 27 lanes idle.  Here lanes [EC, 2 EC) mirror
+// the episode states of lanes [0, EC), and at the START of the step lanes [0, EC) advance their copy assuming action 0 and
+// lanes [EC, 2 EC) assuming action 1 -- the same warp instructions the owners would issue anyway, on lanes that were idle --
+// with the branch-free division (cartpole_step_fastdiv).  The physics therefore depends on nothing the policy computes and
+// sits in the same basic block as the (fully unrolled) GEMV, so the scheduler can fill the FFMA2 stream's issue gaps with
+// it; after the argmax each lane takes the two velocities from the candidate of the chosen action (4 SHFL) -- position,
+// angle and `done` do not depend on the action at all.
+template <int EC, int WARPS, bool TRACE, bool SPEC = false>
 __global__ void __launch_bounds__(WARPS * 32, 2) k_rollout_cartpole_gru(const RolloutParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -119,13 +129,15 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_rollout_cartpole_gru(const Ro
             const int ne = min(EC, p.E - e0);
             double x = 0.0, xd = 0.0, th = 0.0, thd = 0.0;             // lane e: state of episode e0 + e
             int nstep = 0;
-            bool alive = lane < ne;
+            // SPEC: lanes [EC, 2 EC) hold a mirror of the states of lanes [0, EC) (the action-1 candidates)
+            const int ei = SPEC ? (lane >= EC ? lane - EC : lane) : lane;
+            bool alive = SPEC ? (lane < 2 * EC && ei < ne) : (lane < ne);
             if (alive) {
                 if (p.init_states) {
-                    const double *s0 = p.init_states + 4 * (e0 + lane);
+                    const double *s0 = p.init_states + 4 * (e0 + ei);
                     x = s0[0]; xd = s0[1]; th = s0[2]; thd = s0[3];
                 } else {
-                    cartpole_init(p.seed, p.init_mode, p.gen, (uint32_t)id, (uint32_t)(e0 + lane), x, xd, th, thd);
+                    cartpole_init(p.seed, p.init_mode, p.gen, (uint32_t)id, (uint32_t)(e0 + ei), x, xd, th, thd);
                 }
             }
             float h[EC];
@@ -156,11 +168,16 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_rollout_cartpole_gru(const Ro
                     if constexpr (EC & 1) sm.xh[EC - 1][lane].x = tanh32_fast_t<false>(a[EC - 1]);
                 }
                 __syncwarp();
+                // SPEC: this lane's candidate next state (action 0 on lanes < EC, action 1 on the mirror lanes); independent of
+                // everything below up to the argmax
+                [[maybe_unused]] double cx = x, cxd = xd, cth = th, cthd = thd;
+                [[maybe_unused]] bool cdone = false;
+                if constexpr (SPEC) cdone = cartpole_step_fastdiv(cx, cxd, cth, cthd, lane >= EC ? 1 : 0);
                 // gate pre-activations of lane j, as pairs: { r_i, z_i } (W_ih x), { r_h, z_h } (W_hh h), { n_i, n_h }
                 float2 grz_i[EC], grz_h[EC], gn[EC];
 #pragma unroll
                 for (int e = 0; e < EC; ++e) { grz_i[e] = make_float2(bir, biz); grz_h[e] = make_float2(bhr, bhz); gn[e] = make_float2(bin, bhn); }
-#pragma unroll 2
+#pragma unroll(SPEC ? HID / 2 : 2)
                 for (int kp = 0; kp < HID / 2; ++kp) {
                     const float4 a = sm.wrz_i[kp][lane], c = sm.wrz_h[kp][lane], n = sm.wn[kp][lane];
 #pragma unroll
@@ -209,7 +226,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_rollout_cartpole_gru(const Ro
                 // lane e: logits in the contract's sequential order (as the pair { z0, z1 }), action, physics
                 bool done = false;
                 int action = 0;
-                if (alive) {
+                if (alive && (!SPEC || lane < EC)) {
                     float2 z = make_float2(b20, b21);
                     const float4 *orow = reinterpret_cast<const float4 *>(sm.obuf[lane]);
                     const float4 *wp = reinterpret_cast<const float4 *>(sm.w2p);
@@ -223,18 +240,41 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_rollout_cartpole_gru(const Ro
                     }
                     const float z0 = z.x, z1 = z.y;
                     action = argmax_softmax2(z0, z1);
-                    done = cartpole_step(x, xd, th, thd, action);
-                    ++nstep;
-                    if (nstep >= p.max_step) done = true;
-                    if constexpr (TRACE) {
-                        const int local = local_idx;
-                        if (e0 + lane == 0 && local < p.n_trace && nstep <= 200) {
-                            double *t = p.trace + ((size_t)local * 200 + (nstep - 1)) * 4;
-                            t[0] = x; t[1] = xd; t[2] = th; t[3] = thd;
-                            p.trace_actions[(size_t)local * 200 + (nstep - 1)] = action;
+                    if constexpr (!SPEC) {
+                        done = cartpole_step(x, xd, th, thd, action);
+                        ++nstep;
+                        if (nstep >= p.max_step) done = true;
+                        if constexpr (TRACE) {
+                            const int local = local_idx;
+                            if (e0 + lane == 0 && local < p.n_trace && nstep <= 200) {
+                                double *t = p.trace + ((size_t)local * 200 + (nstep - 1)) * 4;
+                                t[0] = x; t[1] = xd; t[2] = th; t[3] = thd;
+                                p.trace_actions[(size_t)local * 200 + (nstep - 1)] = action;
+                            }
                         }
+                        if (done) alive = false;
                     }
-                    if (done) alive = false;
+                }
+                if constexpr (SPEC) {
+                    // owner and mirror of episode ei both continue from the candidate of the chosen action
+                    const int act = __shfl_sync(FULL, action, ei);
+                    const int src = ei + (act ? EC : 0);
+                    const double sxd = __shfl_sync(FULL, cxd, src), sthd = __shfl_sync(FULL, cthd, src);
+                    if (alive) {
+                        x = cx; th = cth; xd = sxd; thd = sthd;            // x, theta, done: the same in both candidates
+                        done = cdone;
+                        ++nstep;
+                        if (nstep >= p.max_step) done = true;
+                        if constexpr (TRACE) {
+                            const int local = local_idx;
+                            if (lane < EC && e0 + lane == 0 && local < p.n_trace && nstep <= 200) {
+                                double *t = p.trace + ((size_t)local * 200 + (nstep - 1)) * 4;
+                                t[0] = x; t[1] = xd; t[2] = th; t[3] = thd;
+                                p.trace_actions[(size_t)local * 200 + (nstep - 1)] = act;
+                            }
+                        }
+                        if (done) alive = false;
+                    }
                 }
                 alive_mask = __ballot_sync(FULL, alive);
             }
@@ -259,7 +299,10 @@ static int launch_rollout_cartpole_gru_ec(int num_sms, int ctas_per_sm, const Ro
 {
     constexpr int WARPS = 4;
     const size_t smem = WARPS * sizeof(GruWarpSmem<EC>);
-    auto kern = trace ? k_rollout_cartpole_gru<EC, WARPS, true> : k_rollout_cartpole_gru<EC, WARPS, false>;
+    const char *ev = getenv("SES_GRU_VARIANT");                       // read per launch: tests switch it inside one process
+    const int spec = ev && *ev ? atoi(ev) : 0;
+    auto kern = spec == 1 ? (trace ? k_rollout_cartpole_gru<EC, WARPS, true, true> : k_rollout_cartpole_gru<EC, WARPS, false, true>)
+                          : (trace ? k_rollout_cartpole_gru<EC, WARPS, true, false> : k_rollout_cartpole_gru<EC, WARPS, false, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = 0;
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem);

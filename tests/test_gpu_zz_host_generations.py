@@ -71,3 +71,18 @@ def test_k1_variants_6_7_branch_free_division_bit_exact(twin, monkeypatch, varia
     fit, steps = eng.rollout(0, 0.05, torch.from_numpy(mu).cuda())
     tf, ts = twin.population_cartpole(mu, sigma=0.05, seed=11, gen=0, group=3000, n_head=1, n=3000, E=5, nthreads=8)
     assert np.array_equal(steps.cpu().numpy(), ts) and (ts == 2500).mean() > 0.5
+
+
+def test_gru_variant1_speculative_lanes_bit_exact(twin, monkeypatch):
+    """SES_GRU_VARIANT=1 (opt-in): the GRU rollout with the cart-pole step evaluated for both actions on otherwise idle
+    lanes at the start of the step.  Same bits as the twin (E = 5 and a chunked E = 7, POMDP on / off)."""
+    from simple_es_b200.engine import RolloutEngine
+    monkeypatch.setenv("SES_GRU_VARIANT", "1")
+    rng = np.random.default_rng(7)
+    mu = rng.normal(0, 0.3, (1, 6562)).astype(np.float32)
+    for pomdp, E in [(True, 5), (False, 7)]:
+        P = 600
+        eng = RolloutEngine("CartPole-v1", 4, 2, True, pomdp, 500, E, P, P, 2, 1, seed=13)
+        fit, steps = eng.rollout(4, 0.7, torch.from_numpy(mu).cuda())
+        tf, ts = twin.population_cartpole(mu, gru=True, pomdp=pomdp, sigma=0.7, seed=13, gen=4, group=P, n_head=2, n=P, E=E, nthreads=8)
+        assert np.array_equal(steps.cpu().numpy(), ts) and np.array_equal(fit.cpu().numpy(), tf)

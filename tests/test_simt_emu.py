@@ -457,8 +457,11 @@ def test_emu_antithetic_sampling_bit_exact_and_mirrored(emu, twin, strategy, n, 
 
 
 # ------------------------------------------------------------------------------------- K1: GRU policy (warp per offspring)
+@pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("pomdp,E,sigma", [(True, 5, 0.7), (False, 3, 0.3), (True, 7, 0.7), (False, 1, 0.5)])
-def test_emu_rollout_gru_philox_bit_exact(emu, twin, pomdp, E, sigma):
+def test_emu_rollout_gru_philox_bit_exact(emu, twin, pomdp, E, sigma, variant, monkeypatch):
+    """variant 1 (SES_GRU_VARIANT=1): the physics evaluated for both actions on otherwise idle lanes at the start of the step."""
+    monkeypatch.setenv("SES_GRU_VARIANT", str(variant))
     P = 40
     eng = emu(population=P, group=P, n_head=2, eval_ep_num=E, gru=True, pomdp=pomdp, seed=13)
     mu = np.random.default_rng(7).normal(0, 0.3, (1, DG)).astype(np.float32)
@@ -468,7 +471,9 @@ def test_emu_rollout_gru_philox_bit_exact(emu, twin, pomdp, E, sigma):
     assert ts[0] == ts[1]                                   # simple_evolution layout: offspring 0 and 1 are both mu
 
 
-def test_emu_rollout_gru_verification_mode_matches_reference(emu, golden):
+@pytest.mark.parametrize("variant", [0, 1])
+def test_emu_rollout_gru_verification_mode_matches_reference(emu, golden, variant, monkeypatch):
+    monkeypatch.setenv("SES_GRU_VARIANT", str(variant))
     g = golden("rollout_cartpole_gru_pomdp")
     W, init, E = g["W"], g["init"], int(g["E"])
     tid = [int(i) for i in g["trace_ids"]]
