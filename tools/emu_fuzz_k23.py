@@ -3,7 +3,7 @@
 kernels; float64 keys incl. +-inf, denormals, -0.0, constant vectors; integer keys) against np.flip(np.argsort(kind="stable")),
 and ses_update_openai / ses_materialize / ses_update_elite_mean with random layouts against the C twin.  No GPU needed.
 
-    python tools/emu_fuzz_k23.py <first_case> <n_cases>      (600 cases, 0 mismatches at the end of round 1)
+    python tools/emu_fuzz_k23.py <first_case> <n_cases>      (4 600 cases, 0 mismatches at the end of round 1)
 """
 import os
 import sys
