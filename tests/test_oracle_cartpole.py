@@ -18,6 +18,30 @@ def test_one_step_analytic(twin):
     assert st2[1] == -st[1] and st2[3] == -st[3]
 
 
+def test_accelerations_equal_the_lagrangian_equations_of_motion(twin):
+    """An independent pin of the physics (gym is not installable here): the restated closed forms for
+    thetaacc / xacc must be THE solution of the cart-pole equations of motion derived from the Lagrangian of the system gym
+    describes (cart 1.0 kg, uniform pole 0.1 kg of half-length 0.5 m pivoting on the cart, theta = 0 upright, no friction;
+    Barto, Sutton & Anderson 1983):
+        (M + m) x'' + m l cos(th) th''            = F + m l th'^2 sin(th)
+        m l cos(th) x'' + (I + m l^2) th''        = m g l sin(th),      I = m (2 l)^2 / 12
+    solved here as a 2x2 linear system per state; the twin's accelerations are read off one Euler step."""
+    M, m, l, g, tau = 1.0, 0.1, 0.5, 9.8, 0.02
+    inertia = m * (2 * l) ** 2 / 12.0
+    rng = np.random.default_rng(11)
+    for _ in range(2000):
+        x, xd, th, thd = rng.uniform(-1, 1, 4) * np.array([2.4, 3.0, 0.2095, 3.5])
+        a = int(rng.integers(0, 2))
+        F = 10.0 if a == 1 else -10.0
+        A = np.array([[M + m, m * l * np.cos(th)], [m * l * np.cos(th), inertia + m * l * l]])
+        b = np.array([F + m * l * thd * thd * np.sin(th), m * g * l * np.sin(th)])
+        xacc, thacc = np.linalg.solve(A, b)
+        st, _ = twin.cartpole_step([x, xd, th, thd], a)
+        assert abs((st[1] - xd) / tau - xacc) <= 1e-9 * max(1.0, abs(xacc))
+        assert abs((st[3] - thd) / tau - thacc) <= 1e-9 * max(1.0, abs(thacc))
+        assert st[0] == x + tau * xd and st[2] == th + tau * thd          # explicit Euler with the OLD velocities
+
+
 def test_termination_thresholds(twin):
     assert twin.cartpole_step([2.39, 1.0, 0.0, 0.0], 1)[1] is True      # x crosses 2.4
     assert twin.cartpole_step([-2.39, -1.0, 0.0, 0.0], 0)[1] is True
