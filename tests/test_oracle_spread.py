@@ -35,3 +35,28 @@ def test_spread_init_and_zero_policy(twin):
     f, n, tr, ac = twin.rollout_mpe(np.zeros(D, np.float32), N=2, E=1, trace_steps=25)
     assert np.all(ac == 0) and n == 25
     assert np.all(tr[:, 4:] == 0) and np.all(tr[:, :4] == tr[0, :4])
+
+
+def test_spread_contact_forces_conserve_momentum_and_repel(twin):
+    """Independent physical pins of the restated MPE world (pettingzoo is not installable here): contact forces are equal and
+    opposite, so with every agent idle (all-zero policy -> action 0) the total momentum stays zero although overlapping
+    agents are pushed apart; the penetration force is repulsive; and the episode return equals the reward formula of
+    SURVEY.md Appendix A.2 re-evaluated in numpy from the traced positions."""
+    N, D = 3, 773
+    init = np.array([0.10, 0.00, 0.22, 0.05, -0.60, -0.55,          # agents 0 and 1 start overlapping (dist 0.13 < 0.3), agent 2 far
+                     0.5, 0.5, -0.5, 0.5, 0.0, -0.8], dtype=np.float64)[None]  # landmarks
+    f, n, tr, ac = twin.rollout_mpe(np.zeros(D, np.float32), N=N, E=1, init=init, trace_steps=25)
+    assert n == 25 and np.all(ac == 0)
+    pos, vel = tr[:, :2 * N].reshape(25, N, 2), tr[:, 2 * N:].reshape(25, N, 2)
+    assert np.abs(vel.sum(axis=1)).max() < 1e-12                      # sum_i m v_i == 0 (masses are 1)
+    d01 = np.linalg.norm(pos[:, 0] - pos[:, 1], axis=1)
+    assert d01[0] > 0.13 and np.all(np.diff(d01) > 0)                 # the overlapping pair separates monotonically
+    assert np.abs(vel[0, 2]).max() < 1e-3                             # the distant agent feels (almost) nothing
+    lm = init[0, 2 * N:].reshape(N, 2)
+    total = 0.0
+    for t in range(25):
+        glob = -sum(min(np.linalg.norm(pos[t, a] - lm[l]) for a in range(N)) for l in range(N))
+        for i in range(N):
+            local = -sum(1.0 for a in range(N) if np.linalg.norm(pos[t, a] - pos[t, i]) < 0.3)    # counts the agent itself
+            total += 0.5 * glob + 0.5 * local
+    assert abs(f - total) <= 1e-12 * abs(total)
