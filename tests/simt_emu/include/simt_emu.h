@@ -57,6 +57,22 @@ static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) {
 static inline int2 make_int2(int x, int y) { return int2{x, y}; }
 static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
 
+// ------------------------------------------------------------------------------------------------ operation counters
+// Optional (-DSIMT_EMU_COUNT, tools/emu_opcount.py): every arithmetic intrinsic a lane executes is counted, which gives the
+// exact per-lane operation mix of a kernel's SOURCE (the algorithmic work behind the roofline arithmetic of DESIGN.md)
+// without a profiler.  Plain C operators are not counted (the sources use the _rn intrinsics and fma()/fmaf() throughout).
+namespace simt {
+enum { C_F32_FMA, C_F32_MUL, C_F32_ADD, C_F32X2_FMA, C_F32X2_MUL, C_F32X2_ADD, C_F32_DIV, C_F32_SQRT, C_F32_RCP, C_F32_MINMAX,
+       C_F64_FMA, C_F64_MUL, C_F64_ADD, C_F64_DIV, C_F64_SQRT, C_F64_RCP, C_SHFL, C_VOTE, C_MATCH, C_SYNCWARP, C_SYNCTHREADS, C_ATOMIC,
+       C_COUNT };
+#ifdef SIMT_EMU_COUNT
+inline unsigned long long g_counts[C_COUNT] = {0};          // global on purpose: summed over every emulated thread of the process
+#define SIMT_CNT(k) (++simt::g_counts[simt::k])
+#else
+#define SIMT_CNT(k) ((void)0)
+#endif
+}  // namespace simt
+
 // ------------------------------------------------------------------------------------------------ fibers
 namespace simt {
 
@@ -249,15 +265,17 @@ void launch(dim3 grid, dim3 block, size_t smem, F &&body)
     free(dyn);
 }
 
-inline float rcp_approx(float x) { return 1.0f / x; }      // MUFU.RCP stand-in (the device value is within 1 ulp of this)
+inline float rcp_approx(float x) { SIMT_CNT(C_F32_RCP); return 1.0f / x; }      // MUFU.RCP stand-in (the device value is within 1 ulp of this)
 inline double rcp_approx_f64(double x)
 {
     // MUFU.RCP64H stand-in: a reciprocal good to ~20 bits whose low word is zero
+    SIMT_CNT(C_F64_RCP);
     return from_bits<double>(to_bits(1.0 / x) & 0xFFFFFFFF00000000ull);
 }
 inline float min_xorsign_abs(float a, float b)
 {
     // min(|a|, |b|) with sign(a) ^ sign(b)
+    SIMT_CNT(C_F32_MINMAX);
     const float m = fminf(fabsf(a), fabsf(b));
     return (signbit(a) != signbit(b)) ? -m : m;
 }
@@ -273,17 +291,19 @@ inline unsigned lanemask_lt() { return (1u << g_cur->lane) - 1u; }
 // ------------------------------------------------------------------------------------------------ barriers, collectives
 inline void __syncthreads()
 {
+    SIMT_CNT(C_SYNCTHREADS);
     simt::Fiber *f = simt::g_cur;
     simt::g_cta_waiting += 1;
     f->state = simt::WAIT_CTA;
     simt::yield();
 }
-inline void __syncwarp(unsigned = 0xffffffffu) { simt::warp_collective(simt::K_SYNCWARP, 0); }
+inline void __syncwarp(unsigned = 0xffffffffu) { SIMT_CNT(C_SYNCWARP); simt::warp_collective(simt::K_SYNCWARP, 0); }
 inline void __threadfence_system() {}
 inline void __threadfence() {}
 
 inline unsigned __ballot_sync(unsigned mask, int pred)
 {
+    SIMT_CNT(C_VOTE);
     const int par = simt::warp_collective(simt::K_BALLOT, pred ? 1u : 0u);
     const simt::Warp &w = *simt::g_cur->warp;
     unsigned r = 0;
@@ -294,6 +314,7 @@ inline unsigned __ballot_sync(unsigned mask, int pred)
 template <class T>
 inline T __shfl_sync(unsigned, T v, int src, int width = 32)
 {
+    SIMT_CNT(C_SHFL);
     const int par = simt::warp_collective(simt::K_SHFL, simt::to_bits(v));
     const simt::Warp &w = *simt::g_cur->warp;
     const int lane = simt::g_cur->lane;
@@ -304,6 +325,7 @@ inline T __shfl_sync(unsigned, T v, int src, int width = 32)
 template <class T>
 inline T __shfl_xor_sync(unsigned, T v, int lanemask, int width = 32)
 {
+    SIMT_CNT(C_SHFL);
     const int par = simt::warp_collective(simt::K_SHFL, simt::to_bits(v));
     const simt::Warp &w = *simt::g_cur->warp;
     const int lane = simt::g_cur->lane;
@@ -314,6 +336,7 @@ inline T __shfl_xor_sync(unsigned, T v, int lanemask, int width = 32)
 template <class T>
 inline unsigned __match_any_sync(unsigned mask, T v)
 {
+    SIMT_CNT(C_MATCH);
     const uint64_t mine = simt::to_bits(v);
     const int par = simt::warp_collective(simt::K_MATCH, mine);
     const simt::Warp &w = *simt::g_cur->warp;
@@ -324,7 +347,7 @@ inline unsigned __match_any_sync(unsigned mask, T v)
 }
 
 template <class T, class U>
-inline T atomicAdd(T *p, U v) { const T o = *p; *p = (T)(o + (T)v); return o; }
+inline T atomicAdd(T *p, U v) { SIMT_CNT(C_ATOMIC); const T o = *p; *p = (T)(o + (T)v); return o; }
 template <class T, class U>
 inline T atomicExch(T *p, U v) { const T o = *p; *p = (T)v; return o; }
 template <class T, class U>
@@ -374,21 +397,21 @@ inline int __float_as_int(float f) { return (int)simt::to_bits(f); }
 inline float __int_as_float(int b) { return simt::from_bits<float>((uint64_t)(unsigned)b); }
 inline double __longlong_as_double(long long b) { return simt::from_bits<double>((uint64_t)b); }
 inline long long __double_as_longlong(double d) { return (long long)simt::to_bits(d); }
-inline float __fadd_rn(float a, float b) { return a + b; }
-inline float __fsub_rn(float a, float b) { return a - b; }
-inline float __fmul_rn(float a, float b) { return a * b; }
-inline float __fdiv_rn(float a, float b) { return a / b; }
-inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
-inline float __fsqrt_rn(float a) { return sqrtf(a); }
-inline double __dadd_rn(double a, double b) { return a + b; }
-inline double __dsub_rn(double a, double b) { return a - b; }
-inline double __dmul_rn(double a, double b) { return a * b; }
-inline double __ddiv_rn(double a, double b) { return a / b; }
-inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
-inline double __dsqrt_rn(double a) { return sqrt(a); }
-inline float2 __fadd2_rn(float2 a, float2 b) { return float2{a.x + b.x, a.y + b.y}; }
-inline float2 __fmul2_rn(float2 a, float2 b) { return float2{a.x * b.x, a.y * b.y}; }
-inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return float2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }
+inline float __fadd_rn(float a, float b) { SIMT_CNT(C_F32_ADD); return a + b; }
+inline float __fsub_rn(float a, float b) { SIMT_CNT(C_F32_ADD); return a - b; }
+inline float __fmul_rn(float a, float b) { SIMT_CNT(C_F32_MUL); return a * b; }
+inline float __fdiv_rn(float a, float b) { SIMT_CNT(C_F32_DIV); return a / b; }
+inline float __fmaf_rn(float a, float b, float c) { SIMT_CNT(C_F32_FMA); return __builtin_fmaf(a, b, c); }
+inline float __fsqrt_rn(float a) { SIMT_CNT(C_F32_SQRT); return sqrtf(a); }
+inline double __dadd_rn(double a, double b) { SIMT_CNT(C_F64_ADD); return a + b; }
+inline double __dsub_rn(double a, double b) { SIMT_CNT(C_F64_ADD); return a - b; }
+inline double __dmul_rn(double a, double b) { SIMT_CNT(C_F64_MUL); return a * b; }
+inline double __ddiv_rn(double a, double b) { SIMT_CNT(C_F64_DIV); return a / b; }
+inline double __fma_rn(double a, double b, double c) { SIMT_CNT(C_F64_FMA); return __builtin_fma(a, b, c); }
+inline double __dsqrt_rn(double a) { SIMT_CNT(C_F64_SQRT); return sqrt(a); }
+inline float2 __fadd2_rn(float2 a, float2 b) { SIMT_CNT(C_F32X2_ADD); return float2{a.x + b.x, a.y + b.y}; }
+inline float2 __fmul2_rn(float2 a, float2 b) { SIMT_CNT(C_F32X2_MUL); return float2{a.x * b.x, a.y * b.y}; }
+inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { SIMT_CNT(C_F32X2_FMA); return float2{__builtin_fmaf(a.x, b.x, c.x), __builtin_fmaf(a.y, b.y, c.y)}; }
 inline long long __double2ll_rn(double a) { return llrint(a); }       // default rounding mode: to nearest even
 inline int __double2int_rn(double a) { return (int)lrint(a); }
 inline int __double2int_rz(double a) { return (int)a; }
@@ -452,3 +475,19 @@ inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSucces
 inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) { e->t = (double)clock64() * 1e-6; return cudaSuccess; }
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)(b->t - a->t); return cudaSuccess; }
+
+#ifdef SIMT_EMU_COUNT
+// fma() / fmaf() / fmaxf() / fminf() are called by name in the kernel sources: route them through counting wrappers
+inline float simt_cnt_fmaf(float a, float b, float c) { SIMT_CNT(C_F32_FMA); return __builtin_fmaf(a, b, c); }
+inline double simt_cnt_fma(double a, double b, double c) { SIMT_CNT(C_F64_FMA); return __builtin_fma(a, b, c); }
+inline float simt_cnt_fmaxf(float a, float b) { SIMT_CNT(C_F32_MINMAX); return __builtin_fmaxf(a, b); }
+inline float simt_cnt_fminf(float a, float b) { SIMT_CNT(C_F32_MINMAX); return __builtin_fminf(a, b); }
+#define fmaf simt_cnt_fmaf
+#define fma simt_cnt_fma
+#define fmaxf simt_cnt_fmaxf
+#define fminf simt_cnt_fminf
+extern "C" inline __attribute__((used, visibility("default"))) void simt_emu_counters(unsigned long long *out, int reset)
+{
+    for (int i = 0; i < simt::C_COUNT; ++i) { out[i] = simt::g_counts[i]; if (reset) simt::g_counts[i] = 0; }
+}
+#endif
