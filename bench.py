@@ -35,6 +35,8 @@ D = 226
 FLOP_PER_STEP = 418          # 192 FMA + 34 bias adds per env step (CartPole MLP)
 FMA_LANE_OPS_PER_STEP = 640  # executed on the FP32 FMA pipe per env step: fc1 128 + fc2 64 + 32 tanh x 14
 K1_DRAM_BYTES_PER_LAUNCH = 33280   # ncu, profiles/r01_k1_v4_conv.txt (reads; no DRAM writes: results stay in L2)
+K1_PROFILE = "profiles/r01_k1_v4_conv.txt"
+K1_SYMBOL = "ses::k_rollout_slots<ses::CartpoleMlpEnvT<7>, 8, 4, false>"   # the kernel ses_rollout launches for this workload
 STRATEGY = dict(name="openai_es", init_sigma=0.2, sigma_decay=0.9999, learning_rate=0.1)
 
 
@@ -209,54 +211,110 @@ def workload_config(args, world):
     return {"workload": "CartPole-v1 MLP(4-32-2, D=226) openai_es pop=%d eval_ep_num=%d max_step=500 "
                         "(BASELINE configs[2]; conf/cartpole_openai.yaml)" % (args.pop, E_DEFAULT),
             "population": args.pop, "eval_ep_num": E_DEFAULT, "strategy": STRATEGY,
+            "regime": REGIME_TEXT[args.regime],
             "parallelism": "pop-shard x%d (%s)" % (world, args.shard if world > 1 else "single"), "fitness_exchange": (args.exchange if world > 1 else "local"),
             "init_states": "shared [E] table (reference mp.Pool semantics)",
             "l2": "flushed between timed generations (256 MiB write); the hot path itself reads 904 B of parameters per generation"}
 
 
+REGIME_TEXT = {
+    "converged": "converged (SURVEY 8d): K real consecutive ES generations continuing the committed generation-30 state of this very "
+                 "run (tests/golden/bench_state_gen30.npz: mu, Adam m/v, t, sigma), nearly every episode 500 steps -- the regime the "
+                 "reference arm and cpu_baseline are timed in",
+    "from_scratch": "from scratch: real consecutive ES generations W..W+K-1 of a run started at mu = 0 (a converging mixture of "
+                    "episode lengths)",
+    "gen0": "generation 0 (SURVEY 8d): mu = 0, sigma = sigma0, ragged episode lengths of ~10-20 steps with a few 500-step stragglers; "
+            "every timed step is a generation-0 population with fresh noise",
+}
+
+# BASELINE.json configs other than the headline one, each as (key, YAML, overrides, steps the config is timed for)
+EXTRA_CONFIGS = [
+    ("c1_cartpole_simple_evolution_as_shipped", "conf/cartpole.yaml", {}, "BASELINE configs[0]: conf/cartpole.yaml as shipped (P = 97)"),
+    ("c2_cartpole_pomdp_gru_pop4096", "conf/cartpole_pomdp_gru.yaml", {}, "BASELINE configs[1]: CartPole POMDP + GRU, simple_evolution, P = 4097"),
+    ("c2_converged_gru_pop4096", "conf/cartpole_pomdp_gru.yaml", {"env.pomdp": False, "strategy.init_sigma": 0.02, "init": "gru_balancing"},
+     "configs[1]'s kernel in the converged regime: the same GRU policy / population started from a hand-built balancing parent on the fully "
+     "observed pole (every episode 500 steps); the POMDP mask only zeroes two observations, the arithmetic per step is identical"),
+    ("c4_simple_spread_n3_pop16384", "conf/simplespread.yaml", {"network.num_state": 18, "engine.n_agents": 3},
+     "BASELINE configs[3]: simple_spread, 3 agents, shared MLP, openai_es, P = 16384 (env steps = world steps)"),
+    ("c4_simple_spread_n2_pop16384", "conf/simplespread.yaml", {}, "the reference's own N = 2 form of configs[3] (pettingzoo_wrapper.py:9)"),
+    ("c5_cartpole_simple_genetic_pop1m", "conf/cartpole_genetic.yaml", {}, "BASELINE configs[4]: CartPole simple_genetic, P = 2^20"),
+]
+
+
+def gru_balancing_parent():
+    """A GRU policy that balances the fully observed pole: fc1 unit 0 is a bang-bang feature, the n gate carries it, z ~ 0."""
+    import numpy as np
+    mu = np.zeros(6562, np.float32)
+    mu[0:128].reshape(32, 4)[0] = [0.0, 0.5, 10.0, 3.0]
+    mu[160:160 + 3072].reshape(96, 32)[64, 0] = 3.0
+    mu[160 + 6144:160 + 6144 + 96][32:64] = -10.0
+    w2 = mu[160 + 6144 + 192:160 + 6144 + 192 + 64].reshape(2, 32)
+    w2[1, 0] = 5.0; w2[0, 0] = -5.0
+    return mu
+
+
+def converged_state():
+    """The committed generation-30 state as a strategy resume dict (strategies._Base.load_state)."""
+    import torch
+    st = bench_state()
+    return {"strategy": "openai_es", "generation": 30, "sigma": st["sigma"], "curr_sigma": st["sigma"], "population": P_DEFAULT,
+            "parents": torch.from_numpy(st["mu"].copy()).reshape(1, -1), "m": torch.from_numpy(st["m"].copy()),
+            "v": torch.from_numpy(st["v"].copy()), "t": st["t"]}
+
+
+def bits_checksum(t):
+    """Position-weighted wrap-around checksum of a tensor's BITS (int64): equal on two ranks iff (for all practical
+    purposes) the tensors are bit-identical."""
+    import torch
+    b = t.detach().contiguous().view(torch.uint8).to(torch.int64)
+    w = torch.arange(1, b.numel() + 1, dtype=torch.int64, device=b.device) * 2654435761
+    return (b * w).sum()
+
+
 # ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
-def run_b200(args):
-    import torch
-    import torch.distributed as dist
-    from simple_es_b200 import dist as sdist
+def make_loop(args, local, gens):
     from simple_es_b200.loop import B200Loop
-
-    rank, world = sdist.init_from_env()
-    local = int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
     config = {"env": {"name": "CartPole-v1", "max_step": 500, "pomdp": False},
               "network": {"name": "gym_model", "num_state": 4, "num_action": 2, "discrete_action": True, "gru": False},
               "strategy": dict(STRATEGY, offspring_num=args.pop),
               "engine": {"name": "b200", "fitness_exchange": args.exchange, "shard": args.shard}}
-    loop = B200Loop(config, args.steps + args.warmup, 1, E_DEFAULT, log=False, save_model_period=0, seed=0, device=local, quiet=True)
-    s = loop.strategy
-    eng = s.engine
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    return B200Loop(config, gens, 1, E_DEFAULT, log=False, save_model_period=0, seed=0, device=local, quiet=True)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        s.step()
-    barrier()
-    steps_before = int(s.total_env_steps.item())
-    launches_before = eng.launches
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+def reset_to_regime(s, regime, rep=0):
+    """Put an OpenAIES strategy at the start of `regime` (rep: which generation-0 repetition)."""
+    if regime == "converged":
+        if s.P == P_DEFAULT:
+            s.load_state(converged_state())
+        else:                                        # another population size: the same parameters, Adam state and sigma
+            st = converged_state(); st["population"] = s.P
+            s.load_state(st)
+    else:
+        s.parents.zero_(); s.m.zero_(); s.v.zero_()
+        s.t = 0
+        s.sigma = s.curr_sigma = float(STRATEGY["init_sigma"])
+        s.generation = rep
+
+
+def timed_generations(s, steps, flush, barrier, gen0=False, keep_prev_mu=None):
+    """`steps` openai_es generations of strategy `s`, each bracketed by CUDA events on the launching stream with one more
+    event after K1 (the dominant kernel is timed alone); the L2 flush sits outside the events.  gen0: every step is a
+    generation-0 population (state reset between steps, outside the events).  Returns (gen_ms, k1_ms, env_steps, wall_s)."""
+    import torch
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    e = s.engine
+    before = int(s.total_env_steps.item())
     barrier()
     wall0 = time.perf_counter()
-    for k in range(args.steps):
-        flush.fill_(k & 0xFF)                      # L2 flush, outside the timed events
+    for k in range(steps):
+        if gen0:
+            reset_to_regime(s, "gen0", rep=1000 + k)
+        if keep_prev_mu is not None:
+            keep_prev_mu.copy_(s.parents)            # 904 B device copy: the population of the last generation can be re-derived
+        flush.fill_(k & 0xFF)                        # L2 flush, outside the timed events
         ev[k][0].record()
-        # one generation, with an extra event after K1 so that the dominant kernel is timed alone
-        e = s.engine
         s.fitness = s._fit[s.generation & 1]
         e.rollout(s.generation, s.sigma, s.parents, fitness=s.fitness, steps=s.steps)
         ev[k][1].record()
@@ -264,94 +322,278 @@ def run_b200(args):
         e.rank_desc(s.fitness, shaped=True, order=s.order, shaped_out=s.shaped)
         s.t += 1
         e.update_openai(s.generation, s.sigma, s.lr, s.t, s.shaped, s.parents.view(-1), s.m, s.v)
+        s.last_sigma = s.sigma
         s.sigma *= s.decay; s.curr_sigma = s.sigma; s.generation += 1
         ev[k][2].record()
     barrier()
     wall = time.perf_counter() - wall0
-    clocks = sampler.stop() if rank == 0 else None
-    gen_ms = sum(ev[k][0].elapsed_time(ev[k][2]) for k in range(args.steps))
-    k1_ms = sum(ev[k][0].elapsed_time(ev[k][1]) for k in range(args.steps))
-    local_steps = int(s.total_env_steps.item()) - steps_before
-    k1_local_steps = local_steps
-    best = float(s.best_reward().item())
-    launches = eng.launches - launches_before
+    gen_ms = sum(ev[k][0].elapsed_time(ev[k][2]) for k in range(steps))
+    k1_ms = sum(ev[k][0].elapsed_time(ev[k][1]) for k in range(steps))
+    return gen_ms, k1_ms, int(s.total_env_steps.item()) - before, wall
+
+
+def reduce_over_ranks(dev, world, gen_ms, k1_ms, n_steps):
+    """max over ranks of the times, sum over ranks of the env steps (device-timed numbers, never wall clock)."""
+    import torch
+    import torch.distributed as dist
     t = torch.tensor([gen_ms, k1_ms], dtype=torch.float64, device=dev)
     tsum = t.clone()
-    n = torch.tensor([local_steps], dtype=torch.int64, device=dev)
+    n = torch.tensor([n_steps], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         dist.all_reduce(n, op=dist.ReduceOp.SUM)
-    # load balance over ranks: K1 time of the slowest rank vs the mean
-    k1_rank_ms = {"max": float(t[1]) / args.steps, "mean": float(tsum[1]) / world / args.steps}
-    gen_ms, k1_ms = float(t[0]), float(t[1])
-    total_steps = int(n[0])
+    return float(t[0]), float(t[1]), float(tsum[1]) / world, int(n[0])
 
-    # ---------------- e2e: the same generations with HOST buffers, copies inside the timed region (wall clock, max over ranks)
+
+def regime_block(gen_ms, k1_ms, total_steps, steps, pop):
+    return {"ms_per_generation": gen_ms / steps, "k1_ms_per_generation": k1_ms / steps, "generations_per_sec": steps / (gen_ms * 1e-3),
+            "env_steps_per_sec": total_steps / (gen_ms * 1e-3), "env_steps": total_steps, "steps": steps,
+            "mean_episode_len": total_steps / float(steps * pop * E_DEFAULT)}
+
+
+def run_extra_config(key, path, overrides, note, local, world, steps, warmup, flush, barrier, args):
+    """One of the other BASELINE configs through the public API (B200Loop.strategy.step()), device-timed."""
+    import torch
+    import yaml
+    from simple_es_b200.loop import B200Loop
+    with open(os.path.join(ROOT, path)) as fh:
+        cfg = yaml.load(fh, Loader=yaml.FullLoader)
+    init = None
+    for k, v in overrides.items():
+        if k == "init":
+            init = v
+            continue
+        a, b = k.split(".")
+        cfg[a][b] = v
+    cfg["engine"] = dict(cfg.get("engine") or {}, fitness_exchange=args.exchange, shard=args.shard)
+    loop = B200Loop(cfg, steps + warmup, 1, E_DEFAULT, log=False, save_model_period=0, seed=0, device=local, quiet=True)
+    s = loop.strategy
+    if init == "gru_balancing":
+        s.load_elite(gru_balancing_parent())
+    for _ in range(warmup):
+        s.step()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(steps)]
+    before = int(s.total_env_steps.item())
+    barrier()
+    for k in range(steps):
+        flush.fill_(k & 0xFF)
+        ev[k][0].record(); s.step(); ev[k][1].record()
+    barrier()
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    n = int(s.total_env_steps.item()) - before
+    best = float(s.best_reward().item())
+    ms, _, _, n = reduce_over_ranks(s.engine.device, world, ms, 0.0, n)
+    out = {"config": note, "yaml": path, "overrides": overrides, "strategy": cfg["strategy"]["name"], "population": s.P, "D": s.D,
+           "steps": steps, "warmup": warmup, "ms_per_generation": ms / steps, "generations_per_sec": steps / (ms * 1e-3),
+           "env_steps_per_sec": n / (ms * 1e-3), "env_steps": n, "mean_episode_len": n / float(steps * s.P * E_DEFAULT),
+           "best_reward_last_gen": best, "n_gpus": world, "regime": "generations %d..%d of a run started from %s" % (warmup, warmup + steps - 1, "mu = 0" if init is None else init)}
+    if s.exchange == "peer":
+        s.engine.peer_check()
+    del loop, s
+    torch.cuda.synchronize()
+    return out
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from simple_es_b200 import dist as sdist
+
+    rank, world = sdist.init_from_env()
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- headline: K timed generations in the chosen regime (default: converged)
+    loop = make_loop(args, local, args.steps + args.warmup)
+    s = loop.strategy
+    eng = s.engine
+    reset_to_regime(s, args.regime)
+    for w in range(args.warmup):
+        if args.regime == "gen0":
+            reset_to_regime(s, "gen0", rep=900 + w)
+        s.step()
+    barrier()
+    launches_before = eng.launches
+    prev_mu = torch.empty_like(s.parents)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    gen_ms_l, k1_ms_l, local_steps, wall = timed_generations(s, args.steps, flush, barrier, gen0=args.regime == "gen0", keep_prev_mu=prev_mu)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = eng.launches - launches_before
+    best = float(s.best_reward().item())
+    gen_ms, k1_ms, k1_mean_ms, total_steps = reduce_over_ranks(dev, world, gen_ms_l, k1_ms_l, local_steps)
+    k1_rank_ms = {"max": k1_ms / args.steps, "mean": k1_mean_ms / args.steps}
+    if s.exchange == "peer":
+        eng.peer_check()
+
+    # ---------------- N > 1: every rank must hold the same bits, and a sample of the last generation must equal a 1-GPU rollout
+    rank_consistency = None
+    if world > 1:
+        sums = torch.stack([bits_checksum(x) for x in (s.parents, s.m, s.v, s.order, s.fitness, s.shaped)])
+        allsums = [torch.empty_like(sums) for _ in range(world)]
+        dist.all_gather(allsums, sums)
+        identical = all(bool(torch.equal(a, allsums[0])) for a in allsums)
+        sample_equal, n_sample = None, min(512, args.pop)
+        if rank == 0:
+            from simple_es_b200.engine import RolloutEngine
+            chk = RolloutEngine("CartPole-v1", 4, 2, False, False, 500, E_DEFAULT, args.pop, args.pop, 1, 1, seed=0, device=local,
+                                id_begin=0, id_end=n_sample)
+            fit1, _ = chk.rollout(s.generation - 1, s.last_sigma, prev_mu)
+            torch.cuda.synchronize()
+            sample_equal = bool(torch.equal(fit1[:n_sample], s.fitness[:n_sample]))
+            chk.close()
+        barrier()
+        rank_consistency = {"identical": identical, "sample_equal": sample_equal,
+                            "checked": "bit checksums of mu, Adam m, Adam v, rank order, fitness[P] and shaped fitness[P] after the last timed "
+                                       "generation, all-gathered from %d ranks; fitness of offspring 0..%d of that generation recomputed on rank 0 "
+                                       "alone by a single-GPU engine (same mu, sigma, seed, generation) and compared bit for bit with the exchanged vector"
+                                       % (world, n_sample - 1)}
+
+    # ---------------- the other regimes of the headline workload (SURVEY 8d: generation-0 and converged reported separately)
+    regimes = {args.regime: regime_block(gen_ms, k1_ms, total_steps, args.steps, args.pop)}
+    if not args.no_regimes:
+        k_other = max(3, min(args.steps, 20))
+        for reg in ("converged", "gen0", "from_scratch"):
+            if reg in regimes:
+                continue
+            reset_to_regime(s, reg)
+            for w in range(3):
+                if reg == "gen0":
+                    reset_to_regime(s, "gen0", rep=900 + w)
+                s.step()
+            if reg == "from_scratch":
+                for _ in range(max(0, args.warmup - 3)):
+                    s.step()
+            g, k1, n, _ = timed_generations(s, k_other, flush, barrier, gen0=reg == "gen0")
+            g, k1, _, n = reduce_over_ranks(dev, world, g, k1, n)
+            regimes[reg] = regime_block(g, k1, n, k_other, args.pop)
+        if s.exchange == "peer":
+            eng.peer_check()
+    n_local = eng.n_local
+    del loop, s, eng
+    torch.cuda.synchronize()
+
+    # ---------------- e2e: THE SAME generations with HOST buffers, copies inside the timed region (wall clock, max over ranks)
     e2e = None
+    P = args.pop
     if world == 1:
         # the reference-facing C-ABI call: ses_generation_openai_host (H2D mu/m/v, K1-K3, D2H fitness[P] + mu/m/v + steps)
         import numpy as np
         from simple_es_b200.engine import RolloutEngine
-        P = args.pop
         eng2 = RolloutEngine("CartPole-v1", 4, 2, False, False, 500, E_DEFAULT, P, P, 1, 1, seed=0, device=local)
         pin = lambda n_, dt: torch.empty(n_, dtype=dt).pin_memory().numpy()
         mu, m, v = pin(D, torch.float32), pin(D, torch.float32), pin(D, torch.float32)
         fit = pin(P, torch.float64)
-        mu[:] = 0; m[:] = 0; v[:] = 0
-        sigma = STRATEGY["init_sigma"]
-        for g in range(args.warmup):
-            eng2.generation_openai_host(g, sigma, STRATEGY["learning_rate"], g + 1, mu, m, v, fit)
-            sigma *= STRATEGY["sigma_decay"]
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        tot = 0
-        for g in range(args.warmup, args.warmup + args.steps):
-            tot += eng2.generation_openai_host(g, sigma, STRATEGY["learning_rate"], g + 1, mu, m, v, fit)
-            sigma *= STRATEGY["sigma_decay"]
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
+        reps = []
+        for rep in range(2):                          # two passes over the same generations; the better one is reported
+            if args.regime == "converged":
+                st = bench_state()
+                mu[:] = st["mu"]; m[:] = st["m"]; v[:] = st["v"]
+                sigma, t, g0 = st["sigma"], st["t"], 30
+            else:
+                mu[:] = 0; m[:] = 0; v[:] = 0
+                sigma, t, g0 = STRATEGY["init_sigma"], 0, 0
+
+            def host_gen(g, sigma, t):
+                return eng2.generation_openai_host(g, sigma, STRATEGY["learning_rate"], t, mu, m, v, fit)
+            for w in range(args.warmup):
+                if args.regime == "gen0":
+                    mu[:] = 0; m[:] = 0; v[:] = 0
+                    host_gen(900 + w, STRATEGY["init_sigma"], 1)
+                else:
+                    t += 1; host_gen(g0, sigma, t); sigma *= STRATEGY["sigma_decay"]; g0 += 1
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            tot = 0
+            for k in range(args.steps):
+                if args.regime == "gen0":
+                    mu[:] = 0; m[:] = 0; v[:] = 0
+                    tot += host_gen(1000 + k, STRATEGY["init_sigma"], 1)
+                else:
+                    t += 1; tot += host_gen(g0, sigma, t); sigma *= STRATEGY["sigma_decay"]; g0 += 1
+            torch.cuda.synchronize()
+            reps.append((time.perf_counter() - t0, tot))
+        dt, tot = min(reps)
         e2e = {"value": tot / dt, "unit": "env-steps/s", "h2d_bytes_per_step": 3 * D * 4, "d2h_bytes_per_step": P * 8 + 3 * D * 4 + 8,
                "api": "ses_generation_openai_host (C ABI, pinned host buffers, synchronous)", "n_gpus": 1, "env_steps": tot,
-               "generations_per_sec": args.steps / dt}
+               "generations_per_sec": args.steps / dt, "same_generations_as_value": tot == total_steps,
+               "note": "the generations `value` was measured on, replayed through the host-buffer call (the engine is deterministic: "
+                       "env_steps equals the device-timed run's); wall clock around K synchronous calls, L2 not flushed in between"}
         eng2.close()
     else:
-        # N ranks: every rank stages mu/m/v from pinned host memory, runs its shard of the generation through the
-        # public strategy API (B200Loop.strategy.step()), and reads the full fitness vector + mu/m/v back to the host
-        P = args.pop
+        # N ranks: a fresh strategy replays the same generations; every rank stages mu/m/v from pinned host memory, runs its
+        # shard of the generation through the public strategy API, and reads the full fitness vector + mu/m/v back to the host
+        loop2 = make_loop(args, local, args.steps + args.warmup)
+        s2 = loop2.strategy
+        reset_to_regime(s2, args.regime)
         pinned = lambda n_, dt: torch.empty(n_, dtype=dt).pin_memory()
         mu_h, m_h, v_h, fit_h = pinned(D, torch.float32), pinned(D, torch.float32), pinned(D, torch.float32), pinned(P, torch.float64)
-        mu_h.copy_(s.parents[0]); m_h.copy_(s.m); v_h.copy_(s.v)
+
+        def host_step():
+            s2.parents[0].copy_(mu_h, non_blocking=True); s2.m.copy_(m_h, non_blocking=True); s2.v.copy_(v_h, non_blocking=True)
+            s2.step()
+            fit_h.copy_(s2.fitness, non_blocking=True)
+            mu_h.copy_(s2.parents[0], non_blocking=True); m_h.copy_(s2.m, non_blocking=True); v_h.copy_(s2.v, non_blocking=True)
+            torch.cuda.synchronize()
+        mu_h.copy_(s2.parents[0]); m_h.copy_(s2.m); v_h.copy_(s2.v)
         torch.cuda.synchronize()
-        steps0 = int(s.total_env_steps.item())
+        for w in range(args.warmup):
+            if args.regime == "gen0":
+                reset_to_regime(s2, "gen0", rep=900 + w); mu_h.zero_(); m_h.zero_(); v_h.zero_()
+            host_step()
+        steps0 = int(s2.total_env_steps.item())
         barrier()
         t0 = time.perf_counter()
         for k in range(args.steps):
-            s.parents[0].copy_(mu_h, non_blocking=True); s.m.copy_(m_h, non_blocking=True); s.v.copy_(v_h, non_blocking=True)
-            s.step()
-            fit_h.copy_(s.fitness, non_blocking=True)
-            mu_h.copy_(s.parents[0], non_blocking=True); m_h.copy_(s.m, non_blocking=True); v_h.copy_(s.v, non_blocking=True)
-            torch.cuda.synchronize()
+            if args.regime == "gen0":
+                reset_to_regime(s2, "gen0", rep=1000 + k); mu_h.zero_(); m_h.zero_(); v_h.zero_()
+            host_step()
         barrier()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        nn = torch.tensor([int(s.total_env_steps.item()) - steps0], dtype=torch.int64, device=dev)
+        nn = torch.tensor([int(s2.total_env_steps.item()) - steps0], dtype=torch.int64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(nn, op=dist.ReduceOp.SUM)
+        if s2.exchange == "peer":
+            s2.engine.peer_check()
         e2e = {"value": int(nn[0]) / float(tt[0]), "unit": "env-steps/s", "h2d_bytes_per_step": 3 * D * 4,
                "d2h_bytes_per_step": P * 8 + 3 * D * 4,
                "api": "B200Loop.strategy.step() per rank with pinned host staging of mu/m/v (H2D) and fitness[P] + mu/m/v (D2H), "
                       "synchronous; bytes are per rank", "n_gpus": world, "env_steps": int(nn[0]),
-               "generations_per_sec": args.steps / float(tt[0])}
+               "generations_per_sec": args.steps / float(tt[0]), "same_generations_as_value": int(nn[0]) == total_steps,
+               "note": "a fresh strategy replays the generations `value` was measured on (same state, same warm-up); wall clock, max over ranks"}
+        del loop2, s2
+        torch.cuda.synchronize()
+
+    # ---------------- the other BASELINE configs (N = 1: all of them; N > 1: the 8-GPU scaling config)
+    extra = None
+    if not args.no_extra:
+        extra = {}
+        for key, path, overrides, note in EXTRA_CONFIGS:
+            if world > 1 and not key.startswith("c5"):
+                continue
+            try:
+                extra[key] = run_extra_config(key, path, overrides, note, local, world, args.extra_steps, 3, flush, barrier, args)
+            except Exception as exc:  # pragma: no cover
+                extra[key] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+            barrier()
 
     if world > 1:
-        s.engine.peer_check() if s.exchange == "peer" else None
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
         return 0
     peak_tf = measure_fp32_peak(local)
-    achieved_tf = k1_local_steps * FLOP_PER_STEP / (k1_ms * 1e-3) / 1e12 if k1_ms > 0 else 0.0
+    achieved_tf = local_steps * FLOP_PER_STEP / (k1_ms_l * 1e-3) / 1e12 if k1_ms_l > 0 else 0.0
     value = total_steps / (gen_ms * 1e-3)
     line = {
         "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
@@ -360,25 +602,37 @@ def run_b200(args):
         "config": workload_config(args, world),
         "per_gpu": value / world, "generations_per_sec": args.steps / (gen_ms * 1e-3), "env_steps": total_steps,
         "best_reward_last_gen": best, "wall_s": wall, "k1_ms_per_generation_over_ranks": k1_rank_ms,
-        "roofline": {"bound": "fp32_pipe", "kernel": "k_rollout_cartpole_mlp", "achieved": achieved_tf, "peak": peak_tf,
+        "regimes": regimes,
+        "roofline": {"bound": "fp32_pipe", "kernel": K1_SYMBOL, "achieved": achieved_tf, "peak": peak_tf,
                      "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": K1_DRAM_BYTES_PER_LAUNCH,
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of K1 (profiles/r01_k1_v4_conv.txt); "
-                                       "algorithmic bytes per launch: 904 B of parameters + 16 B per offspring of results",
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of K1 (%s); "
+                                       "algorithmic bytes per launch: 904 B of parameters + 16 B per offspring of results" % K1_PROFILE,
                      "peak_source": "measured live: dependent-free FFMA microbenchmark on this GPU (MEASURED_PEAKS.json has only HBM and bf16-tensor peaks)",
-                     "algorithmic": "%d FP32 FLOP per env step (SURVEY 8d) x %d env steps of rank 0 / %.3f ms in K1" % (FLOP_PER_STEP, k1_local_steps, k1_ms),
+                     "algorithmic": "%d FP32 FLOP per env step (SURVEY 8d) x %d env steps of rank 0 / %.3f ms in K1 on rank 0" % (FLOP_PER_STEP, local_steps, k1_ms_l),
+                     "frac_ceiling": FLOP_PER_STEP / float(2 * FMA_LANE_OPS_PER_STEP),
+                     "frac_ceiling_note": "the 418 algorithmic FLOP exclude the 32 float32 tanh per env step, each 14 FMA-pipe operations in the bit-reproducible "
+                                          "contract: 640 executed FMA-pipe lane operations (1280 FLOP-equivalents) per env step, so `frac` cannot exceed 418 / 1280 = 0.33; "
+                                          "`fma_pipe_frac` is the executed share and compares with ncu's sm__pipe_fmaheavy_cycles_active",
                      "k1_share_of_step": k1_ms / gen_ms if gen_ms else None,
-                     "fma_pipe_frac": (k1_local_steps * FMA_LANE_OPS_PER_STEP * 2 / (k1_ms * 1e-3) / 1e12 / peak_tf) if (peak_tf and k1_ms > 0) else None,
+                     "fma_pipe_frac": (local_steps * FMA_LANE_OPS_PER_STEP * 2 / (k1_ms_l * 1e-3) / 1e12 / peak_tf) if (peak_tf and k1_ms_l > 0) else None,
                      "fma_pipe_note": "share of the FP32 FMA pipe K1 keeps busy: 640 FMA-pipe lane operations per env step (the 418 algorithmic "
                                       "FLOP count no tanh; an accurate float32 tanh costs 14 FMA-pipe operations) x 2 FLOP / measured FFMA peak"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
     }
-    line["roofline"]["hbm_check"] = hbm_check(eng.n_local, k1_ms / args.steps if args.steps else 0.0)
+    if rank_consistency is not None:
+        line["rank_consistency"] = rank_consistency
+    if extra is not None:
+        line["extra_configs"] = extra
+    line["roofline"]["hbm_check"] = hbm_check(n_local, k1_ms_l / args.steps if args.steps else 0.0)
     if world == 1 and not args.no_cpu:
         try:
             line["cpu_baseline"] = cpu_baseline_block(os.cpu_count() or 1)
         except Exception as exc:  # pragma: no cover
             line["cpu_baseline"] = {"error": str(exc)}
     print(json.dumps(line))
+    if rank_consistency is not None and not (rank_consistency["identical"] and rank_consistency["sample_equal"]):
+        sys.stderr.write("bench.py: ranks disagree after the timed generations: %r\n" % (rank_consistency,))
+        return 3
     return 0
 
 
@@ -422,6 +676,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pop", type=int, default=P_DEFAULT)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--regime", default="converged", choices=["converged", "from_scratch", "gen0"],
+                    help="policy regime of the headline `value` (SURVEY 8d); the other two are reported under `regimes`")
+    ap.add_argument("--no-regimes", action="store_true", help="skip the other regimes of the headline workload")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE configs (`extra_configs`)")
+    ap.add_argument("--extra-steps", type=int, default=10, help="timed generations per extra config")
     ap.add_argument("--exchange", default=os.environ.get("SES_FITNESS_EXCHANGE", "peer"), choices=["peer", "nccl"],
                     help="N > 1: fitness exchange fused into K1 over NVLink peer memory (default) or an NCCL all-gather")
     ap.add_argument("--shard", default="cyclic", choices=["cyclic", "contiguous"],

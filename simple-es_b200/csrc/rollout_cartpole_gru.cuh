@@ -300,7 +300,7 @@ static int launch_rollout_cartpole_gru_ec(int num_sms, int ctas_per_sm, const Ro
     constexpr int WARPS = 4;
     const size_t smem = WARPS * sizeof(GruWarpSmem<EC>);
     const char *ev = getenv("SES_GRU_VARIANT");                       // read per launch: tests switch it inside one process
-    const int spec = ev && *ev ? atoi(ev) : 0;
+    const int spec = ev && *ev ? atoi(ev) : 1;                        // default: the speculative-physics kernel (measured 5 % faster)
     auto kern = spec == 1 ? (trace ? k_rollout_cartpole_gru<EC, WARPS, true, true> : k_rollout_cartpole_gru<EC, WARPS, false, true>)
                           : (trace ? k_rollout_cartpole_gru<EC, WARPS, true, false> : k_rollout_cartpole_gru<EC, WARPS, false, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -83,11 +83,13 @@ struct ses_handle {
     int peer_rank = 0, peer_world = 0;
     unsigned long long peer_epoch = 0;
     int *peer_error = nullptr;
+    long long peer_timeout_cycles = 20000000000ll;
+    double *last_rollout_fitness = nullptr;       // exchange buffer the last fused-exchange rollout wrote (poisoned on a barrier timeout)
     unsigned long long *step_counter = nullptr;   // caller-owned, optional (ses_set_step_counter)
     // rollout launch configuration
     int lanes_used_override = 0;
     int ctas_per_sm = 0;
-    int k1_variant = 4;
+    int k1_variant = 7;
     int spread_slots8 = 0;
 
     int64_t launches = 0;
@@ -165,10 +167,10 @@ extern "C" int ses_create(const ses_config *cfg, ses_handle **out)
     h->eff_max_step = cfg->max_step > 0 ? (cfg->max_step < env_cap ? cfg->max_step : env_cap) : env_cap;
     h->lanes_used_override = env_int("SES_ROLLOUT_LANES", 0);
     h->ctas_per_sm = env_int("SES_ROLLOUT_CTAS_PER_SM", 0);
-    h->k1_variant = env_int("SES_K1_VARIANT", 4);
+    h->k1_variant = env_int("SES_K1_VARIANT", 7);
     h->spread_slots8 = env_int("SES_SPREAD_SLOTS8", 0);
     h->k2_fused = env_int("SES_K2_FUSED", 1);     // 1 + passes launches (default); 0: the separate kernels
-    if (h->k1_variant < 0 || h->k1_variant > 7) h->k1_variant = 4;
+    if (h->k1_variant < 0 || h->k1_variant > 7) h->k1_variant = 7;
 
     const int P = cfg->population;
     h->n_tiles = (P + sort_tile(SORT_ITEMS_SMALL) - 1) / sort_tile(SORT_ITEMS_SMALL);
@@ -282,6 +284,7 @@ extern "C" int ses_rollout(ses_handle *h, uint32_t generation, float sigma, cons
             if (fitness_dev == h->xbuf + (size_t)parity * c.population)
                 for (int r = 0; r < h->peer_world; ++r)
                     if (r != h->peer_rank) rp.peer_fitness[rp.n_peers++] = h->peer_x[r] + (size_t)parity * c.population;
+        h->last_rollout_fitness = rp.n_peers > 0 ? fitness_dev : nullptr;
     }
 
     // lanes of a warp that take episodes: a multiple of E so that slots start and finish together
@@ -304,8 +307,8 @@ extern "C" int ses_rollout(ses_handle *h, uint32_t generation, float sigma, cons
             if (h->k1_variant == 7) return launch_slots<CartpoleMlpEnvT<7>, 8>(h, rp, need_warps, tr, st);
             return launch_slots<CartpoleMlpEnvT<1>, 8>(h, rp, need_warps, tr, st);
         }
-        if (c.eval_ep_num >= 2) return launch_slots<CartpoleMlpEnvT<4>, 16>(h, rp, need_warps, tr, st);
-        return launch_slots<CartpoleMlpEnvT<4>, 32>(h, rp, need_warps, tr, st);
+        if (c.eval_ep_num >= 2) return launch_slots<CartpoleMlpEnvT<7>, 16>(h, rp, need_warps, tr, st);
+        return launch_slots<CartpoleMlpEnvT<7>, 32>(h, rp, need_warps, tr, st);
     }
     if (c.env == SES_ENV_CARTPOLE && c.gru) return launch_rollout_cartpole_gru(h->num_sms, h->ctas_per_sm, rp, tr, st, &h->launches, g_err, sizeof(g_err));
     if (c.env == SES_ENV_MOUNTAINCAR) return launch_slots_by_E<MountainCarEnv>(h, rp, need_warps, tr, st);
@@ -362,6 +365,12 @@ extern "C" int ses_peer_attach(ses_handle *h, const void *ipc_handles, int32_t r
     h->peer_rank = rank;
     h->peer_world = world;
     h->peer_epoch = 0;
+    {
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, h->cfg.device));
+        const long long ms = env_int("SES_PEER_TIMEOUT_MS", 10000);
+        h->peer_timeout_cycles = (ms > 0 ? ms : 10000) * (long long)prop.clockRate;      // clockRate is in kHz = cycles per ms
+    }
     return 0;
 }
 
@@ -372,11 +381,14 @@ extern "C" int ses_peer_fitness_ptr(ses_handle *h, int32_t parity, double **out)
     return 0;
 }
 
-// one CTA, thread r <-> peer r: raise my flag in r's buffer, then wait for r's flag in mine
+// one CTA, thread r <-> peer r: raise my flag in r's buffer, then wait for r's flag in mine.  A peer that does not arrive
+// within `timeout_cycles` SM cycles (SES_PEER_TIMEOUT_MS, default 10 s at the nominal SM clock; a throttled clock only makes
+// the wait longer) sets the sticky error flag AND poisons this generation's fitness vector with a NaN, so that nothing
+// downstream can silently consume a partially filled vector; B200Loop calls ses_peer_check() every generation and raises.
 __global__ void k_peer_barrier(unsigned long long *my_flags, unsigned long long *p0,
                                unsigned long long *p1, unsigned long long *p2, unsigned long long *p3, unsigned long long *p4,
                                unsigned long long *p5, unsigned long long *p6, unsigned long long *p7, int rank, int world,
-                               unsigned long long epoch, int *error)
+                               unsigned long long epoch, long long timeout_cycles, int *error, double *poison)
 {
     unsigned long long *peers[MAX_PEERS] = {p0, p1, p2, p3, p4, p5, p6, p7};
     const int r = threadIdx.x;
@@ -388,11 +400,16 @@ __global__ void k_peer_barrier(unsigned long long *my_flags, unsigned long long 
     for (;;) {
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(my_flags + r) : "memory");
         if (seen >= epoch) break;
-        if (clock64() - t0 > 20000000000ll) { atomicExch(error, 1); break; }     // ~10 s: a peer died
+        if (clock64() - t0 > timeout_cycles) {                                   // a peer died or stalled
+            atomicExch(error, 1);
+            if (poison) poison[0] = __longlong_as_double(0x7ff8000000000000ll);
+            break;
+        }
     }
 }
 
-extern "C" int ses_peer_barrier(ses_handle *h, void *stream)
+// `poison_fitness`: the exchange buffer of the generation this barrier publishes (nullptr for the gradient-row barrier)
+static int peer_barrier_launch(ses_handle *h, void *stream, double *poison_fitness)
 {
     if (!h || h->peer_world < 2) return fail("ses_peer_barrier: peers not attached");
     CU(cudaSetDevice(h->cfg.device));
@@ -400,10 +417,16 @@ extern "C" int ses_peer_barrier(ses_handle *h, void *stream)
     unsigned long long *f[MAX_PEERS] = {nullptr};
     for (int r = 0; r < h->peer_world; ++r) f[r] = xbuf_flags(h->peer_x[r], h);
     k_peer_barrier<<<1, 32, 0, S(stream)>>>(xbuf_flags(h->xbuf, h), f[0], f[1], f[2], f[3], f[4], f[5], f[6], f[7], h->peer_rank,
-                                            h->peer_world, h->peer_epoch, h->peer_error);
+                                            h->peer_world, h->peer_epoch, h->peer_timeout_cycles, h->peer_error, poison_fitness);
     h->launches += 1;
     CU(cudaGetLastError());
     return 0;
+}
+
+extern "C" int ses_peer_barrier(ses_handle *h, void *stream)
+{
+    if (!h) return fail("ses_peer_barrier: null handle");
+    return peer_barrier_launch(h, stream, h->last_rollout_fitness);
 }
 
 extern "C" int ses_peer_check(ses_handle *h)
@@ -516,7 +539,7 @@ static int grad_levels01(ses_handle *h, uint32_t generation, const double *shape
                                                                   part1, h->nb0, g0, n_chunks, n_peers, peers);
         h->launches += 1;
     }
-    if (shard && ses_peer_barrier(h, stream)) return -1;
+    if (shard && peer_barrier_launch(h, stream, nullptr)) return -1;
     *part1_out = part1;
     return 0;
 }

@@ -63,6 +63,8 @@ class B200Loop(BaseESLoop):
         # engine.init_from: a reference-format checkpoint (GymEnvModel.state_dict(), e.g. a saved ep_<n>.pt) as the initial
         # mu / elites; engine.resume: a resume_ep_<n>.pt written by this loop (engine.save_state: true) -- continues the
         # run bit for bit (parameters, sigma, Adam state, generation counter)
+        if self.engine_cfg.get("init_from") and self.engine_cfg.get("resume"):
+            raise ValueError("engine.init_from and engine.resume are exclusive: a resume state already holds the parameters")
         if self.engine_cfg.get("init_from"):
             sd = torch.load(self.engine_cfg["init_from"], map_location="cpu")
             self.strategy.load_elite(checkpoint.state_dict_to_flat(sd, int(net_cfg["num_state"]), int(net_cfg["num_action"]), bool(net_cfg["gru"])))
@@ -70,6 +72,7 @@ class B200Loop(BaseESLoop):
             st = torch.load(self.engine_cfg["resume"], map_location="cpu")
             self.strategy.load_state(st)
             self.start_ep = int(st["generation"])
+            self.ep5_rewards.extend(st.get("ep5_rewards", []))
 
         self.save_dir = save_dir
         if self.rank == 0 and self.save_model_period and self.save_model_period > 0:
@@ -95,6 +98,10 @@ class B200Loop(BaseESLoop):
             ep_num += 1
             s.step()
             best_reward = float(s.best_reward().item())      # the one device->host sync of a generation
+            if s.exchange == "peer":
+                # the stream is idle now, so this 4-byte read costs nothing: a peer GPU that missed the flag barrier
+                # (watchdog, SES_PEER_TIMEOUT_MS) must stop the run instead of letting the ranks drift apart
+                s.engine.peer_check()
             consumed = time.time() - start
             # rollout_t / eval_t (loop.py:70-88) are device times here: K1 + fitness exchange, and K2 + K3, taken from CUDA
             # events that the sync above has completed -- the phases are one stream-ordered pass, the host never waits between
@@ -111,5 +118,5 @@ class B200Loop(BaseESLoop):
             if self.rank == 0 and self.save_model_period and self.save_model_period > 0 and ep_num % self.save_model_period == 0:
                 torch.save(self.elite_state_dict(), self.save_dir + "/saved_models" + f"/ep_{ep_num}.pt")
                 if self.engine_cfg.get("save_state"):
-                    torch.save(s.state(), self.save_dir + "/saved_models" + f"/resume_ep_{ep_num}.pt")
+                    torch.save(dict(s.state(), ep5_rewards=list(self.ep5_rewards)), self.save_dir + "/saved_models" + f"/resume_ep_{ep_num}.pt")
         return self.history

@@ -41,6 +41,10 @@ class _Base:
             id_begin=0 if self.shard else self.lo, id_end=None if self.shard else self.hi, device=device,
             antithetic=bool(engine_cfg.get("antithetic", False)), shard=self.shard)
         self.D = self.engine.D
+        # what a resumed run must share with the run that wrote the state (state() / load_state())
+        self._run_key = {"env": name, "seed": int(seed) & 0xFFFFFFFF, "eval_ep_num": int(eval_ep_num),
+                         "init_states": engine_cfg.get("init_states", "shared"), "antithetic": bool(engine_cfg.get("antithetic", False)),
+                         "max_step": self.engine.max_step, "gru": bool(network_cfg["gru"]), "pomdp": bool(env_cfg.get("pomdp", False))}
         dev = self.engine.device
         self.parents = torch.zeros(n_par, self.D, dtype=torch.float32, device=dev)   # network.zero_init() (loop.py:31)
         # fitness exchange: "peer" = K1 stores fitness into every rank's buffer over NVLink + flag barrier (default);
@@ -116,7 +120,8 @@ class _Base:
         """Everything needed to continue this run bit for bit: the reference cannot resume (it only saves the elite's
         state_dict, loop.py:101-104); populations are functions of (parents, sigma, seed, generation) here."""
         st = {"strategy": self.name, "generation": self.generation, "sigma": self.sigma, "curr_sigma": self.curr_sigma,
-              "parents": self.parents.detach().cpu().clone(), "population": self.P}
+              "parents": self.parents.detach().cpu().clone(), "population": self.P, "run_key": dict(self._run_key),
+              "total_env_steps": int(self.total_env_steps.item())}
         for k in ("m", "v"):
             if hasattr(self, k):
                 st[k] = getattr(self, k).detach().cpu().clone()
@@ -128,6 +133,18 @@ class _Base:
         if st.get("strategy") != self.name or tuple(st["parents"].shape) != tuple(self.parents.shape):
             raise ValueError("resume state is for strategy %r with parents %s; this run is %r with parents %s"
                              % (st.get("strategy"), tuple(st["parents"].shape), self.name, tuple(self.parents.shape)))
+        if int(st.get("population", self.P)) != self.P:
+            raise ValueError("resume state is for a population of %d, this run has %d" % (int(st["population"]), self.P))
+        # populations are functions of (parents, sigma, seed, generation) and fitness of (env, E, initial states): a resumed
+        # run continues the old one bit for bit only if all of these are the same
+        theirs = st.get("run_key")
+        if theirs is not None:
+            diff = {k: (theirs.get(k), v) for k, v in self._run_key.items() if theirs.get(k) != v}
+            if diff:
+                raise ValueError("resume state was written by a different run: " +
+                                 ", ".join("%s was %r, now %r" % (k, a, b) for k, (a, b) in sorted(diff.items())))
+        if "total_env_steps" in st:
+            self.total_env_steps.fill_(int(st["total_env_steps"]))
         self.generation = int(st["generation"])
         self.sigma, self.curr_sigma = float(st["sigma"]), float(st["curr_sigma"])
         self.parents.copy_(st["parents"])

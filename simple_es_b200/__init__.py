@@ -1,11 +1,14 @@
-"""Importable alias of the ``simple-es_b200/`` package directory.
+"""simple-es B200 population-rollout engine (import name of the ``simple-es_b200/`` product directory).
 
-The product directory carries the name the project was given (with a hyphen, which Python cannot
-import); this stub makes ``import simple_es_b200`` resolve every submodule from there.
+Drop-in for the rollout hot path of jinPrelude/simple-es (perturb -> rollout -> fitness -> rank/select -> update) as
+hand-written sm_100a CUDA kernels behind the C ABI in ``include/ses_b200.h``.  There is no CPU fallback: importing works
+anywhere, but every compute call needs ``libses_b200.so`` and a CUDA device and fails loudly otherwise.
+
+The product directory carries the project's name, whose hyphen Python cannot import; this is a regular package whose
+search path is extended with that directory (the mechanism of ``pkgutil.extend_path``), so ``simple_es_b200.engine`` etc.
+are ordinary submodules found by the import system -- no code is executed from here.
 """
 import os as _os
 
-_impl = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "simple-es_b200")
-__path__ = [_impl]
-with open(_os.path.join(_impl, "__init__.py")) as _f:
-    exec(compile(_f.read(), _os.path.join(_impl, "__init__.py"), "exec"))
+__version__ = "0.2.0"
+__path__.append(_os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "simple-es_b200"))

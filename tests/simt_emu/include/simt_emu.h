@@ -427,7 +427,7 @@ enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cuda
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 enum { cudaIpcMemLazyEnablePeerAccess = 1 };
 struct cudaIpcMemHandle_t { char reserved[64]; };
-struct cudaDeviceProp { int major, minor, multiProcessorCount; char name[64]; };
+struct cudaDeviceProp { int major, minor, multiProcessorCount, clockRate; char name[64]; };
 
 inline const char *cudaGetErrorString(cudaError_t e)
 {
@@ -440,6 +440,7 @@ inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int)
 {
     memset(p, 0, sizeof(*p));
     p->major = 10; p->minor = 0;
+    p->clockRate = 1000000;          // kHz; the emulated clock64() counts nanoseconds
     const char *v = getenv("SES_SIMT_EMU_SMS");
     p->multiProcessorCount = v && *v ? atoi(v) : 2;
     snprintf(p->name, sizeof(p->name), "SIMT emulator (host)");

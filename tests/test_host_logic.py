@@ -2,6 +2,7 @@
 switch, the CLI flags and the checkpoint format."""
 import ctypes as C
 import os
+import sys
 import re
 
 import numpy as np
@@ -77,6 +78,52 @@ def test_builder_switch_and_configs():
     # max_step: None parses as the string "None", as in the reference (gym_wrapper.py:37)
     spread = yaml.load(open(os.path.join(ROOT, "conf", "simplespread.yaml")), Loader=yaml.FullLoader)
     assert spread["env"]["max_step"] == "None"
+
+
+def test_configs_without_engine_key_reach_the_reference_builder_by_path(tmp_path, monkeypatch):
+    """run_es.py / sweep_main.py import THIS repository's top-level `builder` shim, so the reference's module of
+    the same name can only be reached by path (SES_REFERENCE_ROOT/builder.py), with the checkout's root importable while
+    it executes.  A stand-in checkout records that its own build_loop received the call, through the shim the entry
+    points import."""
+    import builder
+    from simple_es_b200 import builder as impl
+    (tmp_path / "envs.py").write_text("NAME = 'stand-in envs package of the checkout'\n")
+    (tmp_path / "builder.py").write_text(
+        "import envs\n"
+        "def build_loop(config, gen_num, process_num, eval_ep_num, log, save_model_period):\n"
+        "    return ('reference loop', envs.NAME, config['env']['name'], gen_num, process_num, eval_ep_num, log, save_model_period)\n")
+    monkeypatch.setenv("SES_REFERENCE_ROOT", str(tmp_path))
+    monkeypatch.setattr(impl, "_REF_BUILDER", None)
+    cfg = {"env": {"name": "LunarLander-v2"}, "network": {}, "strategy": {}}
+    got = builder.build_loop(cfg, 7, 3, 5, False, 10)
+    assert got == ("reference loop", "stand-in envs package of the checkout", "LunarLander-v2", 7, 3, 5, False, 10)
+    # a checkout whose dependencies are missing fails loudly and names the module that is missing
+    (tmp_path / "builder.py").write_text("import gym_that_is_not_installed\n")
+    monkeypatch.setattr(impl, "_REF_BUILDER", None)
+    with pytest.raises(RuntimeError, match="gym_that_is_not_installed"):
+        builder.build_loop(cfg, 1, 1, 5, False, 10)
+    monkeypatch.delenv("SES_REFERENCE_ROOT")
+    monkeypatch.setattr(impl, "_REF_BUILDER", None)
+    with pytest.raises(RuntimeError, match="SES_REFERENCE_ROOT"):
+        builder.build_loop(cfg, 1, 1, 5, False, 10)
+    sys.modules.pop("envs", None)
+
+
+@pytest.mark.refonly
+def test_real_reference_builder_is_reached_when_present(monkeypatch):
+    """With the real checkout the path loader must get as far as the reference's own `import gym` (not installed here)."""
+    import builder
+    from simple_es_b200 import builder as impl
+    monkeypatch.setenv("SES_REFERENCE_ROOT", "/root/reference")
+    monkeypatch.setattr(impl, "_REF_BUILDER", None)
+    cfg = yaml.load(open(os.path.join(ROOT, "conf", "cartpole.yaml")), Loader=yaml.FullLoader)
+    cfg.pop("engine")
+    try:
+        loop = builder.build_loop(cfg, 1, 1, 5, False, 10)
+    except RuntimeError as exc:
+        assert "/root/reference/builder.py" in str(exc) and ("gym" in str(exc) or "pybullet" in str(exc) or "pettingzoo" in str(exc))
+    else:
+        assert type(loop).__name__ == "ESLoop"
 
 
 def test_cli_flags_match_reference():

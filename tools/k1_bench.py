@@ -36,7 +36,7 @@ def main():
     ap.add_argument("--regime", default="both")
     args = ap.parse_args()
     P = args.pop
-    out = {"variant": os.environ.get("SES_K1_VARIANT", "4"), "lanes": os.environ.get("SES_ROLLOUT_LANES", "auto"), "ctas_per_sm": os.environ.get("SES_ROLLOUT_CTAS_PER_SM", "auto"), "pop": P}
+    out = {"variant": os.environ.get("SES_K1_VARIANT", "7"), "lanes": os.environ.get("SES_ROLLOUT_LANES", "auto"), "ctas_per_sm": os.environ.get("SES_ROLLOUT_CTAS_PER_SM", "auto"), "pop": P}
     for regime in (["gen0", "converged"] if args.regime == "both" else [args.regime]):
         eng = RolloutEngine("CartPole-v1", 4, 2, False, False, 500, args.E, P, P, 1, 1, seed=0)
         mu = torch.from_numpy(np.zeros((1, D), np.float32) if regime == "gen0" else balancing_parent()).cuda()
