@@ -28,6 +28,7 @@
 /* from ses_twin.c */
 void tw_philox(const uint32_t *ctr, const uint32_t *key, uint32_t *out);
 int tw_param_count(int obs, int act, int gru);
+float tw_fc2_row(const float *w2row, const float *x, float bias);
 void tw_perturb(const float *parent, int D, float sigma, uint32_t seed, uint32_t gen, uint32_t id, int perturbed, float *w);
 void tw_tanhf_v(const float *x, float *y, int64_t n);
 
@@ -139,10 +140,8 @@ static int spread_policy(const float *w, int obs, const float *o, float *logits)
     tw_tanhf_v(pre, x, HID);
     float z[5];
     for (int m = 0; m < 5; ++m) {
-        float a = b2[m];
-        for (int j = 0; j < HID; ++j) a = fmaf(W2[m * HID + j], x[j], a);
-        z[m] = a;
-        if (logits) logits[m] = a;
+        z[m] = tw_fc2_row(W2 + m * HID, x, b2[m]);          /* four blocks of eight hidden units (ses_twin.c) */
+        if (logits) logits[m] = z[m];
     }
     return argmax_softmax(z, 5);
 }

@@ -5,7 +5,8 @@ import subprocess
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-LIB_PATH = os.path.join(_PKG, "libses_b200.so")
+# SES_B200_LIB: an alternative build of the same sources (A/B timing of compile-time choices; tools/ only)
+LIB_PATH = os.environ.get("SES_B200_LIB") or os.path.join(_PKG, "libses_b200.so")
 SOURCES = [os.path.join(_PKG, "csrc", f) for f in (
     "ses_abi.cu", "ses_common.cuh", "rollout_slots.cuh", "rollout_cartpole_mlp.cuh", "rollout_cartpole_gru.cuh", "rollout_mpe.cuh",
     "rollout_classic.cuh",

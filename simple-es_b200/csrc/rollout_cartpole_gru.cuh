@@ -230,13 +230,15 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_rollout_cartpole_gru(const Ro
                     float2 z = make_float2(b20, b21);
                     const float4 *orow = reinterpret_cast<const float4 *>(sm.obuf[lane]);
                     const float4 *wp = reinterpret_cast<const float4 *>(sm.w2p);
+                    float2 sblk = make_float2(0.0f, 0.0f);                 // contract 4.4: four blocks of eight hidden units
 #pragma unroll
                     for (int jq = 0; jq < HID / 4; ++jq) {
                         const float4 o = orow[jq], wa = wp[2 * jq], wb = wp[2 * jq + 1];
-                        z = __ffma2_rn(make_float2(wa.x, wa.y), make_float2(o.x, o.x), z);
-                        z = __ffma2_rn(make_float2(wa.z, wa.w), make_float2(o.y, o.y), z);
-                        z = __ffma2_rn(make_float2(wb.x, wb.y), make_float2(o.z, o.z), z);
-                        z = __ffma2_rn(make_float2(wb.z, wb.w), make_float2(o.w, o.w), z);
+                        sblk = __ffma2_rn(make_float2(wa.x, wa.y), make_float2(o.x, o.x), sblk);
+                        sblk = __ffma2_rn(make_float2(wa.z, wa.w), make_float2(o.y, o.y), sblk);
+                        sblk = __ffma2_rn(make_float2(wb.x, wb.y), make_float2(o.z, o.z), sblk);
+                        sblk = __ffma2_rn(make_float2(wb.z, wb.w), make_float2(o.w, o.w), sblk);
+                        if (jq & 1) { z = __fadd2_rn(z, sblk); sblk = make_float2(0.0f, 0.0f); }
                     }
                     const float z0 = z.x, z1 = z.y;
                     action = argmax_softmax2(z0, z1);

@@ -68,6 +68,9 @@ __device__ __forceinline__ int mlp_policy_flat(const float4 (&w)[NQ][S], int slo
 #pragma unroll
         for (int m = 0; m < ACT; ++m) z[m] = bz[m];
     }
+    float sblk[ACT];                                   // fc2 block sums (contract 4.4: four blocks of eight hidden units)
+#pragma unroll
+    for (int m = 0; m < ACT; ++m) sblk[m] = 0.0f;
 #pragma unroll
     for (int jq = 0; jq < HID / 4; ++jq) {
         float wr[4 * OBS];
@@ -87,7 +90,8 @@ __device__ __forceinline__ int mlp_policy_flat(const float4 (&w)[NQ][S], int slo
 #pragma unroll
         for (int m = 0; m < ACT; ++m) {
             const float4 t = w[O_W2 / 4 + m * (HID / 4) + jq][slot];
-            z[m] = fmaf(t.x, h[0], z[m]); z[m] = fmaf(t.y, h[1], z[m]); z[m] = fmaf(t.z, h[2], z[m]); z[m] = fmaf(t.w, h[3], z[m]);
+            sblk[m] = fmaf(t.x, h[0], sblk[m]); sblk[m] = fmaf(t.y, h[1], sblk[m]); sblk[m] = fmaf(t.z, h[2], sblk[m]); sblk[m] = fmaf(t.w, h[3], sblk[m]);
+            if (jq & 1) { z[m] = __fadd_rn(z[m], sblk[m]); sblk[m] = 0.0f; }
         }
     }
     // argmax(softmax(z)) with the float32 collapse rule (neural_network.py:30-31; ses_common.cuh argmax_softmax2)
@@ -112,6 +116,7 @@ struct MountainCarEnv {
     static constexpr int D = param_count(OBS, ACT, 0), NQ = (D + 3) / 4;     // 195, 49
     static constexpr int STATE_DIM = 2, N_AGENTS = 1;
     static constexpr bool UNIT_REWARD = false;
+    static constexpr bool LANES32_OK = true;     // the launcher may give all 32 lanes episodes (rollout_slots.cuh scheduler)
     struct State { double pos, vel, ret; };
 
     __device__ static __forceinline__ void init(State &s, const RolloutParams &p, int id, int ep)
@@ -157,6 +162,7 @@ struct AcrobotEnv {
     static constexpr int D = param_count(OBS, ACT, 0), NQ = (D + 3) / 4;     // 323, 81
     static constexpr int STATE_DIM = 4, N_AGENTS = 1;
     static constexpr bool UNIT_REWARD = false;
+    static constexpr bool LANES32_OK = true;     // the launcher may give all 32 lanes episodes (rollout_slots.cuh scheduler)
     static constexpr double PI = 3.141592653589793;
     // sc = { sin th1, cos th1, sin th2, cos th2 } of the current state: computed once per step (terminal test) and reused
     // by the next step's observation and first RK4 stage (same function, same argument: same bits as recomputing)

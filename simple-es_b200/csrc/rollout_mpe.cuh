@@ -83,6 +83,7 @@ struct SpreadEnv {
     static constexpr int D = param_count(OBS, ACT, 0), NQ = (D + 3) / 4;
     static constexpr int STATE_DIM = 4 * N, N_AGENTS = N;
     static constexpr bool UNIT_REWARD = false;
+    static constexpr bool LANES32_OK = false;     // the launcher may give all 32 lanes episodes (rollout_slots.cuh scheduler)
     static constexpr int OBS_EFF = OBS - 2 * (N - 1);      // trailing comm entries are always 0 (silent agents)
     // flat offsets (floats): W1 [32][OBS] | b1 [32] | W2 [5][32] | b2 [5]
     static constexpr int O_B1 = HID * OBS, O_W2 = O_B1 + HID, O_B2 = O_W2 + ACT * HID;
@@ -167,8 +168,19 @@ struct SpreadEnv {
                 for (int i = 0; i < NS; ++i) zs[i][m] = bz[m];
             }
         }
+        // fc2 in four blocks of eight hidden units (contract 4.4): block sums sp / ss live over two iterations of the inner loop
 #pragma unroll 1
-        for (int jq = 0; jq < HID / 4; ++jq) {
+        for (int g = 0; g < HID / 8; ++g) {
+        float2 sp[ACT];
+        float ss[NS > 0 ? NS : 1][ACT];
+#pragma unroll
+        for (int m = 0; m < ACT; ++m) {
+            sp[m] = make_float2(0.0f, 0.0f);
+#pragma unroll
+            for (int i = 0; i < NS; ++i) ss[i][m] = 0.0f;
+        }
+#pragma unroll 1
+        for (int jq = 2 * g; jq < 2 * g + 2; ++jq) {
             // 4 hidden units = OBS consecutive quads of W1
             float wr[4 * OBS];
 #pragma unroll
@@ -192,7 +204,7 @@ struct SpreadEnv {
                 // the skipped comm inputs are exactly 0: fmaf(w, 0, a) == a
                 const float2 h = tanh32x2<false>(a);
 #pragma unroll
-                for (int m = 0; m < ACT; ++m) zp[m] = __ffma2_rn(make_float2(w2[m][u], w2[m][u]), h, zp[m]);
+                for (int m = 0; m < ACT; ++m) sp[m] = __ffma2_rn(make_float2(w2[m][u], w2[m][u]), h, sp[m]);
 #pragma unroll
                 for (int i = 0; i < NS; ++i) {
                     float as = bias[u];
@@ -200,9 +212,16 @@ struct SpreadEnv {
                     for (int k = 0; k < OBS_EFF; ++k) as = fmaf(wr[u * OBS + k], o[2 + i][k], as);
                     const float hs = tanh32_fast_t<false>(as);
 #pragma unroll
-                    for (int m = 0; m < ACT; ++m) zs[i][m] = fmaf(w2[m][u], hs, zs[i][m]);
+                    for (int m = 0; m < ACT; ++m) ss[i][m] = fmaf(w2[m][u], hs, ss[i][m]);
                 }
             }
+        }
+#pragma unroll
+        for (int m = 0; m < ACT; ++m) {
+            zp[m] = __fadd2_rn(zp[m], sp[m]);
+#pragma unroll
+            for (int i = 0; i < NS; ++i) zs[i][m] = __fadd_rn(zs[i][m], ss[i][m]);
+        }
         }
         float z[N][ACT];
 #pragma unroll

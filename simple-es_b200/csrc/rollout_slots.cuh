@@ -62,6 +62,9 @@ struct RolloutParams {
     int n_agents;                // simple_spread only
     int n_peers;                 // fused fitness exchange: other ranks' exchange buffers (NVLink peer memory)
     double *peer_fitness[MAX_PEERS];
+    int split_ok;                // Envs with step_split(): a warp left with few episodes and nothing to refill spreads each over 2 / 4 lanes
+    int strict_tail;             // > 0: once fewer than this many offspring are left in the queue, a warp takes a new offspring
+                                 // only if ALL its E episodes get a lane at once (see the scheduler)
 };
 
 constexpr int MAX_E = 32;
@@ -101,6 +104,67 @@ struct __align__(16) SlotSmem<Env, S, true> {
     int steps[S];
 };
 
+template <class Env, class = void> struct EnvSplit { static constexpr bool value = false; };
+template <class Env> struct EnvSplit<Env, decltype((void)Env::SPLIT)> { static constexpr bool value = Env::SPLIT; };
+
+// Straggler phase of the slot kernel (Envs that provide step_split<K, S>()): the warp's queue is empty and it holds at most
+// 32 / K running episodes, so every further warp-step would cost a full step's latency for a handful of lanes.  The running
+// episodes are compacted -- episode g moves to lanes [K g, K g + K) with its state replicated -- and stepped by K lanes each
+// until they end, or until so few are left that twice as many lanes per episode fit (K = 2 -> 4).  A finished episode is
+// booked into its slot (steps, ep_done) exactly as the throughput loop does; the caller retires the slots afterwards.
+template <class Env, int S, int K, class Smem>
+__device__ __forceinline__ void run_split(Smem &sm, int pomdp, int max_step, int lane, bool &active, int &slot, int &nstep, double &x,
+                                          double &xd, double &th, double &thd)
+{
+    static_assert(Env::UNIT_REWARD && Env::N_AGENTS == 1, "run_split: CartPole-like envs");
+    const unsigned FULL = 0xffffffffu;
+    const unsigned act_mask = __ballot_sync(FULL, active);
+    const int n_act = __popc(act_mask);
+    const int g = lane / K;
+    const int src = g < n_act ? __fns(act_mask, 0, g + 1) : lane;         // lane that holds the g-th running episode
+    x = __shfl_sync(FULL, x, src); xd = __shfl_sync(FULL, xd, src);
+    th = __shfl_sync(FULL, th, src); thd = __shfl_sync(FULL, thd, src);
+    slot = __shfl_sync(FULL, slot, src); nstep = __shfl_sync(FULL, nstep, src);
+    active = g < n_act;
+    if (!active) slot = 0;                                                // idle groups step a dummy episode (result unused)
+    constexpr int RESPLIT = K < 4 ? 32 / (2 * K) : 0;
+    for (;;) {
+        const int n = __popc(__ballot_sync(FULL, active)) / K;
+        if (n == 0 || n <= RESPLIT) break;
+        int action;
+        bool done = Env::template step_split<K, S>(x, xd, th, thd, sm.w, slot, pomdp, lane, action);
+        if (active) {
+            ++nstep;
+            if (nstep >= max_step) done = true;
+            if (done) {
+                if ((lane & (K - 1)) == 0) {
+                    atomicAdd(&sm.steps[slot], nstep);
+                    atomicAdd(&sm.ep_done[slot], 1);
+                }
+                active = false;
+                slot = 0;
+            }
+        }
+    }
+    active = active && (lane & (K - 1)) == 0;                             // the leader lane keeps the episode
+    __syncwarp();
+}
+
+// Kept out of line (and fed scalars only) so that the throughput loop of k_rollout_slots keeps the register allocation and
+// instruction schedule it has without this phase: the loop is bound by register-operand delivery, and its speed moved by
+// 4-5 % with the allocation ptxas happened to choose when this code was inlined after it (profiles/r02_k1_experiments.md).
+template <class Env, int S, class Smem>
+__device__ __noinline__ void split_phase(Smem *smp, int pomdp, int max_step, int slot, int nstep, double x, double xd, double th, double thd)
+{
+    Smem &sm = *smp;
+    const int lane = threadIdx.x & 31;
+    bool active = slot >= 0;
+    if (__popc(__ballot_sync(0xffffffffu, active)) > 8)
+        run_split<Env, S, 2>(sm, pomdp, max_step, lane, active, slot, nstep, x, xd, th, thd);      // returns when <= 8 are left
+    if (__ballot_sync(0xffffffffu, active))
+        run_split<Env, S, 4>(sm, pomdp, max_step, lane, active, slot, nstep, x, xd, th, thd);      // runs them to their end
+}
+
 template <class Env, int S, int WARPS, bool TRACE>
 __global__ void __launch_bounds__(WARPS * 32) k_rollout_slots(const RolloutParams p)
 {
@@ -123,6 +187,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_rollout_slots(const RolloutParam
     unsigned long long warp_steps = 0;   // lanes < S: steps of the offspring they retired
     bool more = true;          // warp-uniform: the global offspring queue may still hold work
     bool sched = true;         // warp-uniform: something changed that the scheduler must look at
+    [[maybe_unused]] bool to_split = false;
 
     for (;;) {
         if (sched) {
@@ -154,8 +219,21 @@ __global__ void __launch_bounds__(WARPS * 32) k_rollout_slots(const RolloutParam
             for (int o = 16; o; o >>= 1) pending += __shfl_xor_sync(FULL, pending, o);
             const unsigned idle_mask = __ballot_sync(FULL, usable && slot < 0);
             const int n_idle = __popc(idle_mask);
-            // demand-driven refill: just enough new offspring to occupy the idle lanes
+            // demand-driven refill: just enough new offspring to occupy the idle lanes.  When lanes_used is not a multiple
+            // of E (32 lanes, E = 5) the last offspring taken is split over two rounds of the warp, which keeps every lane
+            // busy -- except at the end of the queue, where the left-over episodes would cost each warp one more, nearly
+            // empty, round: there (fewer than strict_tail offspring left) an offspring is taken only if it fits entirely.
             int want = (n_idle - pending + p.E - 1) / p.E;
+            if (p.strict_tail > 0 && more && want > 0) {
+                int taken = 0;                                     // one lane reads: the value must be warp-uniform
+                if (lane == 0) taken = *reinterpret_cast<volatile int *>(p.work_counter);
+                taken = __shfl_sync(FULL, taken, 0);
+                if (p.shard.n_local - taken <= p.strict_tail) {
+                    const int whole = (n_idle - pending) / p.E;
+                    // (a warp with fewer lanes than E, nothing running and nothing pending must still take one)
+                    if (whole > 0 || pending > 0 || __ballot_sync(FULL, slot >= 0) != 0) want = whole;
+                }
+            }
             want = min(max(want, 0), __popc(empty_mask));
             if (want > 0 && more) {
                 int base = 0;
@@ -218,7 +296,13 @@ __global__ void __launch_bounds__(WARPS * 32) k_rollout_slots(const RolloutParam
                 Env::init(st, p, sm.off_id[my_slot], my_ep);
                 Env::template bind<S>(st, sm.w, my_slot);
             }
-            if (__ballot_sync(FULL, slot >= 0) == 0) break;        // queue empty and every lane idle
+            const unsigned act_mask = __ballot_sync(FULL, slot >= 0);
+            if (act_mask == 0) break;                              // queue empty and every lane idle
+            if constexpr (EnvSplit<Env>::value && !TRACE) {
+                // nothing left to hand out (queue empty, every pending pair has a lane) and few episodes running: leave the
+                // throughput loop for the straggler phase below
+                if (p.split_ok && !more && acc <= n_idle && __popc(act_mask) <= 16) { to_split = true; break; }
+            }
         }
 
         bool just_done = false;
@@ -247,6 +331,24 @@ __global__ void __launch_bounds__(WARPS * 32) k_rollout_slots(const RolloutParam
         // the scheduler has work only right after an episode ended (a lane to re-arm, maybe a slot
         // to retire and refill); otherwise idle lanes stay idle and the warp keeps stepping
         sched = __ballot_sync(FULL, just_done) != 0;
+    }
+    if constexpr (EnvSplit<Env>::value && !TRACE) {
+        // ------------------------------------------------------------------ straggler phase (kept out of the loop above so
+        // that its code does not touch the throughput loop's register allocation and schedule)
+        if (to_split) {
+            split_phase<Env, S, Smem>(&sm, p.pomdp, p.max_step, slot, nstep, st.x, st.xd, st.th, st.thd);
+            __syncwarp();
+            if (lane < S) {                                        // retire every slot the warp still holds
+                const int my_id = sm.off_id[lane];
+                if (my_id >= 0) {
+                    const int stp = sm.steps[lane];
+                    p.steps[my_id] = (long long)stp;
+                    warp_steps += (unsigned long long)stp;
+                    publish_fitness(p, my_id, __ddiv_rn((double)stp, (double)p.E));
+                    sm.off_id[lane] = -1;
+                }
+            }
+        }
     }
     if (p.total_steps) {
 #pragma unroll

@@ -91,6 +91,7 @@ struct ses_handle {
     int ctas_per_sm = 0;
     int k1_variant = 7;
     int spread_slots8 = 0;
+    int k1_split = 1;
 
     int64_t launches = 0;
 };
@@ -169,6 +170,7 @@ extern "C" int ses_create(const ses_config *cfg, ses_handle **out)
     h->ctas_per_sm = env_int("SES_ROLLOUT_CTAS_PER_SM", 0);
     h->k1_variant = env_int("SES_K1_VARIANT", 7);
     h->spread_slots8 = env_int("SES_SPREAD_SLOTS8", 0);
+    h->k1_split = env_int("SES_K1_SPLIT", 1);
     h->k2_fused = env_int("SES_K2_FUSED", 1);     // 1 + passes launches (default); 0: the separate kernels
     if (h->k1_variant < 0 || h->k1_variant > 7) h->k1_variant = 7;
 
@@ -230,6 +232,35 @@ static int launch_slots(ses_handle *h, RolloutParams &rp, int need_warps, bool t
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, WARPS * 32, smem));
     if (per_sm < 1) return fail("rollout kernel does not fit on an SM (smem %zu B)", smem);
     if (h->ctas_per_sm > 0 && h->ctas_per_sm < per_sm) per_sm = h->ctas_per_sm;
+    const int resident_warps = per_sm * h->num_sms * WARPS;
+    // lanes of a warp that take episodes.  E * floor(32 / E) (30 for E = 5) lets slots start and finish together; all 32
+    // with the last offspring of a refill carried into the warp's next round (and a strict end of the queue) holds more
+    // episodes per round.  Episodes of a launch run in rounds of resident_warps * lanes; a converged population (equal
+    // episode lengths) pays for every started round, so take 32 lanes exactly when that saves a round
+    // (profiles/r02_k1_rounds.jsonl: 0.76 ms per 500-step round of 3 warps per sub-partition, whatever the lanes).
+    const int E = h->cfg.eval_ep_num;
+    const long long n_ep = (long long)h->shard.n_local * E;
+    const int lanes_even = E >= 32 ? 32 : E * (32 / E);
+    int lanes = lanes_even;
+    if (h->lanes_used_override > 0) {
+        lanes = h->lanes_used_override < 32 ? h->lanes_used_override : 32;
+    } else if (lanes_even < 32 && Env::LANES32_OK && SL >= (32 + E - 1) / E + 1) {
+        const long long cap_even = (long long)resident_warps * lanes_even;
+        const long long rounds_even = (n_ep + cap_even - 1) / cap_even;
+        // 32 lanes: a warp's rounds hold 32 episodes each (the refill takes ceil((32 - pending) / E) offspring and carries the
+        // rest), its last, strict, round `pending` + whole offspring only
+        long long rounds_32 = rounds_even;
+        for (long long R = 1; R < rounds_even; ++R) {
+            long long pend = 0, held = 0;
+            for (long long r = 1; r < R; ++r) { const long long nw = (32 - pend + E - 1) / E; held += 32; pend += nw * E - 32; }
+            held += pend + ((32 - pend) / E) * E;
+            if (held * resident_warps >= n_ep) { rounds_32 = R; break; }
+        }
+        if (rounds_32 < rounds_even) lanes = 32;
+    }
+    rp.lanes_used = lanes;
+    rp.strict_tail = (lanes > E && lanes % E) ? resident_warps * ((32 + E - 1) / E) : 0;
+    need_warps = (int)((n_ep + lanes - 1) / lanes);
     int grid = per_sm * h->num_sms;
     const int need = (need_warps + WARPS - 1) / WARPS;
     if (grid > need) grid = need;
@@ -287,13 +318,11 @@ extern "C" int ses_rollout(ses_handle *h, uint32_t generation, float sigma, cons
         h->last_rollout_fitness = rp.n_peers > 0 ? fitness_dev : nullptr;
     }
 
-    // lanes of a warp that take episodes: a multiple of E so that slots start and finish together
+    // lanes per warp and the grid are chosen per kernel in launch_slots(); the GRU kernel maps a warp to one offspring
     rp.lanes_used = c.eval_ep_num >= 32 ? 32 : c.eval_ep_num * (32 / c.eval_ep_num);
-    if (h->lanes_used_override > 0) rp.lanes_used = h->lanes_used_override < 32 ? h->lanes_used_override : 32;
-
-    // as few warps as give every episode a lane at once; all resident warps when there is more work than that
-    const long long n_episodes = (long long)n_local * c.eval_ep_num;
-    const int need_warps = (int)((n_episodes + rp.lanes_used - 1) / rp.lanes_used);
+    rp.strict_tail = 0;
+    rp.split_ok = h->k1_split;
+    const int need_warps = 0;
     const bool tr = n_trace > 0;
     if (c.env == SES_ENV_CARTPOLE && !c.gru) {
         // slots per warp: enough offspring to occupy 32 lanes (E >= 4: 8, E in {2,3}: 16, E = 1: 32)

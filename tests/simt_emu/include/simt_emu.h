@@ -31,6 +31,7 @@
 #define __device__
 #define __global__
 #define __forceinline__ inline
+#define __noinline__ __attribute__((noinline))
 #define __launch_bounds__(...)
 #define __shared__ static thread_local
 #define __constant__ static const
