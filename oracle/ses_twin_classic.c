@@ -6,6 +6,11 @@
  * name straight to gym.make) with the discrete-action policy head (networks/neural_network.py:29-31):
  *   env 2  MountainCar-v0   obs 2, 3 actions, reward -1 per step, TimeLimit 200
  *   env 3  Acrobot-v1       obs 6, 3 actions, reward -1 per step (0 on the terminal step), TimeLimit 500
+ * and, with the continuous-action head (`discrete_action: False`, networks/neural_network.py:32-33: tanh of fc2):
+ *   env 4  Pendulum-v0      obs 3, 1 action in (-1, 1) used as the torque, reward -(th_norm^2 + .1 thdot^2 + .001 u^2),
+ *                           never terminates, TimeLimit 200
+ * Each of them also with the recurrent policy (`gru: True`): the hidden state is reset per episode
+ * (loop.py:114-116 -> GymEnvModel.reset, neural_network.py:38-40).
  *
  * Restates (citations relative to /root/reference):
  *   - GymWrapper.reset/step, max_step truncation                 envs/gym_wrapper.py:23-45
@@ -33,12 +38,14 @@
 
 #define ENV_MOUNTAINCAR 2
 #define ENV_ACROBOT 3
+#define ENV_PENDULUM 4       /* continuous action: the policy's tanh head (networks/neural_network.py:32-33) */
 
 /* from ses_twin.c */
 void tw_philox(const uint32_t *ctr, const uint32_t *key, uint32_t *out);
 int tw_param_count(int obs, int act, int gru);
 void tw_perturb(const float *parent, int D, float sigma, uint32_t seed, uint32_t gen, uint32_t id, int perturbed, float *w);
 int tw_policy_step(const float *w, int obs, int act, int gru, const float *o, float *h, float *logits);
+void tw_tanhf_v(const float *x, float *y, int64_t n);
 
 /* ------------------------------------------------------------------------------------ */
 /* float64 sin / cos, full range (|x| * 2/pi must fit an int32; here |x| < 100)           */
@@ -178,9 +185,40 @@ static int acrobot_step(double st[4], int action, double *reward)
 /* ------------------------------------------------------------------------------------ */
 /* generic dispatch                                                                        */
 /* ------------------------------------------------------------------------------------ */
+/* ------------------------------------------------------------------------------------ */
+/* Pendulum-v0 (gym classic_control/pendulum.py, gym ~0.18): max_speed 8, max_torque 2, dt .05, g 10, m = l = 1.  */
+/* The action is the float32 tanh output of the policy widened to double (|u| < 1 < max_torque: the clip is the    */
+/* identity); Python's float % is fmod with the divisor's sign, exact.                                             */
+/* ------------------------------------------------------------------------------------ */
+#define PEND_PI 3.141592653589793
+static double pend_angle_normalize(double x)
+{
+    double m = fmod(x + PEND_PI, 2.0 * PEND_PI);              /* ((x + pi) % (2 pi)) - pi */
+    if (m < 0.0) m = m + 2.0 * PEND_PI;
+    return m - PEND_PI;
+}
+
+static int pendulum_step(double st[2], double u, double *reward)
+{
+    const double th = st[0], thdot = st[1];
+    u = clipd(u, -2.0, 2.0);
+    const double an = pend_angle_normalize(th);
+    const double costs = an * an + 0.1 * (thdot * thdot) + 0.001 * (u * u);
+    /* newthdot = thdot + (-3 g / (2 l) * sin(th + pi) + 3. / (m l^2) * u) * dt:  -3*10/(2*1) = -15.0, 3./(1*1) = 3.0 */
+    double newthdot = thdot + (-15.0 * tw_sin_full(th + PEND_PI) + 3.0 * u) * 0.05;
+    const double newth = th + newthdot * 0.05;
+    newthdot = clipd(newthdot, -8.0, 8.0);
+    st[0] = newth; st[1] = newthdot;
+    *reward = -costs;
+    return 0;
+}
+
+TW_EXPORT int tw_classic_continuous(int env) { return env == ENV_PENDULUM; }
+
 TW_EXPORT int tw_classic_dims(int env, int *obs, int *act, int *state_dim, int *time_limit)
 {
     switch (env) {
+    case ENV_PENDULUM: *obs = 3; *act = 1; *state_dim = 2; *time_limit = 200; return 0;
     case ENV_MOUNTAINCAR: *obs = 2; *act = 3; *state_dim = 2; *time_limit = 200; return 0;
     case ENV_ACROBOT: *obs = 6; *act = 3; *state_dim = 4; *time_limit = 500; return 0;
     default: return -1;
@@ -192,10 +230,20 @@ TW_EXPORT int tw_classic_step(int env, double *st, int action, double *reward)
     return env == ENV_MOUNTAINCAR ? mountaincar_step(st, action, reward) : acrobot_step(st, action, reward);
 }
 
+TW_EXPORT int tw_classic_step_continuous(int env, double *st, double u, double *reward)
+{
+    (void)env;
+    return pendulum_step(st, u, reward);
+}
+
 static void classic_obs(int env, const double *st, float *o)
 {
     if (env == ENV_MOUNTAINCAR) {
         o[0] = (float)st[0]; o[1] = (float)st[1];
+    } else if (env == ENV_PENDULUM) {
+        double sn, cs;
+        tw_sincos_full(st[0], &sn, &cs);
+        o[0] = (float)cs; o[1] = (float)sn; o[2] = (float)st[1];                 /* [cos th, sin th, thdot] */
     } else {
         double s0, c0, s1, c1;
         tw_sincos_full(st[0], &s0, &c0);
@@ -218,6 +266,10 @@ TW_EXPORT void tw_classic_init(int env, uint32_t seed, int init_mode, uint32_t g
         double u = ((double)r[0] + 0.5) * 2.3283064365386963e-10;
         st[0] = u * 0.2 - 0.6;
         st[1] = 0.0;
+    } else if (env == ENV_PENDULUM) {                              /* uniform(-[pi, 1], [pi, 1]) */
+        double u0 = ((double)r[0] + 0.5) * 2.3283064365386963e-10, u1 = ((double)r[1] + 0.5) * 2.3283064365386963e-10;
+        st[0] = u0 * (2.0 * PEND_PI) - PEND_PI;
+        st[1] = u1 * 2.0 - 1.0;
     } else {
         for (int k = 0; k < 4; ++k) {
             double u = ((double)r[k] + 0.5) * 2.3283064365386963e-10;
@@ -225,6 +277,10 @@ TW_EXPORT void tw_classic_init(int env, uint32_t seed, int init_mode, uint32_t g
         }
     }
 }
+
+TW_EXPORT double tw_rollout_classic_gru(int env, int gru, const float *w, int E, int max_step, const double *init, uint32_t seed,
+                                        int init_mode, uint32_t gen, uint32_t id, double *trace, int32_t *actions,
+                                        int trace_steps, int64_t *steps_out);
 
 /* One offspring: E episodes (loop.py:111-125).  Returns fitness = (sum over episodes, in episode order, of the
  * sequential float64 sum of the episode's rewards) / E.
@@ -234,22 +290,41 @@ TW_EXPORT double tw_rollout_classic(int env, const float *w, int E, int max_step
                                     int init_mode, uint32_t gen, uint32_t id, double *trace, int32_t *actions,
                                     int trace_steps, int64_t *steps_out)
 {
+    return tw_rollout_classic_gru(env, 0, w, E, max_step, init, seed, init_mode, gen, id, trace, actions, trace_steps, steps_out);
+}
+
+/* The same with the policy kind as a parameter: gru = 1 runs GymEnvModel's recurrent branch, hidden state zeroed at the start
+ * of every episode.  Continuous envs: `actions` receives the float32 action's bit pattern. */
+TW_EXPORT double tw_rollout_classic_gru(int env, int gru, const float *w, int E, int max_step, const double *init, uint32_t seed,
+                                        int init_mode, uint32_t gen, uint32_t id, double *trace, int32_t *actions,
+                                        int trace_steps, int64_t *steps_out)
+{
     int obs, act, sd, cap;
     if (tw_classic_dims(env, &obs, &act, &sd, &cap)) return NAN;
+    const int continuous = tw_classic_continuous(env);
     double total = 0.0;
     int64_t nsteps = 0;
     for (int e = 0; e < E; ++e) {
         double st[4];
+        float h[HID];
+        memset(h, 0, sizeof(h));                                   /* model.reset() (loop.py:114-116) */
         if (init) memcpy(st, init + (size_t)sd * e, sizeof(double) * (size_t)sd);
         else tw_classic_init(env, seed, init_mode, gen, id, (uint32_t)e, st);
         double R = 0.0;
         int step = 0, done = 0;
         while (!done) {
-            float o[8];
+            float o[8], logits[16];
             classic_obs(env, st, o);
-            int a = tw_policy_step(w, obs, act, 0, o, NULL, NULL);
+            int a = tw_policy_step(w, obs, act, gru, o, h, logits);
             double r;
-            done = tw_classic_step(env, st, a, &r);
+            if (continuous) {
+                float u;                                           /* tanh head (neural_network.py:32-33), float32 */
+                tw_tanhf_v(logits, &u, 1);
+                memcpy(&a, &u, 4);
+                done = tw_classic_step_continuous(env, st, (double)u, &r);
+            } else {
+                done = tw_classic_step(env, st, a, &r);
+            }
             R = R + r;                                             /* loop.py:120-122 */
             ++step;                                                /* gym_wrapper.py:33 */
             if (step >= max_step) done = 1;                        /* gym_wrapper.py:37-39 / TimeLimit */
@@ -269,6 +344,7 @@ typedef struct {
     int env; const float *parents; float sigma; uint32_t seed, gen; int group, n_head, id0, n, E, max_step;
     const float *W_override; const double *init; int init_mode; double *fitness; int64_t *steps; int D;
     atomic_int next;
+    int gru;
 } classic_job;
 
 static void *classic_worker(void *arg)
@@ -283,26 +359,34 @@ static void *classic_worker(void *arg)
             if (jb->W_override) memcpy(w, jb->W_override + (size_t)j * jb->D, sizeof(float) * (size_t)jb->D);
             else tw_perturb(jb->parents + (size_t)(id / jb->group) * jb->D, jb->D, jb->sigma, jb->seed, jb->gen, (uint32_t)id,
                             (id % jb->group) - jb->n_head + 1, w);
-            jb->fitness[j] = tw_rollout_classic(jb->env, w, jb->E, jb->max_step, jb->init, jb->seed, jb->init_mode, jb->gen,
-                                                (uint32_t)id, NULL, NULL, 0, &jb->steps[j]);
+            jb->fitness[j] = tw_rollout_classic_gru(jb->env, jb->gru, w, jb->E, jb->max_step, jb->init, jb->seed, jb->init_mode, jb->gen,
+                                                    (uint32_t)id, NULL, NULL, 0, &jb->steps[j]);
         }
     }
     free(w);
     return NULL;
 }
 
-TW_EXPORT void tw_population_classic(int env, const float *parents, float sigma, uint32_t seed, uint32_t gen, int group,
-                                     int n_head, int id0, int n, int E, int max_step, const float *W_override,
-                                     const double *init, int init_mode, double *fitness, int64_t *steps, int nthreads)
+TW_EXPORT void tw_population_classic_gru(int env, int gru, const float *parents, float sigma, uint32_t seed, uint32_t gen, int group,
+                                         int n_head, int id0, int n, int E, int max_step, const float *W_override,
+                                         const double *init, int init_mode, double *fitness, int64_t *steps, int nthreads)
 {
     int obs, act, sd, cap;
     if (tw_classic_dims(env, &obs, &act, &sd, &cap)) return;
     classic_job jb = { env, parents, sigma, seed, gen, group, n_head, id0, n, E, max_step, W_override, init, init_mode,
-                       fitness, steps, tw_param_count(obs, act, 0), 0 };
+                       fitness, steps, tw_param_count(obs, act, gru), 0, gru };
     if (nthreads < 1) nthreads = 1;
     if (nthreads > 256) nthreads = 256;
     pthread_t th[256];
     for (int t = 1; t < nthreads; ++t) pthread_create(&th[t], NULL, classic_worker, &jb);
     classic_worker(&jb);
     for (int t = 1; t < nthreads; ++t) pthread_join(th[t], NULL);
+}
+
+TW_EXPORT void tw_population_classic(int env, const float *parents, float sigma, uint32_t seed, uint32_t gen, int group,
+                                     int n_head, int id0, int n, int E, int max_step, const float *W_override,
+                                     const double *init, int init_mode, double *fitness, int64_t *steps, int nthreads)
+{
+    tw_population_classic_gru(env, 0, parents, sigma, seed, gen, group, n_head, id0, n, E, max_step, W_override, init, init_mode,
+                              fitness, steps, nthreads);
 }

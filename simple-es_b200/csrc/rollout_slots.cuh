@@ -62,6 +62,8 @@ struct RolloutParams {
     int n_agents;                // simple_spread only
     int n_peers;                 // fused fitness exchange: other ranks' exchange buffers (NVLink peer memory)
     double *peer_fitness[MAX_PEERS];
+    int sparse_rank;             // >= 0: warps of the CTAs that arrive on their SM as number sparse_rank or later take at most
+    int sparse_quota;            //       sparse_quota offspring in total ("fractional" warps of a launch that does not fill the SMs)
     int split_ok;                // Envs with step_split(): a warp left with few episodes and nothing to refill spreads each over 2 / 4 lanes
     int strict_tail;             // > 0: once fewer than this many offspring are left in the queue, a warp takes a new offspring
                                  // only if ALL its E episodes get a lane at once (see the scheduler)
@@ -127,12 +129,14 @@ __device__ __forceinline__ void run_split(Smem &sm, int pomdp, int max_step, int
     slot = __shfl_sync(FULL, slot, src); nstep = __shfl_sync(FULL, nstep, src);
     active = g < n_act;
     if (!active) slot = 0;                                                // idle groups step a dummy episode (result unused)
+    typename Env::template SplitW<K> wr;
+    Env::template split_load<K, S>(wr, sm.w, slot, lane);
     constexpr int RESPLIT = K < 4 ? 32 / (2 * K) : 0;
     for (;;) {
         const int n = __popc(__ballot_sync(FULL, active)) / K;
         if (n == 0 || n <= RESPLIT) break;
         int action;
-        bool done = Env::template step_split<K, S>(x, xd, th, thd, sm.w, slot, pomdp, lane, action);
+        bool done = Env::template step_split<K>(x, xd, th, thd, wr, pomdp, lane, action);
         if (active) {
             ++nstep;
             if (nstep >= max_step) done = true;
@@ -179,6 +183,22 @@ __global__ void __launch_bounds__(WARPS * 32) k_rollout_slots(const RolloutParam
 
     if (lane < S) { sm.off_id[lane] = -1; sm.ep_next[lane] = 0; sm.ep_done[lane] = 0; sm.steps[lane] = 0; }
     __syncwarp();
+    // Sparse warps.  A launch whose episodes do not fill every resident warp (one rank's share of an 8-GPU run: 2.3 warps
+    // per SM sub-partition) would leave some sub-partitions with three full warps and others with two; the former set the
+    // time.  Instead every SM gets the same CTAs: those that arrive first take full loads, the CTA that arrives as number
+    // sparse_rank shares what is left -- a few episodes per warp, which the straggler phase then runs on 2 or 4 lanes each,
+    // at a fraction of a full warp's cost per step.  work_counter[1 + smid] counts the CTAs arriving on an SM.
+    int quota = 0x7fffffff;
+    if (p.sparse_rank >= 0) {
+        __shared__ int cta_rank_s;
+        if (threadIdx.x == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            cta_rank_s = atomicAdd(p.work_counter + 1 + (smid & 255u), 1);
+        }
+        __syncthreads();
+        if (cta_rank_s >= p.sparse_rank) quota = p.sparse_quota;
+    }
 
     // per-lane episode state
     int slot = -1, nstep = 0;
@@ -234,13 +254,15 @@ __global__ void __launch_bounds__(WARPS * 32) k_rollout_slots(const RolloutParam
                     if (whole > 0 || pending > 0 || __ballot_sync(FULL, slot >= 0) != 0) want = whole;
                 }
             }
-            want = min(max(want, 0), __popc(empty_mask));
+            want = min(min(max(want, 0), __popc(empty_mask)), quota);
+            if (quota == 0) more = false;                          // a sparse warp that has taken its share
             if (want > 0 && more) {
                 int base = 0;
                 if (lane == 0) base = atomicAdd(p.work_counter, want);
                 base = __shfl_sync(FULL, base, 0);                 // local index of the first new offspring
                 if (base + want >= p.shard.n_local) more = false;
                 const int got = max(0, min(want, p.shard.n_local - base));
+                if (quota != 0x7fffffff) { quota -= want; if (quota == 0) more = false; }
                 const int my_rank = __popc(empty_mask & lt);       // rank of this lane's slot among the empty ones
                 const bool fill = ((empty_mask >> lane) & 1u) && my_rank < got;
                 if (fill) {

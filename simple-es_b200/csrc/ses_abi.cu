@@ -92,9 +92,12 @@ struct ses_handle {
     int k1_variant = 7;
     int spread_slots8 = 0;
     int k1_split = 1;
+    int k1_sparse = 1;
 
     int64_t launches = 0;
 };
+
+constexpr int WORK_COUNTER_INTS = 1 + 256;    // [0] the offspring queue, [1 + smid] CTAs that have arrived on an SM (sparse warps)
 
 static cudaStream_t S(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -171,6 +174,7 @@ extern "C" int ses_create(const ses_config *cfg, ses_handle **out)
     h->k1_variant = env_int("SES_K1_VARIANT", 7);
     h->spread_slots8 = env_int("SES_SPREAD_SLOTS8", 0);
     h->k1_split = env_int("SES_K1_SPLIT", 1);
+    h->k1_sparse = env_int("SES_K1_SPARSE", 1);
     h->k2_fused = env_int("SES_K2_FUSED", 1);     // 1 + passes launches (default); 0: the separate kernels
     if (h->k1_variant < 0 || h->k1_variant > 7) h->k1_variant = 7;
 
@@ -178,7 +182,7 @@ extern "C" int ses_create(const ses_config *cfg, ses_handle **out)
     h->n_tiles = (P + sort_tile(SORT_ITEMS_SMALL) - 1) / sort_tile(SORT_ITEMS_SMALL);
     h->nb0 = (P + GB0 - 1) / GB0;
     h->nb1 = (h->nb0 + GB1 - 1) / GB1;
-    CU(cudaMalloc(&h->work_counter, sizeof(int)));
+    CU(cudaMalloc(&h->work_counter, sizeof(int) * WORK_COUNTER_INTS));
     CU(cudaMalloc(&h->keys[0], sizeof(unsigned long long) * P));
     CU(cudaMalloc(&h->keys[1], sizeof(unsigned long long) * P));
     CU(cudaMalloc(&h->vals_scratch, sizeof(int) * P));
@@ -265,6 +269,27 @@ static int launch_slots(ses_handle *h, RolloutParams &rp, int need_warps, bool t
     const int need = (need_warps + WARPS - 1) / WARPS;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
+    // A launch that does not fill the SMs (need < resident CTAs): give every SM the same CTAs -- `full` CTAs with full warps
+    // plus one whose warps share the rest, a few episodes each, which the straggler phase runs on 2 / 4 lanes per episode
+    // (see the kernel).  Only where the sparse warps end up with at most 16 episodes, i.e. where they can split.
+    if constexpr (EnvSplit<Env>::value) {
+        const int per_warp = lanes / E;                                   // offspring of a full warp
+        const int full = need / h->num_sms;                               // full CTAs per SM
+        const long long rest = (long long)h->shard.n_local - (long long)full * h->num_sms * WARPS * per_warp;
+        if (h->k1_sparse && h->k1_split && !trace && lanes % E == 0 && need < per_sm * h->num_sms && full >= 1 && full < per_sm && rest > 0) {
+            const int quota = (int)((rest + (long long)h->num_sms * WARPS - 1) / ((long long)h->num_sms * WARPS));
+            if (quota * E <= 16) {
+                rp.sparse_rank = full;
+                rp.sparse_quota = quota;
+                grid = (full + 1) * h->num_sms;
+            }
+        }
+        if (env_int("SES_K1_SPARSE_QUOTA", 0) > 0) {                      // experiments: force the sparse class and its share
+            rp.sparse_rank = env_int("SES_K1_SPARSE_RANK", 0);
+            rp.sparse_quota = env_int("SES_K1_SPARSE_QUOTA", 0);
+            grid = (h->ctas_per_sm > 0 ? h->ctas_per_sm : per_sm) * h->num_sms;
+        }
+    }
     kernel<<<grid, WARPS * 32, smem, st>>>(rp);
     CU(cudaGetLastError());
     h->launches += 1;
@@ -295,7 +320,7 @@ extern "C" int ses_rollout(ses_handle *h, uint32_t generation, float sigma, cons
     if (n_trace > n_local) n_trace = n_local;
     CU(cudaSetDevice(c.device));
     cudaStream_t st = S(stream);
-    CU(cudaMemsetAsync(h->work_counter, 0, sizeof(int), st));
+    CU(cudaMemsetAsync(h->work_counter, 0, sizeof(int) * WORK_COUNTER_INTS, st));
 
     RolloutParams rp;
     rp.parents = parents_dev; rp.w_override = w_override_dev; rp.init_states = init_states_dev;
@@ -322,6 +347,7 @@ extern "C" int ses_rollout(ses_handle *h, uint32_t generation, float sigma, cons
     rp.lanes_used = c.eval_ep_num >= 32 ? 32 : c.eval_ep_num * (32 / c.eval_ep_num);
     rp.strict_tail = 0;
     rp.split_ok = h->k1_split;
+    rp.sparse_rank = -1; rp.sparse_quota = 0;
     const int need_warps = 0;
     const bool tr = n_trace > 0;
     if (c.env == SES_ENV_CARTPOLE && !c.gru) {

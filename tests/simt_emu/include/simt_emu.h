@@ -281,6 +281,13 @@ inline float min_xorsign_abs(float a, float b)
     return (signbit(a) != signbit(b)) ? -m : m;
 }
 inline unsigned lanemask_lt() { return (1u << g_cur->lane) - 1u; }
+// %smid stand-in: blocks are dealt round robin over the emulated SMs (SES_SIMT_EMU_SMS, default 2)
+inline unsigned smid()
+{
+    const char *v = getenv("SES_SIMT_EMU_SMS");
+    const unsigned n = v && *v ? (unsigned)atoi(v) : 2u;
+    return g_blockIdx.x % (n ? n : 1u);
+}
 
 }  // namespace simt
 

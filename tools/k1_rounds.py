@@ -30,15 +30,20 @@ def run_point(P, lanes, ctas, variant, E, regime, reps, extra_env=None):
     mu = torch.from_numpy(np.zeros((1, D), np.float32) if regime == "gen0" else balancing_parent()).cuda()
     sigma = 2.0 if regime == "gen0" else 0.05
     fit = torch.zeros(P, dtype=torch.float64, device="cuda"); steps = torch.zeros(P, dtype=torch.int64, device="cuda")
-    for g in range(2):
+    # keep the GPU busy (and its clocks up) before and during the measurement: back-to-back launches, one event pair around all
+    busy = max(3, int(30.0 / max(0.3, P * E * 1e-5)))            # ~30 ms of warm-up launches
+    for g in range(busy):
         eng.rollout(g, sigma, mu, fitness=fit, steps=steps)
-    torch.cuda.synchronize()
     ts = []
-    for g in range(reps):
+    for r in range(reps):
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record(); eng.rollout(10 + g, sigma, mu, fitness=fit, steps=steps); e1.record()
+        inner = max(1, busy // 3)
+        e0.record()
+        for g in range(inner):
+            eng.rollout(1000 + r * inner + g, sigma, mu, fitness=fit, steps=steps)
+        e1.record()
         torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
+        ts.append(e0.elapsed_time(e1) / inner)
     n = int(steps.sum().item())
     eng.close()
     t = min(ts)
