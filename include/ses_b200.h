@@ -27,8 +27,9 @@ extern "C" {
 #define SES_ABI_VERSION 1
 
 /* env.name -> SES_ENV_*: "CartPole-v1" / "CartPole-v0" (same physics, TimeLimit 500 / 200: pass max_step), "simple_spread",
- * "MountainCar-v0", "Acrobot-v1" (discrete classic control any reference config can name, envs/gym_wrapper.py:8-9) */
-enum { SES_ENV_CARTPOLE = 0, SES_ENV_SIMPLE_SPREAD = 1, SES_ENV_MOUNTAINCAR = 2, SES_ENV_ACROBOT = 3 };
+ * "MountainCar-v0", "Acrobot-v1" (discrete classic control any reference config can name, envs/gym_wrapper.py:8-9),
+ * "Pendulum-v0" (continuous action: the policy's tanh head, networks/neural_network.py:32-33, `discrete_action: False`) */
+enum { SES_ENV_CARTPOLE = 0, SES_ENV_SIMPLE_SPREAD = 1, SES_ENV_MOUNTAINCAR = 2, SES_ENV_ACROBOT = 3, SES_ENV_PENDULUM = 4 };
 enum { SES_INIT_SHARED = 0, SES_INIT_FRESH = 1 };
 
 /* Static description of one engine instance (one per process / GPU).
@@ -36,8 +37,8 @@ enum { SES_INIT_SHARED = 0, SES_INIT_FRESH = 1 };
  * YAML (builder.py:10-75, conf/cartpole.yaml, conf/simplespread.yaml). */
 typedef struct ses_config {
     int32_t env;          /* SES_ENV_*                                   (env.name)                */
-    int32_t obs_dim;      /* network.num_state   4 | 12 (N=2) | 18 (N=3) | 2 (MountainCar) | 6 (Acrobot)  */
-    int32_t act_dim;      /* network.num_action  2 | 5 | 3 | 3                                     */
+    int32_t obs_dim;      /* network.num_state   4 | 12 (N=2) | 18 (N=3) | 2 (MountainCar) | 6 (Acrobot) | 3 (Pendulum) */
+    int32_t act_dim;      /* network.num_action  2 | 5 | 3 | 3 | 1                                 */
     int32_t gru;          /* network.gru                                                           */
     int32_t pomdp;        /* env.pomdp: CartPole obs[1], obs[3] zeroed   (envs/gym_wrapper.py:69-77) */
     int32_t n_agents;     /* simple_spread N (reference hard-codes 2, envs/pettingzoo_wrapper.py:9) */
@@ -60,7 +61,9 @@ typedef struct ses_config {
     int32_t shard_rank;   /* sharding -- blocks of B consecutive ids are dealt round robin to shard_world    */
     int32_t shard_world;  /* handles, this one owns blocks b with b % shard_world == shard_rank (id_begin = 0, */
                           /* id_end = population); w_override rows / traces are in local order               */
-    int32_t reserved[3];
+    int32_t continuous_action; /* network.discrete_action == False: action = tanh(fc2(...)) (networks/neural_network.py:32-33); */
+                          /* required for (and only valid with) SES_ENV_PENDULUM                   */
+    int32_t reserved[2];
 } ses_config;
 
 typedef struct ses_handle ses_handle;

@@ -93,7 +93,7 @@ def golden_rollout(ref, gru, pomdp, P, E, seed, sigma, n_trace):
     # trace the offspring whose first episode is longest (first 200 steps of episode 0)
     trace_ids = np.argsort([-len(l) for l in logs], kind="stable")[:n_trace].astype(np.int32)
     traces = np.full((n_trace, 200, 4), np.nan)
-    tr_actions = np.full((n_trace, 200), -1, dtype=np.int32)
+    tr_actions = np.full((n_trace, 200), -1, dtype=np.int32) if discrete else np.full((n_trace, 200), np.nan, dtype=np.float32)
     for j, i in enumerate(trace_ids):
         for t, rec in enumerate(logs[i][:200]):
             tr_actions[j, t] = rec[0]
@@ -147,6 +147,10 @@ def golden_spread(ref, N, P, E, seed, sigma, n_trace):
                 N=np.int32(N), E=np.int32(E))
 
 
+def pyref_continuous():
+    return ("Pendulum-v0",)
+
+
 class TracingClassic(pyref.ClassicShim):
     def __init__(self, *a, **kw):
         super().__init__(*a, **kw)
@@ -158,7 +162,8 @@ class TracingClassic(pyref.ClassicShim):
 
     def step(self, action):
         out = super().step(action)
-        self.log.append((int(action["0"]), tuple(self.state), out[1]))
+        a = action["0"]
+        self.log.append((float(a) if self.name in pyref_continuous() else int(a), tuple(self.state), out[1]))
         return out
 
 
@@ -167,10 +172,13 @@ def golden_classic(ref, env_name, P, E, seed, sigma, n_trace):
     [E, state_dim] table of initial states shared by every offspring (pool semantics)."""
     rng = np.random.RandomState(seed)
     sd, cap = pyref.ClassicShim.SPECS[env_name]
-    obs_dim, act = {"MountainCar-v0": (2, 3), "Acrobot-v1": (6, 3)}[env_name]
+    obs_dim, act = {"MountainCar-v0": (2, 3), "Acrobot-v1": (6, 3), "Pendulum-v0": (3, 1)}[env_name]
+    discrete = env_name not in pyref_continuous()          # Pendulum: GymEnvModel(discrete_action=False), the tanh head
     D = pyref.param_count(obs_dim, act, False)
     if env_name == "MountainCar-v0":
         init = np.stack([rng.uniform(-0.6, -0.4, size=E), np.zeros(E)], axis=1)
+    elif env_name == "Pendulum-v0":
+        init = rng.uniform([-np.pi, -1.0], [np.pi, 1.0], size=(E, 2))
     else:
         init = rng.uniform(-0.1, 0.1, size=(E, 4))
     W = rng.normal(0, sigma, size=(P, D)).astype(np.float32)
@@ -179,7 +187,7 @@ def golden_classic(ref, env_name, P, E, seed, sigma, n_trace):
     steps = np.zeros(P, dtype=np.int64)
     logs = []
     for i in range(P):
-        model = ref.GymEnvModel(obs_dim, act, True, False)
+        model = ref.GymEnvModel(obs_dim, act, discrete, False)
         set_flat(model, W[i], obs_dim, act, False)
         env = TracingClassic(env_name, max_step=cap, init_states=init)
         fitness[i] = ref.RolloutWorker((env, {"0": model}, E))
@@ -192,7 +200,7 @@ def golden_classic(ref, env_name, P, E, seed, sigma, n_trace):
         logs.append(ep0)
     trace_ids = np.arange(n_trace, dtype=np.int32) + 1           # offspring 1..n_trace (0 is the all-zero policy)
     traces = np.full((n_trace, 200, sd), np.nan)
-    tr_actions = np.full((n_trace, 200), -1, dtype=np.int32)
+    tr_actions = np.full((n_trace, 200), -1, dtype=np.int32) if discrete else np.full((n_trace, 200), np.nan, dtype=np.float32)
     for j, i in enumerate(trace_ids):
         for t, rec in enumerate(logs[i][:200]):
             tr_actions[j, t] = rec[0]
@@ -280,6 +288,7 @@ def main():
         "rollout_spread_n3": lambda: golden_spread(ref, 3, 48, 3, 42, 1.0, 2),
         "rollout_mountaincar": lambda: golden_classic(ref, "MountainCar-v0", 96, 3, 51, 3.0, 4),
         "rollout_acrobot": lambda: golden_classic(ref, "Acrobot-v1", 64, 3, 52, 2.0, 4),
+        "rollout_pendulum": lambda: golden_classic(ref, "Pendulum-v0", 96, 3, 53, 1.0, 4),
         "strategy_simple_evolution": lambda: golden_strategy(ref, "simple_evolution", 31),
         "strategy_simple_genetic": lambda: golden_strategy(ref, "simple_genetic", 32),
         "strategy_openai_es": lambda: golden_strategy(ref, "openai_es", 33),

@@ -171,10 +171,25 @@ def acrobot_physics(state, action):
     return tuple(ns), (-1.0 if not terminal else 0.0), terminal
 
 
+def pendulum_physics(state, u):
+    """gym classic_control/pendulum.py (Pendulum-v0, gym ~0.18): max_speed 8, max_torque 2, dt .05, g 10, m = l = 1.
+    `u` is the policy's action widened to a Python float (the real env does `np.clip(u, -2, 2)[0]`, which a 0-d action --
+    what GymEnvModel returns for num_action = 1 -- cannot be indexed by: the shim takes the scalar)."""
+    th, thdot = state
+    g, m, l, dt = 10.0, 1.0, 1.0, 0.05
+    u = float(np.clip(u, -2.0, 2.0))
+    angle_normalize = ((th + np.pi) % (2 * np.pi)) - np.pi
+    costs = angle_normalize ** 2 + .1 * thdot ** 2 + .001 * (u ** 2)
+    newthdot = thdot + (-3 * g / (2 * l) * np.sin(th + np.pi) + 3. / (m * l ** 2) * u) * dt
+    newth = th + newthdot * dt
+    newthdot = float(np.clip(newthdot, -8.0, 8.0))
+    return (float(newth), newthdot), float(-costs), False
+
+
 class ClassicShim:
-    """GymWrapper duck type (envs/gym_wrapper.py:7-54) over MountainCar-v0 / Acrobot-v1; `max_step` is
+    """GymWrapper duck type (envs/gym_wrapper.py:7-54) over MountainCar-v0 / Acrobot-v1 / Pendulum-v0; `max_step` is
     min(the config's max_step, gym's TimeLimit) as GymWrapper over a TimeLimit-wrapped env behaves."""
-    SPECS = {"MountainCar-v0": (2, 200), "Acrobot-v1": (4, 500)}
+    SPECS = {"MountainCar-v0": (2, 200), "Acrobot-v1": (4, 500), "Pendulum-v0": (2, 200)}
 
     def __init__(self, name, max_step=None, init_states=None, seed=None):
         self.name = name
@@ -190,6 +205,8 @@ class ClassicShim:
         s = self.state
         if self.name == "MountainCar-v0":
             return np.array(s, dtype=np.float64)
+        if self.name == "Pendulum-v0":
+            return np.array([np.cos(s[0]), np.sin(s[0]), s[1]], dtype=np.float64)
         return np.array([np.cos(s[0]), np.sin(s[0]), np.cos(s[1]), np.sin(s[1]), s[2], s[3]], dtype=np.float64)
 
     def reset(self):
@@ -199,6 +216,8 @@ class ClassicShim:
             self._reset_count += 1
         elif self.name == "MountainCar-v0":
             s = [self.rng.uniform(low=-0.6, high=-0.4), 0.0]
+        elif self.name == "Pendulum-v0":
+            s = self.rng.uniform(low=[-np.pi, -1.0], high=[np.pi, 1.0])
         else:
             s = self.rng.uniform(low=-0.1, high=0.1, size=(4,))
         self.state = tuple(float(v) for v in s)
@@ -206,8 +225,11 @@ class ClassicShim:
 
     def step(self, action):
         self.curr_step += 1
-        physics = mountaincar_physics if self.name == "MountainCar-v0" else acrobot_physics
-        self.state, r, d = physics(self.state, int(action["0"]))
+        if self.name == "Pendulum-v0":
+            self.state, r, d = pendulum_physics(self.state, float(action["0"]))      # 0-d float32 array from the tanh head
+        else:
+            physics = mountaincar_physics if self.name == "MountainCar-v0" else acrobot_physics
+            self.state, r, d = physics(self.state, int(action["0"]))
         if self.curr_step >= self.max_step or d:
             d = True
         tr = {"state": self._obs(), "reward": r, "done": d, "info": {}}

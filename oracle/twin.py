@@ -36,6 +36,7 @@ def lib():
             _lib.tw_rollout_mpe.restype = C.c_double
         if hasattr(_lib, "tw_rollout_classic"):
             _lib.tw_rollout_classic.restype = C.c_double
+            _lib.tw_rollout_classic_gru.restype = C.c_double
     return _lib
 
 
@@ -274,7 +275,8 @@ def population_mpe(parents, N=2, sigma=0.0, seed=0, gen=0, group=1, n_head=1, id
 
 
 # ---------------------------------------------------------------------------- classic control (ses_twin_classic.c)
-CLASSIC_ENVS = {"MountainCar-v0": 2, "Acrobot-v1": 3}
+CLASSIC_ENVS = {"MountainCar-v0": 2, "Acrobot-v1": 3, "Pendulum-v0": 4}
+CONTINUOUS_ENVS = ("Pendulum-v0",)          # tanh head (networks/neural_network.py:32-33): actions are float32
 
 
 def classic_dims(env):
@@ -294,7 +296,10 @@ def sincos_full(x):
 def classic_step(env, state, action):
     st = _f64(state).copy()
     r = C.c_double()
-    done = lib().tw_classic_step(CLASSIC_ENVS[env], _p(st), int(action), C.byref(r))
+    if env in CONTINUOUS_ENVS:
+        done = lib().tw_classic_step_continuous(CLASSIC_ENVS[env], _p(st), C.c_double(float(action)), C.byref(r))
+    else:
+        done = lib().tw_classic_step(CLASSIC_ENVS[env], _p(st), int(action), C.byref(r))
     return st, r.value, bool(done)
 
 
@@ -305,8 +310,8 @@ def classic_init(env, seed, init_mode, gen, idx, e):
     return st
 
 
-def rollout_classic(env, w, E=5, max_step=None, init=None, seed=0, init_mode=0, gen=0, idx=0, trace_steps=0):
-    """fitness, steps[, trace, actions] of one offspring."""
+def rollout_classic(env, w, E=5, max_step=None, init=None, seed=0, init_mode=0, gen=0, idx=0, trace_steps=0, gru=False):
+    """fitness, steps[, trace, actions] of one offspring (continuous envs: actions are float32)."""
     obs, act, sd, cap = classic_dims(env)
     max_step = cap if max_step is None else min(int(max_step), cap)
     w = _f32(w)
@@ -314,15 +319,18 @@ def rollout_classic(env, w, E=5, max_step=None, init=None, seed=0, init_mode=0, 
     trace = np.full((trace_steps, sd), np.nan) if trace_steps else None
     actions = np.full(trace_steps, -1, dtype=np.int32) if trace_steps else None
     steps = C.c_int64()
-    f = lib().tw_rollout_classic(CLASSIC_ENVS[env], _p(w), int(E), int(max_step), _p(init), C.c_uint32(seed), int(init_mode),
-                                 C.c_uint32(gen), C.c_uint32(idx), _p(trace), _p(actions), int(trace_steps), C.byref(steps))
+    f = lib().tw_rollout_classic_gru(CLASSIC_ENVS[env], int(bool(gru)), _p(w), int(E), int(max_step), _p(init), C.c_uint32(seed),
+                                     int(init_mode), C.c_uint32(gen), C.c_uint32(idx), _p(trace), _p(actions), int(trace_steps),
+                                     C.byref(steps))
     if trace_steps:
+        if env in CONTINUOUS_ENVS:
+            actions = actions.view(np.float32)
         return f, steps.value, trace, actions
     return f, steps.value
 
 
 def population_classic(env, parents, sigma=0.0, seed=0, gen=0, group=1, n_head=1, id0=0, n=1, E=5, max_step=None,
-                       W_override=None, init=None, init_mode=0, nthreads=8):
+                       W_override=None, init=None, init_mode=0, nthreads=8, gru=False):
     obs, act, sd, cap = classic_dims(env)
     max_step = cap if max_step is None else min(int(max_step), cap)
     parents = _f32(parents)
@@ -330,7 +338,7 @@ def population_classic(env, parents, sigma=0.0, seed=0, gen=0, group=1, n_head=1
     init = None if init is None else _f64(init)
     fitness = np.zeros(n)
     steps = np.zeros(n, dtype=np.int64)
-    lib().tw_population_classic(CLASSIC_ENVS[env], _p(parents), C.c_float(sigma), C.c_uint32(seed), C.c_uint32(gen), int(group),
-                                int(n_head), int(id0), int(n), int(E), int(max_step), _p(W_override), _p(init), int(init_mode),
-                                _p(fitness), _p(steps), int(nthreads))
+    lib().tw_population_classic_gru(CLASSIC_ENVS[env], int(bool(gru)), _p(parents), C.c_float(sigma), C.c_uint32(seed), C.c_uint32(gen),
+                                    int(group), int(n_head), int(id0), int(n), int(E), int(max_step), _p(W_override), _p(init),
+                                    int(init_mode), _p(fitness), _p(steps), int(nthreads))
     return fitness, steps

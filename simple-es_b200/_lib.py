@@ -20,7 +20,7 @@ class ses_config(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "env", "obs_dim", "act_dim", "gru", "pomdp", "n_agents", "max_step", "eval_ep_num", "population", "group",
         "n_head", "n_parents")] + [("seed", C.c_uint32)] + [(n, C.c_int32) for n in (
-            "init_mode", "id_begin", "id_end", "device", "antithetic", "shard_block", "shard_rank", "shard_world")] + [("reserved", C.c_int32 * 3)]
+            "init_mode", "id_begin", "id_end", "device", "antithetic", "shard_block", "shard_rank", "shard_world", "continuous_action")] + [("reserved", C.c_int32 * 2)]
 
 
 # every symbol include/ses_b200.h declares: name -> (restype, argtypes)

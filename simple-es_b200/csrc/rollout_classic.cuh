@@ -57,11 +57,10 @@ __device__ __forceinline__ double clip64(double v, double lo, double hi) { retur
 // packed pairs; every accumulator sees its products in ascending index order, one rounding per fma.
 // ---------------------------------------------------------------------------------------------
 template <int OBS, int ACT, int NQ, int S>
-__device__ __forceinline__ int mlp_policy_flat(const float4 (&w)[NQ][S], int slot, const float (&o)[OBS])
+__device__ __forceinline__ void mlp_logits_flat(const float4 (&w)[NQ][S], int slot, const float (&o)[OBS], float (&z)[ACT])
 {
     constexpr int O_B1 = HID * OBS, O_W2 = O_B1 + HID, O_B2 = O_W2 + ACT * HID;
     static_assert(O_B1 % 4 == 0 && O_W2 % 4 == 0 && O_B2 % 4 == 0 && ACT <= 4, "blocks are quad aligned");
-    float z[ACT];
     {
         const float4 b = w[O_B2 / 4][slot];
         const float bz[4] = {b.x, b.y, b.z, b.w};
@@ -94,6 +93,14 @@ __device__ __forceinline__ int mlp_policy_flat(const float4 (&w)[NQ][S], int slo
             if (jq & 1) { z[m] = __fadd_rn(z[m], sblk[m]); sblk[m] = 0.0f; }
         }
     }
+}
+
+// discrete head (neural_network.py:29-31)
+template <int OBS, int ACT, int NQ, int S>
+__device__ __forceinline__ int mlp_policy_flat(const float4 (&w)[NQ][S], int slot, const float (&o)[OBS])
+{
+    float z[ACT];
+    mlp_logits_flat<OBS, ACT, NQ, S>(w, slot, o, z);
     // argmax(softmax(z)) with the float32 collapse rule (neural_network.py:30-31; ses_common.cuh argmax_softmax2)
     float zmax = z[0];
 #pragma unroll
@@ -152,6 +159,64 @@ struct MountainCarEnv {
     }
 
     __device__ static __forceinline__ void store_trace(const State &s, double *row) { row[0] = s.pos; row[1] = s.vel; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Pendulum-v0 with the continuous-action head: action = tanh(fc2(...)) (neural_network.py:32-33), one float32 in (-1, 1)
+// used as the torque.  gym classic_control/pendulum.py (gym ~0.18): never terminates (TimeLimit 200),
+// reward -(angle_normalize(th)^2 + .1 thdot^2 + .001 u^2), obs [cos th, sin th, thdot].
+// ---------------------------------------------------------------------------------------------
+struct PendulumEnv {
+    static constexpr int OBS = 3, ACT = 1;
+    static constexpr int D = param_count(OBS, ACT, 0), NQ = (D + 3) / 4;     // 161, 41
+    static constexpr int STATE_DIM = 2, N_AGENTS = 1;
+    static constexpr bool UNIT_REWARD = false;
+    static constexpr bool LANES32_OK = true;
+    static constexpr double PI = 3.141592653589793;
+    struct State { double th, thd, ret; };
+
+    __device__ static __forceinline__ void init(State &s, const RolloutParams &p, int id, int ep)
+    {
+        if (p.init_states) {
+            s.th = p.init_states[2 * ep]; s.thd = p.init_states[2 * ep + 1];
+        } else {                                                       // uniform(-[pi, 1], [pi, 1])
+            const uint4 r = philox4x32_10((uint32_t)ep, p.init_mode ? (uint32_t)id : 0u, p.init_mode ? p.gen : 0u, 0u, p.seed, STREAM_INIT);
+            s.th = __dsub_rn(__dmul_rn(unit64(r.x), __dmul_rn(2.0, PI)), PI);
+            s.thd = __dsub_rn(__dmul_rn(unit64(r.y), 2.0), 1.0);
+        }
+        s.ret = 0.0;
+    }
+
+    template <int S>
+    __device__ static __forceinline__ void store_quad(float4 (&w)[NQ][S], int q, int s, const float4 v) { w[q][s] = v; }
+    template <int S>
+    __device__ static __forceinline__ void bind(State &, const float4 (&)[NQ][S], int) {}
+
+    template <int S>
+    __device__ static __forceinline__ bool step(State &s, const float4 (&w)[NQ][S], int slot, const RolloutParams &, int *actions)
+    {
+        double sn, cs;
+        sincos64_full(s.th, sn, cs);
+        const float o[OBS] = {(float)cs, (float)sn, (float)s.thd};
+        float z[ACT];
+        mlp_logits_flat<OBS, ACT, NQ, S>(w, slot, o, z);
+        const float uf = tanh32_fast_t<false>(z[0]);                   // == the contract's tanh32 for every input (exhaustive test)
+        actions[0] = __float_as_int(uf);                               // traces carry the float32 action's bit pattern
+        const double u = clip64((double)uf, -2.0, 2.0);
+        double m = fmod(__dadd_rn(s.th, PI), __dmul_rn(2.0, PI));      // Python's float %: fmod, then the divisor's sign
+        if (m < 0.0) m = __dadd_rn(m, __dmul_rn(2.0, PI));
+        const double an = __dsub_rn(m, PI);
+        const double costs = __dadd_rn(__dadd_rn(__dmul_rn(an, an), __dmul_rn(0.1, __dmul_rn(s.thd, s.thd))), __dmul_rn(0.001, __dmul_rn(u, u)));
+        double s2, c2;
+        sincos64_full(__dadd_rn(s.th, PI), s2, c2);
+        double nthd = __dadd_rn(s.thd, __dmul_rn(__dadd_rn(__dmul_rn(-15.0, s2), __dmul_rn(3.0, u)), 0.05));
+        s.th = __dadd_rn(s.th, __dmul_rn(nthd, 0.05));
+        s.thd = clip64(nthd, -8.0, 8.0);
+        s.ret = __dadd_rn(s.ret, -costs);
+        return false;
+    }
+
+    __device__ static __forceinline__ void store_trace(const State &s, double *row) { row[0] = s.th; row[1] = s.thd; }
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -115,11 +115,17 @@ extern "C" int ses_create(const ses_config *cfg, ses_handle **out)
     if (e != cudaSuccess || ndev == 0)
         return fail("ses_create: no CUDA device (%s); this engine has no CPU fallback", cudaGetErrorString(e));
     if (cfg->device < 0 || cfg->device >= ndev) return fail("ses_create: device %d out of range (%d devices)", cfg->device, ndev);
-    if (cfg->env < SES_ENV_CARTPOLE || cfg->env > SES_ENV_ACROBOT) return fail("ses_create: unknown env %d", cfg->env);
+    if (cfg->env < SES_ENV_CARTPOLE || cfg->env > SES_ENV_PENDULUM) return fail("ses_create: unknown env %d", cfg->env);
     if (cfg->env == SES_ENV_MOUNTAINCAR && (cfg->obs_dim != 2 || cfg->act_dim != 3))
         return fail("ses_create: MountainCar-v0 needs num_state=2, num_action=3 (got %d, %d)", cfg->obs_dim, cfg->act_dim);
     if (cfg->env == SES_ENV_ACROBOT && (cfg->obs_dim != 6 || cfg->act_dim != 3))
         return fail("ses_create: Acrobot-v1 needs num_state=6, num_action=3 (got %d, %d)", cfg->obs_dim, cfg->act_dim);
+    if (cfg->env == SES_ENV_PENDULUM && (cfg->obs_dim != 3 || cfg->act_dim != 1))
+        return fail("ses_create: Pendulum-v0 needs num_state=3, num_action=1 (got %d, %d)", cfg->obs_dim, cfg->act_dim);
+    if ((cfg->env == SES_ENV_PENDULUM) != (cfg->continuous_action != 0))
+        return fail("ses_create: the continuous-action head (discrete_action: False) is implemented for Pendulum-v0, and Pendulum-v0 needs it");
+    if (cfg->env == SES_ENV_PENDULUM && (cfg->gru || cfg->pomdp))
+        return fail("ses_create: Pendulum-v0 runs with the MLP policy and full observations only");
     if ((cfg->env == SES_ENV_MOUNTAINCAR || cfg->env == SES_ENV_ACROBOT) && (cfg->gru || cfg->pomdp))
         return fail("ses_create: MountainCar-v0 / Acrobot-v1 run with the MLP policy and full observations only");
     if (cfg->env == SES_ENV_CARTPOLE && (cfg->obs_dim != 4 || cfg->act_dim != 2))
@@ -161,12 +167,12 @@ extern "C" int ses_create(const ses_config *cfg, ses_handle **out)
     }
     h->NQ = (h->D + 3) / 4;
     h->DP = h->NQ * 4;
-    h->state_dim = cfg->env == SES_ENV_SIMPLE_SPREAD ? 4 * cfg->n_agents : (cfg->env == SES_ENV_MOUNTAINCAR ? 2 : 4);
+    h->state_dim = cfg->env == SES_ENV_SIMPLE_SPREAD ? 4 * cfg->n_agents : ((cfg->env == SES_ENV_MOUNTAINCAR || cfg->env == SES_ENV_PENDULUM) ? 2 : 4);
     h->num_sms = prop.multiProcessorCount;
     // gym registers CartPole-v1 with max_episode_steps=500 (TimeLimit); the wrapper's own max_step
     // (gym_wrapper.py:37-39) can only shorten it (CartPole-v0: the caller passes max_step <= 200).
     // simple_spread: max_cycles=25; MountainCar-v0: 200; Acrobot-v1: 500.
-    static const int caps[4] = {500, 25, 200, 500};
+    static const int caps[5] = {500, 25, 200, 500, 200};
     const int env_cap = caps[cfg->env];
     h->eff_max_step = cfg->max_step > 0 ? (cfg->max_step < env_cap ? cfg->max_step : env_cap) : env_cap;
     h->lanes_used_override = env_int("SES_ROLLOUT_LANES", 0);
@@ -368,6 +374,7 @@ extern "C" int ses_rollout(ses_handle *h, uint32_t generation, float sigma, cons
     if (c.env == SES_ENV_CARTPOLE && c.gru) return launch_rollout_cartpole_gru(h->num_sms, h->ctas_per_sm, rp, tr, st, &h->launches, g_err, sizeof(g_err));
     if (c.env == SES_ENV_MOUNTAINCAR) return launch_slots_by_E<MountainCarEnv>(h, rp, need_warps, tr, st);
     if (c.env == SES_ENV_ACROBOT) return launch_slots_by_E<AcrobotEnv>(h, rp, need_warps, tr, st);
+    if (c.env == SES_ENV_PENDULUM) return launch_slots_by_E<PendulumEnv>(h, rp, need_warps, tr, st);
     // simple_spread episodes all last max_cycles steps, so a warp never holds more than ceil(lanes_used / E) offspring at
     // once: 6 slots instead of 8 for E >= 5 (and 2-warp CTAs for N = 3) put 12 / 10 warps on an SM instead of 8
     // (shared-memory capacity is what limits this kernel)
@@ -706,7 +713,7 @@ extern "C" int ses_generation_openai_host(ses_handle *h, uint32_t generation, fl
     if (rc_roll) return -1;
     int key_bits = 0;
     double key_scale = 1.0;
-    if (c.env != SES_ENV_SIMPLE_SPREAD) {     // fitness = +-steps / E with integer |steps| <= E * max_step
+    if (c.env != SES_ENV_SIMPLE_SPREAD && c.env != SES_ENV_PENDULUM) {     // fitness = +-steps / E with integer |steps| <= E * max_step
         const long long vmax = (long long)c.eval_ep_num * h->eff_max_step;
         while ((1ll << key_bits) <= vmax) ++key_bits;
         key_scale = (double)c.eval_ep_num;
@@ -757,7 +764,7 @@ static int elite_generation_prologue(ses_handle *h, const char *who, uint32_t ge
     if (rc_roll) return -1;
     int key_bits = 0;
     double key_scale = 1.0;
-    if (c.env != SES_ENV_SIMPLE_SPREAD) {     // fitness = +-steps / E with integer |steps| <= E * max_step
+    if (c.env != SES_ENV_SIMPLE_SPREAD && c.env != SES_ENV_PENDULUM) {     // fitness = +-steps / E with integer |steps| <= E * max_step
         const long long vmax = (long long)c.eval_ep_num * h->eff_max_step;
         while ((1ll << key_bits) <= vmax) ++key_bits;
         key_scale = (double)c.eval_ep_num;

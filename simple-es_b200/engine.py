@@ -24,7 +24,9 @@ ENV_SPECS = {
     "simple_spread": (1, 25, None, None),
     "MountainCar-v0": (2, 200, 2, (2, 3)),
     "Acrobot-v1": (3, 500, 4, (6, 3)),
+    "Pendulum-v0": (4, 200, 2, (3, 1)),          # continuous action: the policy's tanh head (discrete_action: False)
 }
+CONTINUOUS_ENVS = ("Pendulum-v0",)
 ENV_IDS = {k: v[0] for k, v in ENV_SPECS.items()}
 
 
@@ -82,12 +84,15 @@ class RolloutEngine:
 
     def __init__(self, env_name, obs_dim, act_dim, gru, pomdp, max_step, eval_ep_num, population, group, n_head,
                  n_parents, seed=0, init_mode="shared", n_agents=2, id_begin=0, id_end=None, device=0, antithetic=False,
-                 shard=None):
+                 shard=None, discrete_action=True):
         """`shard` = (rank, world, block): block-cyclic slice instead of the contiguous [id_begin, id_end)."""
         if env_name not in ENV_IDS:
             raise ValueError(
                 "env %r is not supported by the B200 engine (%s; Box2D, PyBullet and "
                 "Unity environments stay on the reference CPU path)" % (env_name, ", ".join(sorted(ENV_IDS))))
+        if bool(discrete_action) == (env_name in CONTINUOUS_ENVS):
+            raise ValueError("%s runs with discrete_action: %s (networks/neural_network.py:29-33); the continuous-action head is "
+                             "implemented for %s" % (env_name, env_name not in CONTINUOUS_ENVS, ", ".join(CONTINUOUS_ENVS)))
         if not torch.cuda.is_available():
             raise RuntimeError("simple-es_b200: no CUDA device; the engine has no CPU fallback")
         self.lib = _lib.load()
@@ -115,13 +120,14 @@ class RolloutEngine:
             n_head=int(n_head), n_parents=int(n_parents), seed=int(seed) & 0xFFFFFFFF,
             init_mode={"shared": 0, "fresh": 1}[init_mode], id_begin=self.id_begin, id_end=self.id_end, device=device,
             antithetic=int(bool(antithetic)), shard_block=self.shard[2] if self.shard else 0,
-            shard_rank=self.shard[0] if self.shard else 0, shard_world=self.shard[1] if self.shard else 0)
+            shard_rank=self.shard[0] if self.shard else 0, shard_world=self.shard[1] if self.shard else 0,
+            continuous_action=int(not discrete_action))
         h = C.c_void_p()
         _lib.check(self.lib.ses_create(C.byref(self.cfg), C.byref(h)))
         self._h = h
         # integer-key fast path of K2: CartPole fitness*E is an integer < 2^key_bits
         # (CartPole: +1 per step; MountainCar / Acrobot: -1 or 0 per step => |fitness * E| <= E * max_step)
-        if env_name != "simple_spread":
+        if env_name != "simple_spread" and env_name not in CONTINUOUS_ENVS:
             self.key_bits = int(self.E * self.max_step).bit_length()
             self.key_scale = float(self.E)
         else:

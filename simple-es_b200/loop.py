@@ -40,8 +40,6 @@ class B200Loop(BaseESLoop):
         self.engine_cfg = dict(config.get("engine") or {})
         if net_cfg.get("name") != "gym_model":
             raise ValueError("the B200 engine implements the reference's only network, gym_model (builder.py:17-24)")
-        if not net_cfg.get("discrete_action", True):
-            raise ValueError("continuous-action heads run only on Box2D/PyBullet envs, which stay on the reference CPU path")
         if strat_cfg["name"] not in STRATEGIES:
             raise ValueError("unknown strategy %r" % strat_cfg["name"])
         self.rank, self.world = sdist.init_from_env()

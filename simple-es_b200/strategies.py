@@ -39,7 +39,8 @@ class _Base:
             bool(env_cfg.get("pomdp", False)), env_cfg.get("max_step"), eval_ep_num, self.P, group, n_head, n_par,
             seed=seed, init_mode=engine_cfg.get("init_states", "shared"), n_agents=int(engine_cfg.get("n_agents", 2)),
             id_begin=0 if self.shard else self.lo, id_end=None if self.shard else self.hi, device=device,
-            antithetic=bool(engine_cfg.get("antithetic", False)), shard=self.shard)
+            antithetic=bool(engine_cfg.get("antithetic", False)), shard=self.shard,
+            discrete_action=bool(network_cfg.get("discrete_action", True)))
         self.D = self.engine.D
         # what a resumed run must share with the run that wrote the state (state() / load_state())
         self._run_key = {"env": name, "seed": int(seed) & 0xFFFFFFFF, "eval_ep_num": int(eval_ep_num),

@@ -14,7 +14,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 from simple_es_b200 import _lib as product_lib  # noqa: E402  (signatures and the ses_config struct only)
-from simple_es_b200.engine import ENV_IDS, ENV_SPECS, owned_ids  # noqa: E402  (pure-Python host logic)
+from simple_es_b200.engine import CONTINUOUS_ENVS, ENV_IDS, ENV_SPECS, owned_ids  # noqa: E402  (pure-Python host logic)
 
 from . import build as emu_build  # noqa: E402
 
@@ -63,11 +63,12 @@ class EmuEngine:
             n_head=int(n_head), n_parents=int(n_parents), seed=int(seed) & 0xFFFFFFFF,
             init_mode={"shared": 0, "fresh": 1}[init_mode], id_begin=self.id_begin, id_end=self.id_end, device=0,
             antithetic=int(bool(antithetic)), shard_block=self.shard[2] if self.shard else 0,
-            shard_rank=self.shard[0] if self.shard else 0, shard_world=self.shard[1] if self.shard else 0)
+            shard_rank=self.shard[0] if self.shard else 0, shard_world=self.shard[1] if self.shard else 0,
+            continuous_action=int(env_name in CONTINUOUS_ENVS))
         h = C.c_void_p()
         self._check(self.lib.ses_create(C.byref(self.cfg), C.byref(h)))
         self._h = h
-        if env_name != "simple_spread":
+        if env_name != "simple_spread" and env_name not in CONTINUOUS_ENVS:
             self.key_bits, self.key_scale = int(self.E * self.max_step).bit_length(), float(self.E)
         else:
             self.key_bits, self.key_scale = 0, 1.0

@@ -158,3 +158,82 @@ def test_classic_loops_match_oracle_composition(twin, conf, env, ngen):
             mu = mu1[None]
             assert np.array_equal(s.parents.cpu().numpy(), mu)
             sigma *= 0.9
+
+
+# ------------------------------------------------------------------------------------- Pendulum-v0, continuous-action head
+def _pendulum(**kw):
+    from simple_es_b200.engine import RolloutEngine
+    args = dict(env_name="Pendulum-v0", obs_dim=3, act_dim=1, gru=False, pomdp=False, max_step=200, eval_ep_num=5, population=1024,
+                group=1024, n_head=1, n_parents=1, seed=0, init_mode="shared", discrete_action=False)
+    args.update(kw)
+    return RolloutEngine(**args)
+
+
+@pytest.mark.parametrize("E,init_mode,sigma", [(5, "shared", 1.0), (3, "fresh", 0.5), (1, "fresh", 2.0)])
+def test_rollout_pendulum_philox_bit_exact(twin, E, init_mode, sigma):
+    """`discrete_action: False` (the tanh head, networks/neural_network.py:32-33) + Pendulum-v0 physics in the slot kernel:
+    float64 returns bit-exact against the twin."""
+    P = 1500
+    eng = _pendulum(population=P, group=P, eval_ep_num=E, seed=29, init_mode=init_mode)
+    assert eng.D == 161 and eng.key_bits == 0
+    mu = np.random.default_rng(6).normal(0, 0.5, (1, 161)).astype(np.float32)
+    fit, steps = eng.rollout(4, sigma, _cuda(mu))
+    tf, ts = twin.population_classic("Pendulum-v0", mu, sigma=sigma, seed=29, gen=4, group=P, n_head=1, n=P, E=E,
+                                     init_mode=0 if init_mode == "shared" else 1)
+    assert np.array_equal(steps.cpu().numpy(), ts) and np.all(ts == 200 * E)
+    assert np.array_equal(fit.cpu().numpy(), tf)
+
+
+def test_rollout_pendulum_verification_mode_matches_reference(twin, golden):
+    """Golden = the reference's RolloutWorker + GymEnvModel(3, 1, discrete_action=False) over the float64 Python Pendulum
+    restatement.  The engine consumes the reference's weights and initial states: returns within rtol 1e-4 (north_star),
+    traced actions within float32 rounding noise of torch's tanh, traced states within 1e-4 over the whole 200-step episode;
+    bit-exact against the twin."""
+    g = golden("rollout_pendulum")
+    W, init, E = g["W"], g["init"], int(g["E"])
+    P = W.shape[0]
+    eng = _pendulum(population=P, group=P, eval_ep_num=E)
+    fit, steps, trace, actions = eng.rollout(0, 0.0, None, w_override=_cuda(W), init_states=_cuda(init), n_trace=P)
+    fit = fit.cpu().numpy(); trace = trace.cpu().numpy(); actions = actions.cpu().numpy()[:, :, 0].copy().view(np.float32)
+    tf, ts = twin.population_classic("Pendulum-v0", np.zeros((1, 161), np.float32), n=P, E=E, W_override=W, init=init)
+    assert np.array_equal(fit, tf) and np.array_equal(steps.cpu().numpy(), ts)
+    np.testing.assert_allclose(fit, g["fitness"], rtol=1e-4)
+    for j, i in enumerate(g["trace_ids"]):
+        assert np.abs(actions[i] - g["trace_actions"][j]).max() <= 2e-5
+        assert np.abs(trace[i] - g["traces"][j]).max() <= 1e-4
+        f, n, tr, ac = twin.rollout_classic("Pendulum-v0", W[i], E=E, init=init, trace_steps=200)
+        assert np.array_equal(trace[i], tr) and np.array_equal(actions[i], ac)
+
+
+def test_pendulum_loop_matches_oracle_composition(twin):
+    """conf/pendulum.yaml (openai_es, discrete_action: False) through B200Loop: fitness, rank order (float64 keys, full radix
+    path) and updated parameters of every generation equal a composition of oracle steps; the checkpoint has the reference's
+    state_dict keys with a 1-row fc2."""
+    from simple_es_b200.loop import B200Loop
+    cfg = yaml.load(open(os.path.join(ROOT, "conf", "pendulum.yaml")), Loader=yaml.FullLoader)
+    cfg["strategy"].update(offspring_num=512, init_sigma=0.5, learning_rate=0.1, sigma_decay=0.9)
+    D, E, P, sigma, lr = 161, 3, 512, 0.5, 0.1
+    loop = B200Loop(cfg, 3, 1, E, save_model_period=0, seed=5, quiet=True)
+    s = loop.strategy
+    mu = np.zeros((1, D), np.float32); m = np.zeros(D, np.float32); v = np.zeros(D, np.float32)
+    for gen in range(3):
+        s.step()
+        tf, ts = twin.population_classic("Pendulum-v0", mu, sigma=sigma, seed=5, gen=gen, group=P, n_head=1, n=P, E=E, init_mode=1)
+        assert np.array_equal(s.fitness.cpu().numpy(), tf)
+        order = twin.rank_desc(tf)
+        assert np.array_equal(s.order.cpu().numpy(), order)
+        g = twin.grad_openai(twin.centered_rank(order), D, 5, gen, P, 1, -(lr / (P * sigma)))
+        mu1, m, v = twin.adam(mu[0], m, v, g, s.engine.adam_a(lr, gen + 1))
+        mu = mu1[None]
+        assert np.array_equal(s.parents.cpu().numpy(), mu)
+        sigma *= 0.9
+    sd = loop.elite_state_dict()
+    assert list(sd) == ["fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias"] and tuple(sd["fc2.weight"].shape) == (1, 32)
+
+
+def test_continuous_head_is_rejected_elsewhere():
+    from simple_es_b200.engine import RolloutEngine
+    with pytest.raises(ValueError, match="discrete_action"):
+        RolloutEngine("CartPole-v1", 4, 2, False, False, 500, 5, 64, 64, 1, 1, discrete_action=False)
+    with pytest.raises(ValueError, match="discrete_action"):
+        RolloutEngine("Pendulum-v0", 3, 1, False, False, 200, 5, 64, 64, 1, 1)

@@ -104,3 +104,60 @@ def test_classic_init_streams(twin, env):
         assert -0.6 <= a[0] <= -0.4 and a[1] == 0.0
     else:
         assert np.all(np.abs(a) <= 0.1)
+
+
+# ------------------------------------------------------------------------------------- Pendulum-v0, continuous-action head
+def test_pendulum_known_answers(twin):
+    """gym pendulum.py (Pendulum-v0): hanging down (th = pi) at rest with zero torque stays put and costs pi^2; upright at rest is
+    an (unstable) equilibrium with zero cost; torque enters as 3 u dt; the speed is clipped at 8 after the angle has advanced."""
+    st, r, done = twin.classic_step("Pendulum-v0", [math.pi, 0.0], 0.0)
+    assert abs(st[0] - math.pi) < 1e-15 and abs(st[1]) < 1e-14 and abs(r + math.pi ** 2) < 1e-14 and not done
+    st, r, done = twin.classic_step("Pendulum-v0", [0.0, 0.0], 0.0)
+    assert abs(st[0]) < 1e-16 and abs(st[1]) < 1e-15 and r == 0.0 and not done
+    st, r, _ = twin.classic_step("Pendulum-v0", [0.0, 0.0], 1.0)
+    assert abs(st[1] - 3.0 * 0.05) < 1e-15 and abs(st[0] - 3.0 * 0.05 * 0.05) < 1e-16 and abs(r + 0.001) < 1e-18
+    st, _, _ = twin.classic_step("Pendulum-v0", [math.pi / 2, 7.9], 1.0)       # gravity + torque push the speed past 8
+    assert st[1] == 8.0 and st[0] > math.pi / 2 + 8.0 * 0.05                   # newth used the unclipped speed (v0 ordering)
+    # angle_normalize: the cost sees the angle modulo 2 pi
+    _, r1, _ = twin.classic_step("Pendulum-v0", [0.3, 0.0], 0.0)
+    _, r2, _ = twin.classic_step("Pendulum-v0", [0.3 + 4 * math.pi, 0.0], 0.0)
+    assert abs(r1 - r2) < 1e-14
+    # the all-zero policy answers tanh(0) = 0: a free pendulum, 200 steps per episode
+    f, n = twin.rollout_classic("Pendulum-v0", np.zeros(161, np.float32), E=2)
+    assert n == 400 and f < 0.0
+
+
+def test_pendulum_twin_matches_python_restatement(twin):
+    from oracle import pyref
+    rng = np.random.default_rng(4)
+    for trial in range(8):
+        s_py = (float(rng.uniform(-math.pi, math.pi)), float(rng.uniform(-1, 1)))
+        s_tw = np.array(s_py)
+        for t in range(200):
+            u = float(np.float32(rng.uniform(-1, 1)))
+            s_py, r_py, d_py = pyref.pendulum_physics(s_py, u)
+            s_tw, r_tw, d_tw = twin.classic_step("Pendulum-v0", s_tw, u)
+            assert np.abs(np.array(s_py) - s_tw).max() <= 1e-11 and abs(r_py - r_tw) <= 1e-11 and not d_py and not d_tw
+
+
+def test_pendulum_rollout_golden(twin, golden):
+    """The reference's RolloutWorker + GymEnvModel(num_state 3, num_action 1, discrete_action=False) -- the tanh head of
+    networks/neural_network.py:32-33 -- over the Python Pendulum restatement vs the twin: returns within rtol 1e-4 (north_star),
+    actions within float32 rounding noise of torch's tanh, states <= 1e-6 over the 200 steps of an episode."""
+    g = golden("rollout_pendulum")
+    E, W, init = int(g["E"]), g["W"], g["init"]
+    fit, steps = twin.population_classic("Pendulum-v0", np.zeros((1, W.shape[1]), np.float32), n=W.shape[0], E=E, W_override=W, init=init)
+    np.testing.assert_allclose(fit, g["fitness"], rtol=1e-4)
+    assert np.array_equal(steps, g["steps"]) and np.all(steps == 200 * E)
+    for j, i in enumerate(g["trace_ids"]):
+        f, n, tr, ac = twin.rollout_classic("Pendulum-v0", W[i], E=E, init=init, trace_steps=200)
+        assert ac.dtype == np.float32 and np.abs(ac - g["trace_actions"][j]).max() <= 2e-5
+        assert np.abs(tr - g["traces"][j]).max() <= 1e-4
+
+
+def test_pendulum_init_stream(twin):
+    a = twin.classic_init("Pendulum-v0", 5, 0, 0, 0, 1)
+    assert np.array_equal(a, twin.classic_init("Pendulum-v0", 5, 0, 9, 4, 1))
+    assert abs(a[0]) <= math.pi and abs(a[1]) <= 1.0
+    many = np.array([twin.classic_init("Pendulum-v0", 1, 1, 0, i, 0) for i in range(400)])
+    assert many[:, 0].min() < -2.5 and many[:, 0].max() > 2.5 and many[:, 1].min() < -0.8 and many[:, 1].max() > 0.8

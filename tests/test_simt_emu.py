@@ -554,6 +554,42 @@ def test_emu_rollout_classic_traces_equal_the_twin(emu, twin, golden, env):
         assert fit[j] == tf and steps[j] == tsteps
 
 
+# ------------------------------------------------------------------------------------- K1: Pendulum-v0, continuous-action head
+@pytest.mark.parametrize("E,init_mode,sigma", [(5, "shared", 1.0), (3, "fresh", 0.5), (1, "fresh", 2.0)])
+def test_emu_rollout_pendulum_philox_bit_exact(emu, twin, E, init_mode, sigma):
+    """The tanh head (networks/neural_network.py:32-33) + Pendulum-v0 in the slot kernel == the twin, bit for bit (float64 returns)."""
+    P = 96
+    eng = emu(env_name="Pendulum-v0", obs_dim=3, act_dim=1, max_step=200, population=P, group=P, eval_ep_num=E, seed=29, init_mode=init_mode)
+    assert eng.D == 161
+    mu = np.random.default_rng(6).normal(0, 0.5, (1, 161)).astype(np.float32)
+    fit, steps = eng.rollout(4, sigma, mu)
+    tf, ts = twin.population_classic("Pendulum-v0", mu, sigma=sigma, seed=29, gen=4, group=P, n_head=1, n=P, E=E,
+                                     init_mode=0 if init_mode == "shared" else 1)
+    assert np.array_equal(steps, ts) and np.all(ts == 200 * E) and np.array_equal(fit, tf)
+
+
+def test_emu_rollout_pendulum_traces_equal_the_twin(emu, twin, golden):
+    g = golden("rollout_pendulum")
+    W, init, E = g["W"][:10], g["init"], int(g["E"])
+    eng = emu(env_name="Pendulum-v0", obs_dim=3, act_dim=1, max_step=200, population=10, group=10, eval_ep_num=E)
+    fit, steps, trace, actions = eng.rollout(0, 0.0, None, w_override=W, init_states=init, n_trace=10)
+    for j in range(10):
+        tf, tsteps, ttr, tac = twin.rollout_classic("Pendulum-v0", W[j], E=E, init=init, trace_steps=200)
+        assert np.array_equal(trace[j], ttr) and np.array_equal(actions[j, :, 0].view(np.float32), tac)      # float32 action bit patterns
+        assert fit[j] == tf and steps[j] == tsteps
+    np.testing.assert_allclose(fit, g["fitness"][:10], rtol=1e-4)            # vs the reference path (north_star tolerance)
+
+
+def test_emu_continuous_head_needs_pendulum(emu):
+    from simple_es_b200 import _lib as product_lib
+    import ctypes as C
+    eng = emu()
+    cfg = product_lib.ses_config(env=0, obs_dim=4, act_dim=2, eval_ep_num=5, population=8, group=8, n_head=1, n_parents=1, id_end=8,
+                                 continuous_action=1)
+    h = C.c_void_p()
+    assert eng.lib.ses_create(C.byref(cfg), C.byref(h)) != 0 and b"continuous-action head" in eng.lib.ses_last_error()
+
+
 # ------------------------------------------------------------------------------------- multi-GPU: peer exchange fused into K1
 def _openai_rank(emu, rank, world, P, gens, seed, barrier, handles, out, shard_mode):
     """One emulated rank (an OS thread): the steps of strategies.OpenAIES.step() with the peer exchange."""
