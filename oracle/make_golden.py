@@ -117,13 +117,13 @@ class TracingSpread(pyref.SimpleSpreadShim):
         return out
 
 
-def golden_spread(ref, N, P, E, seed, sigma, n_trace):
-    """Reference RolloutWorker + one GymEnvModel copy per agent (utils.wrap_agentid semantics) over the
-    simple_spread restatement, fixed [E, 4N] initial positions shared by every offspring."""
-    from copy import deepcopy
+def golden_spread(ref, N, P, E, seed, sigma, n_trace, gru=False):
+    """Reference RolloutWorker + one GymEnvModel copy per agent (the reference's own utils.wrap_agentid: a deepcopy per agent id,
+    so with gru=True every agent has its own hidden state) over the simple_spread restatement, fixed [E, 4N] initial positions
+    shared by every offspring."""
     rng = np.random.RandomState(seed)
     obs_dim, act = 6 * N, 5
-    D = pyref.param_count(obs_dim, act, False)
+    D = pyref.param_count(obs_dim, act, gru)
     init = rng.uniform(-1, 1, size=(E, 4 * N))
     W = rng.normal(0, sigma, size=(P, D)).astype(np.float32)
     W[0] = 0.0
@@ -132,11 +132,11 @@ def golden_spread(ref, N, P, E, seed, sigma, n_trace):
     tr_actions = np.full((n_trace, 25, N), -1, dtype=np.int32)
     tr_rewards = np.full((n_trace, 25), np.nan)
     for i in range(P):
-        model = ref.GymEnvModel(obs_dim, act, True, False)
-        set_flat(model, W[i], obs_dim, act, False)
+        model = ref.GymEnvModel(obs_dim, act, True, gru)
+        set_flat(model, W[i], obs_dim, act, gru)
         env = TracingSpread(N=N, init_states=init)
         env.log = []
-        group = {a: deepcopy(model) for a in env.get_agent_ids()}
+        group = ref.wrap_agentid(env.get_agent_ids(), model)           # learning_strategies/evolution/utils.py:4-8
         fitness[i] = ref.RolloutWorker((env, group, E))
         if i < n_trace:
             for t, rec in enumerate(env.log[1:26]):
@@ -144,7 +144,7 @@ def golden_spread(ref, N, P, E, seed, sigma, n_trace):
                 traces[i, t] = np.concatenate([rec[1], rec[2]])
                 tr_rewards[i, t] = rec[3]
     return dict(W=W, init=init, fitness=fitness, traces=traces, trace_actions=tr_actions, trace_rewards=tr_rewards,
-                N=np.int32(N), E=np.int32(E))
+                N=np.int32(N), E=np.int32(E), gru=np.int32(gru))
 
 
 def pyref_continuous():
@@ -167,14 +167,14 @@ class TracingClassic(pyref.ClassicShim):
         return out
 
 
-def golden_classic(ref, env_name, P, E, seed, sigma, n_trace):
+def golden_classic(ref, env_name, P, E, seed, sigma, n_trace, gru=False):
     """Reference RolloutWorker + GymEnvModel over MountainCar-v0 / Acrobot-v1 (oracle/pyref.py::ClassicShim), a fixed
     [E, state_dim] table of initial states shared by every offspring (pool semantics)."""
     rng = np.random.RandomState(seed)
     sd, cap = pyref.ClassicShim.SPECS[env_name]
     obs_dim, act = {"MountainCar-v0": (2, 3), "Acrobot-v1": (6, 3), "Pendulum-v0": (3, 1)}[env_name]
     discrete = env_name not in pyref_continuous()          # Pendulum: GymEnvModel(discrete_action=False), the tanh head
-    D = pyref.param_count(obs_dim, act, False)
+    D = pyref.param_count(obs_dim, act, gru)
     if env_name == "MountainCar-v0":
         init = np.stack([rng.uniform(-0.6, -0.4, size=E), np.zeros(E)], axis=1)
     elif env_name == "Pendulum-v0":
@@ -187,8 +187,8 @@ def golden_classic(ref, env_name, P, E, seed, sigma, n_trace):
     steps = np.zeros(P, dtype=np.int64)
     logs = []
     for i in range(P):
-        model = ref.GymEnvModel(obs_dim, act, discrete, False)
-        set_flat(model, W[i], obs_dim, act, False)
+        model = ref.GymEnvModel(obs_dim, act, discrete, gru)
+        set_flat(model, W[i], obs_dim, act, gru)
         env = TracingClassic(env_name, max_step=cap, init_states=init)
         fitness[i] = ref.RolloutWorker((env, {"0": model}, E))
         steps[i] = sum(1 for rec in env.log if rec[0] != "reset")
@@ -289,6 +289,12 @@ def main():
         "rollout_mountaincar": lambda: golden_classic(ref, "MountainCar-v0", 96, 3, 51, 3.0, 4),
         "rollout_acrobot": lambda: golden_classic(ref, "Acrobot-v1", 64, 3, 52, 2.0, 4),
         "rollout_pendulum": lambda: golden_classic(ref, "Pendulum-v0", 96, 3, 53, 1.0, 4),
+        # the recurrent policy (`gru: True`) beyond CartPole: one hidden state per agent copy (utils.wrap_agentid)
+        "rollout_spread_n2_gru": lambda: golden_spread(ref, 2, 32, 3, 61, 0.5, 4, gru=True),
+        "rollout_spread_n3_gru": lambda: golden_spread(ref, 3, 16, 2, 62, 0.5, 2, gru=True),
+        "rollout_mountaincar_gru": lambda: golden_classic(ref, "MountainCar-v0", 24, 2, 63, 1.0, 4, gru=True),
+        "rollout_pendulum_gru": lambda: golden_classic(ref, "Pendulum-v0", 24, 2, 64, 0.5, 4, gru=True),
+        "rollout_acrobot_gru": lambda: golden_classic(ref, "Acrobot-v1", 16, 2, 65, 0.7, 2, gru=True),
         "strategy_simple_evolution": lambda: golden_strategy(ref, "simple_evolution", 31),
         "strategy_simple_genetic": lambda: golden_strategy(ref, "simple_genetic", 32),
         "strategy_openai_es": lambda: golden_strategy(ref, "openai_es", 33),

@@ -29,6 +29,7 @@ def load():
     os.environ.setdefault("WANDB_MODE", "disabled")
     from learning_strategies.evolution import offspring_strategies as strategies
     from learning_strategies.evolution import loop
+    from learning_strategies.evolution import utils as es_utils
     from learning_strategies import optimizers
     from networks import neural_network
 
@@ -44,6 +45,7 @@ def load():
     ns.GymEnvModel = neural_network.GymEnvModel
     ns.RolloutWorker = loop.RolloutWorker
     ns.ESLoop = loop.ESLoop
+    ns.wrap_agentid = es_utils.wrap_agentid
     return ns
 
 

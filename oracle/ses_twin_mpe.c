@@ -29,6 +29,7 @@
 void tw_philox(const uint32_t *ctr, const uint32_t *key, uint32_t *out);
 int tw_param_count(int obs, int act, int gru);
 float tw_fc2_row(const float *w2row, const float *x, float bias);
+int tw_policy_step(const float *w, int obs, int act, int gru, const float *o, float *h, float *logits);
 void tw_perturb(const float *parent, int D, float sigma, uint32_t seed, uint32_t gen, uint32_t id, int perturbed, float *w);
 void tw_tanhf_v(const float *x, float *y, int64_t n);
 
@@ -215,16 +216,31 @@ TW_EXPORT void tw_spread_init(uint32_t seed, int init_mode, uint32_t gen, uint32
  * init: [E][4N] explicit positions (agents then landmarks) or NULL -> Philox.
  * trace: optional [trace_steps][4N] (agent pos, agent vel) after each step of episode 0;
  * actions: optional [trace_steps][N]. */
+TW_EXPORT double tw_rollout_mpe_gru(int gru, const float *w, int N, int E, int max_cycles, const double *init, uint32_t seed,
+                                    int init_mode, uint32_t gen, uint32_t id, double *trace, int32_t *actions, int trace_steps,
+                                    int64_t *steps_out);
+
 TW_EXPORT double tw_rollout_mpe(const float *w, int N, int E, int max_cycles, const double *init, uint32_t seed,
                                 int init_mode, uint32_t gen, uint32_t id, double *trace, int32_t *actions, int trace_steps,
                                 int64_t *steps_out)
+{
+    return tw_rollout_mpe_gru(0, w, N, E, max_cycles, init, seed, init_mode, gen, id, trace, actions, trace_steps, steps_out);
+}
+
+/* gru = 1: the recurrent policy.  wrap_agentid (learning_strategies/evolution/utils.py:4-8) deep-copies the network once per
+ * agent id: shared weights, ONE HIDDEN STATE PER AGENT, all reset at the start of every episode (loop.py:114-116). */
+TW_EXPORT double tw_rollout_mpe_gru(int gru, const float *w, int N, int E, int max_cycles, const double *init, uint32_t seed,
+                                    int init_mode, uint32_t gen, uint32_t id, double *trace, int32_t *actions, int trace_steps,
+                                    int64_t *steps_out)
 {
     const int obs = 6 * N;
     double total = 0.0;
     int64_t nsteps = 0;
     for (int e = 0; e < E; ++e) {
         double st[4 * MAXN];
+        float hid[MAXN][HID];
         spread_state s;
+        memset(hid, 0, sizeof(hid));
         if (init) memcpy(st, init + (size_t)4 * N * e, sizeof(double) * 4 * N);
         else tw_spread_init(seed, init_mode, gen, id, (uint32_t)e, N, st);
         for (int i = 0; i < N; ++i) {
@@ -236,7 +252,10 @@ TW_EXPORT double tw_rollout_mpe(const float *w, int N, int E, int max_cycles, co
         for (int t = 0; t < max_cycles; ++t) {
             int act[MAXN];
             float o[6 * MAXN];
-            for (int i = 0; i < N; ++i) { spread_obs(&s, N, i, o); act[i] = spread_policy(w, obs, o, NULL); }
+            for (int i = 0; i < N; ++i) {
+                spread_obs(&s, N, i, o);
+                act[i] = gru ? tw_policy_step(w, obs, 5, 1, o, hid[i], NULL) : spread_policy(w, obs, o, NULL);
+            }
             R = R + spread_step(&s, N, act);
             ++nsteps;
             if (e == 0 && t < trace_steps) {
@@ -253,19 +272,26 @@ TW_EXPORT double tw_rollout_mpe(const float *w, int N, int E, int max_cycles, co
     return total / (double)E;
 }
 
-TW_EXPORT void tw_population_mpe(const float *parents, int N, float sigma, uint32_t seed, uint32_t gen, int group, int n_head,
-                                 int id0, int n, int E, int max_cycles, const float *W_override, const double *init,
-                                 int init_mode, double *fitness, int64_t *steps)
+TW_EXPORT void tw_population_mpe_gru(int gru, const float *parents, int N, float sigma, uint32_t seed, uint32_t gen, int group, int n_head,
+                                     int id0, int n, int E, int max_cycles, const float *W_override, const double *init,
+                                     int init_mode, double *fitness, int64_t *steps)
 {
-    const int D = tw_param_count(6 * N, 5, 0);
+    const int D = tw_param_count(6 * N, 5, gru);
     float *w = (float *)malloc(sizeof(float) * (size_t)D);
     for (int j = 0; j < n; ++j) {
         int id = id0 + j;
         if (W_override) memcpy(w, W_override + (size_t)j * D, sizeof(float) * (size_t)D);
         else tw_perturb(parents + (size_t)(id / group) * D, D, sigma, seed, gen, (uint32_t)id, (id % group) - n_head + 1, w);
-        fitness[j] = tw_rollout_mpe(w, N, E, max_cycles, init, seed, init_mode, gen, (uint32_t)id, NULL, NULL, 0, &steps[j]);
+        fitness[j] = tw_rollout_mpe_gru(gru, w, N, E, max_cycles, init, seed, init_mode, gen, (uint32_t)id, NULL, NULL, 0, &steps[j]);
     }
     free(w);
+}
+
+TW_EXPORT void tw_population_mpe(const float *parents, int N, float sigma, uint32_t seed, uint32_t gen, int group, int n_head,
+                                 int id0, int n, int E, int max_cycles, const float *W_override, const double *init,
+                                 int init_mode, double *fitness, int64_t *steps)
+{
+    tw_population_mpe_gru(0, parents, N, sigma, seed, gen, group, n_head, id0, n, E, max_cycles, W_override, init, init_mode, fitness, steps);
 }
 
 TW_EXPORT int tw_spread_policy(const float *w, int N, const float *o, float *logits) { return spread_policy(w, 6 * N, o, logits); }

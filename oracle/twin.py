@@ -34,6 +34,7 @@ def lib():
         _lib.tw_rollout_cartpole.restype = C.c_int64
         if hasattr(_lib, "tw_rollout_mpe"):
             _lib.tw_rollout_mpe.restype = C.c_double
+            _lib.tw_rollout_mpe_gru.restype = C.c_double
         if hasattr(_lib, "tw_rollout_classic"):
             _lib.tw_rollout_classic.restype = C.c_double
             _lib.tw_rollout_classic_gru.restype = C.c_double
@@ -248,29 +249,29 @@ def spread_policy(w, N, o):
     return int(a), logits
 
 
-def rollout_mpe(w, N=2, E=5, max_cycles=25, init=None, seed=0, init_mode=0, gen=0, idx=0, trace_steps=0):
+def rollout_mpe(w, N=2, E=5, max_cycles=25, init=None, seed=0, init_mode=0, gen=0, idx=0, trace_steps=0, gru=False):
     """One offspring.  Returns (fitness, steps, trace[trace_steps,4N], actions[trace_steps,N])."""
     w = _f32(w)
     init_a = None if init is None else _f64(init)
     trace = np.full((max(trace_steps, 1), 4 * N), np.nan, dtype=np.float64)
     acts = np.full((max(trace_steps, 1), N), -1, dtype=np.int32)
     steps = C.c_int64(0)
-    f = lib().tw_rollout_mpe(_p(w), C.c_int(N), C.c_int(E), C.c_int(max_cycles), _p(init_a), C.c_uint32(seed),
-                             C.c_int(init_mode), C.c_uint32(gen), C.c_uint32(idx), _p(trace), _p(acts), C.c_int(trace_steps),
-                             C.byref(steps))
+    f = lib().tw_rollout_mpe_gru(C.c_int(int(bool(gru))), _p(w), C.c_int(N), C.c_int(E), C.c_int(max_cycles), _p(init_a), C.c_uint32(seed),
+                                 C.c_int(init_mode), C.c_uint32(gen), C.c_uint32(idx), _p(trace), _p(acts), C.c_int(trace_steps),
+                                 C.byref(steps))
     return float(f), int(steps.value), trace[:trace_steps], acts[:trace_steps]
 
 
 def population_mpe(parents, N=2, sigma=0.0, seed=0, gen=0, group=1, n_head=1, id0=0, n=1, E=5, max_cycles=25,
-                   W_override=None, init=None, init_mode=0):
+                   W_override=None, init=None, init_mode=0, gru=False):
     parents = _f32(parents)
     Wo = None if W_override is None else _f32(W_override)
     init_a = None if init is None else _f64(init)
     fit = np.empty(n, dtype=np.float64)
     steps = np.empty(n, dtype=np.int64)
-    lib().tw_population_mpe(_p(parents), C.c_int(N), C.c_float(sigma), C.c_uint32(seed), C.c_uint32(gen), C.c_int(group),
-                            C.c_int(n_head), C.c_int(id0), C.c_int(n), C.c_int(E), C.c_int(max_cycles), _p(Wo), _p(init_a),
-                            C.c_int(init_mode), _p(fit), _p(steps))
+    lib().tw_population_mpe_gru(C.c_int(int(bool(gru))), _p(parents), C.c_int(N), C.c_float(sigma), C.c_uint32(seed), C.c_uint32(gen),
+                                C.c_int(group), C.c_int(n_head), C.c_int(id0), C.c_int(n), C.c_int(E), C.c_int(max_cycles), _p(Wo),
+                                _p(init_a), C.c_int(init_mode), _p(fit), _p(steps))
     return fit, steps
 
 

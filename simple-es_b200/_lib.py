@@ -9,7 +9,7 @@ _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.environ.get("SES_B200_LIB") or os.path.join(_PKG, "libses_b200.so")
 SOURCES = [os.path.join(_PKG, "csrc", f) for f in (
     "ses_abi.cu", "ses_common.cuh", "rollout_slots.cuh", "rollout_cartpole_mlp.cuh", "rollout_cartpole_gru.cuh", "rollout_mpe.cuh",
-    "rollout_classic.cuh",
+    "rollout_classic.cuh", "rollout_gru_generic.cuh",
     "rank.cuh", "update.cuh")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-fmad=false",           # numerical contract: FMAs only where written

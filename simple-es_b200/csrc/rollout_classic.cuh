@@ -143,12 +143,23 @@ struct MountainCarEnv {
     template <int S>
     __device__ static __forceinline__ void bind(State &, const float4 (&)[NQ][S], int) {}
 
+    // the env seen by a policy kernel: observations of every agent, and one step under the chosen actions
+    static constexpr int OBS_EFF = OBS;
+    static constexpr bool CONTINUOUS = false;
+    __device__ static __forceinline__ void observe(const State &s, float (&o)[N_AGENTS][OBS_EFF]) { o[0][0] = (float)s.pos; o[0][1] = (float)s.vel; }
+
     template <int S>
     __device__ static __forceinline__ bool step(State &s, const float4 (&w)[NQ][S], int slot, const RolloutParams &, int *actions)
     {
-        const float o[OBS] = {(float)s.pos, (float)s.vel};
-        const int a = mlp_policy_flat<OBS, ACT, NQ, S>(w, slot, o);
-        actions[0] = a;
+        float o[N_AGENTS][OBS_EFF];
+        observe(s, o);
+        actions[0] = mlp_policy_flat<OBS, ACT, NQ, S>(w, slot, o[0]);
+        return advance(s, actions);
+    }
+
+    __device__ static __forceinline__ bool advance(State &s, const int *actions)
+    {
+        const int a = actions[0];
         double v = __dadd_rn(s.vel, __dadd_rn(__dmul_rn((double)(a - 1), 0.001), __dmul_rn(cos64_full(__dmul_rn(3.0, s.pos)), -0.0025)));
         v = clip64(v, -0.07, 0.07);
         double x = clip64(__dadd_rn(s.pos, v), -1.2, 0.6);
@@ -192,16 +203,31 @@ struct PendulumEnv {
     template <int S>
     __device__ static __forceinline__ void bind(State &, const float4 (&)[NQ][S], int) {}
 
-    template <int S>
-    __device__ static __forceinline__ bool step(State &s, const float4 (&w)[NQ][S], int slot, const RolloutParams &, int *actions)
+    static constexpr int OBS_EFF = OBS;
+    static constexpr bool CONTINUOUS = true;
+    __device__ static __forceinline__ void observe(const State &s, float (&o)[N_AGENTS][OBS_EFF])
     {
         double sn, cs;
         sincos64_full(s.th, sn, cs);
-        const float o[OBS] = {(float)cs, (float)sn, (float)s.thd};
+        o[0][0] = (float)cs; o[0][1] = (float)sn; o[0][2] = (float)s.thd;
+    }
+
+    template <int S>
+    __device__ static __forceinline__ bool step(State &s, const float4 (&w)[NQ][S], int slot, const RolloutParams &, int *actions)
+    {
+        float o[N_AGENTS][OBS_EFF];
+        observe(s, o);
         float z[ACT];
-        mlp_logits_flat<OBS, ACT, NQ, S>(w, slot, o, z);
+        mlp_logits_flat<OBS, ACT, NQ, S>(w, slot, o[0], z);
         const float uf = tanh32_fast_t<false>(z[0]);                   // == the contract's tanh32 for every input (exhaustive test)
         actions[0] = __float_as_int(uf);                               // traces carry the float32 action's bit pattern
+        return advance(s, actions);
+    }
+
+    // actions[0]: bit pattern of the float32 action in (-1, 1)
+    __device__ static __forceinline__ bool advance(State &s, const int *actions)
+    {
+        const float uf = __int_as_float(actions[0]);
         const double u = clip64((double)uf, -2.0, 2.0);
         double m = fmod(__dadd_rn(s.th, PI), __dmul_rn(2.0, PI));      // Python's float %: fmod, then the divisor's sign
         if (m < 0.0) m = __dadd_rn(m, __dmul_rn(2.0, PI));
@@ -282,12 +308,26 @@ struct AcrobotEnv {
         return x;
     }
 
+    static constexpr int OBS_EFF = OBS;
+    static constexpr bool CONTINUOUS = false;
+    __device__ static __forceinline__ void observe(const State &st, float (&o)[N_AGENTS][OBS_EFF])
+    {
+        o[0][0] = (float)st.sc[1]; o[0][1] = (float)st.sc[0]; o[0][2] = (float)st.sc[3]; o[0][3] = (float)st.sc[2];
+        o[0][4] = (float)st.s[2]; o[0][5] = (float)st.s[3];
+    }
+
     template <int S>
     __device__ static __forceinline__ bool step(State &st, const float4 (&w)[NQ][S], int slot, const RolloutParams &, int *actions)
     {
-        const float o[OBS] = {(float)st.sc[1], (float)st.sc[0], (float)st.sc[3], (float)st.sc[2], (float)st.s[2], (float)st.s[3]};
-        const int act = mlp_policy_flat<OBS, ACT, NQ, S>(w, slot, o);
-        actions[0] = act;
+        float o[N_AGENTS][OBS_EFF];
+        observe(st, o);
+        actions[0] = mlp_policy_flat<OBS, ACT, NQ, S>(w, slot, o[0]);
+        return advance(st, actions);
+    }
+
+    __device__ static __forceinline__ bool advance(State &st, const int *actions)
+    {
+        const int act = actions[0];
         const double torque = (double)(act - 1);
         const double dt = 0.2, dt2 = 0.2 / 2.0;
         double k1[4], k2[4], k3[4], k4[4], y[4];

@@ -127,11 +127,10 @@ struct SpreadEnv {
     template <int S>
     __device__ static __forceinline__ void bind(State &, const float4 (&)[NQ][S], int) {}
 
-    template <int S>
-    __device__ static __forceinline__ bool step(State &s, const float4 (&w)[NQ][S], int slot, const RolloutParams &, int *actions)
+    static constexpr bool CONTINUOUS = false;
+    // observations (Scenario.observation): [vel, pos, landmarks - pos, others - pos, comm = 0], f64 -> f32
+    __device__ static __forceinline__ void observe(const State &s, float (&o)[N][OBS_EFF])
     {
-        // observations (Scenario.observation): [vel, pos, landmarks - pos, others - pos, comm = 0], f64 -> f32
-        float o[N][OBS_EFF];
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             int c = 0;
@@ -149,6 +148,13 @@ struct SpreadEnv {
                     o[i][c++] = (float)__dsub_rn(s.apos[j][1], s.apos[i][1]);
                 }
         }
+    }
+
+    template <int S>
+    __device__ static __forceinline__ bool step(State &s, const float4 (&w)[NQ][S], int slot, const RolloutParams &, int *actions)
+    {
+        float o[N][OBS_EFF];
+        observe(s, o);
         // shared MLP, all agents off the same weight loads; logits in the contract's sequential order.
         // Agents 0 and 1 run as the two halves of packed FFMA2 operations (same weight, two observations);
         // a third agent runs scalar.  Same operations, same order, one rounding each as the oracle.
@@ -242,7 +248,12 @@ struct SpreadEnv {
                 if (__fsub_rn(zmax, z[i][m]) <= __uint_as_float(0x33000000u)) a = m;
             actions[i] = a;
         }
-        // world step (MPE core.World.step)
+        return advance(s, actions);
+    }
+
+    // world step (MPE core.World.step) under the agents' actions + the team reward
+    __device__ static __forceinline__ bool advance(State &s, const int *actions)
+    {
         double F[N][2];
 #pragma unroll
         for (int i = 0; i < N; ++i) {

@@ -16,6 +16,7 @@
 #include "rollout_cartpole_gru.cuh"
 #include "rollout_mpe.cuh"
 #include "rollout_classic.cuh"
+#include "rollout_gru_generic.cuh"
 #include "ses_common.cuh"
 #include "update.cuh"
 
@@ -124,17 +125,15 @@ extern "C" int ses_create(const ses_config *cfg, ses_handle **out)
         return fail("ses_create: Pendulum-v0 needs num_state=3, num_action=1 (got %d, %d)", cfg->obs_dim, cfg->act_dim);
     if ((cfg->env == SES_ENV_PENDULUM) != (cfg->continuous_action != 0))
         return fail("ses_create: the continuous-action head (discrete_action: False) is implemented for Pendulum-v0, and Pendulum-v0 needs it");
-    if (cfg->env == SES_ENV_PENDULUM && (cfg->gru || cfg->pomdp))
-        return fail("ses_create: Pendulum-v0 runs with the MLP policy and full observations only");
-    if ((cfg->env == SES_ENV_MOUNTAINCAR || cfg->env == SES_ENV_ACROBOT) && (cfg->gru || cfg->pomdp))
-        return fail("ses_create: MountainCar-v0 / Acrobot-v1 run with the MLP policy and full observations only");
+    // envs/gym_wrapper.py:11-19: the reference's POMDP wrapper exists for LunarLander and CartPole only (AssertionError otherwise)
+    if ((cfg->env == SES_ENV_MOUNTAINCAR || cfg->env == SES_ENV_ACROBOT || cfg->env == SES_ENV_PENDULUM) && cfg->pomdp)
+        return fail("ses_create: only CartPole supports pomdp (envs/gym_wrapper.py:11-19 raises for every other env)");
     if (cfg->env == SES_ENV_CARTPOLE && (cfg->obs_dim != 4 || cfg->act_dim != 2))
         return fail("ses_create: CartPole-v1 needs num_state=4, num_action=2 (got %d, %d)", cfg->obs_dim, cfg->act_dim);
     if (cfg->env == SES_ENV_SIMPLE_SPREAD) {
         if (cfg->n_agents < 2 || cfg->n_agents > 3) return fail("ses_create: simple_spread supports N=2 or N=3 agents (got %d)", cfg->n_agents);
         if (cfg->obs_dim != 6 * cfg->n_agents || cfg->act_dim != 5)
             return fail("ses_create: simple_spread N=%d needs num_state=%d, num_action=5", cfg->n_agents, 6 * cfg->n_agents);
-        if (cfg->gru) return fail("ses_create: simple_spread GRU policy is not implemented in the GPU engine");
     }
     if (cfg->eval_ep_num < 1 || cfg->eval_ep_num > 32) return fail("ses_create: eval_ep_num must be in [1, 32] (got %d)", cfg->eval_ep_num);
     if (cfg->population < 2) return fail("ses_create: population must be >= 2");
@@ -372,6 +371,16 @@ extern "C" int ses_rollout(ses_handle *h, uint32_t generation, float sigma, cons
         return launch_slots<CartpoleMlpEnvT<7>, 32>(h, rp, need_warps, tr, st);
     }
     if (c.env == SES_ENV_CARTPOLE && c.gru) return launch_rollout_cartpole_gru(h->num_sms, h->ctas_per_sm, rp, tr, st, &h->launches, g_err, sizeof(g_err));
+    if (c.gru) {            // the recurrent policy on every other env: one generic warp-per-offspring kernel (rollout_gru_generic.cuh)
+        switch (c.env) {
+        case SES_ENV_MOUNTAINCAR: return launch_rollout_gru_generic<MountainCarEnv>(h->num_sms, h->ctas_per_sm, rp, tr, st, &h->launches, g_err, sizeof(g_err));
+        case SES_ENV_ACROBOT: return launch_rollout_gru_generic<AcrobotEnv>(h->num_sms, h->ctas_per_sm, rp, tr, st, &h->launches, g_err, sizeof(g_err));
+        case SES_ENV_PENDULUM: return launch_rollout_gru_generic<PendulumEnv>(h->num_sms, h->ctas_per_sm, rp, tr, st, &h->launches, g_err, sizeof(g_err));
+        default:
+            if (c.n_agents == 2) return launch_rollout_gru_generic<SpreadEnv<2>>(h->num_sms, h->ctas_per_sm, rp, tr, st, &h->launches, g_err, sizeof(g_err));
+            return launch_rollout_gru_generic<SpreadEnv<3>>(h->num_sms, h->ctas_per_sm, rp, tr, st, &h->launches, g_err, sizeof(g_err));
+        }
+    }
     if (c.env == SES_ENV_MOUNTAINCAR) return launch_slots_by_E<MountainCarEnv>(h, rp, need_warps, tr, st);
     if (c.env == SES_ENV_ACROBOT) return launch_slots_by_E<AcrobotEnv>(h, rp, need_warps, tr, st);
     if (c.env == SES_ENV_PENDULUM) return launch_slots_by_E<PendulumEnv>(h, rp, need_warps, tr, st);

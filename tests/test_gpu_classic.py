@@ -109,8 +109,8 @@ def test_classic_engine_rejects_wrong_shapes():
     from simple_es_b200.engine import RolloutEngine
     with pytest.raises(ValueError, match="num_state=2"):
         RolloutEngine("MountainCar-v0", 4, 2, False, False, 200, 5, 64, 64, 1, 1)
-    with pytest.raises(RuntimeError, match="MLP policy"):
-        RolloutEngine("Acrobot-v1", 6, 3, True, False, 500, 5, 64, 64, 1, 1)
+    with pytest.raises(RuntimeError, match="only CartPole supports pomdp"):          # envs/gym_wrapper.py:11-19
+        RolloutEngine("Acrobot-v1", 6, 3, False, True, 500, 5, 64, 64, 1, 1)
 
 
 @pytest.mark.parametrize("conf,env,ngen", [("mountaincar.yaml", "MountainCar-v0", 3), ("acrobot.yaml", "Acrobot-v1", 3)])
