@@ -121,6 +121,10 @@ class ClockSampler:
 # CPU legs (oracle; allowed importers of oracle/: tests, smoke, and these two functions)
 # ----------------------------------------------------------------------------------------------
 STATE_FIXTURE = os.path.join(ROOT, "tests", "golden", "bench_state_gen30.npz")
+CALIBRATION = ("calibration (profiles/r02_reference_calibration.json, tools/calibrate_reference.py, dev container, 8 cores, same 365-offspring "
+               "sample): the UNMODIFIED reference ESLoop + openai_es + GymEnvModel + RolloutWorker runs 93.7 k env-steps/s where this "
+               "port runs 131 k -- the port is 1.40x faster than the reference's own code (it ships flat weight vectors instead of "
+               "deep-copied, pickled nn.Modules), so ratios against it are conservative")
 REGIME = ("population drawn around the generation-30 state of this very workload (tests/golden/bench_state_gen30.npz, "
           "tools/make_bench_fixture.py): episodes of ~500 steps, the regime the GPU arm's timed generations run in")
 CPU_SEC_PER_OFFSPRING = 0.21   # 5 episodes x 500 steps x ~85 us per reference policy-forward + env step on one core
@@ -193,7 +197,7 @@ def run_reference(args):
         tot_steps += s; tot_t += dt
     v = tot_steps / tot_t
     sample = ("each step = 1 generation of the reference CPU path (oracle/pyref.py port, mp.Pool(%d)) on %d offspring x %d "
-              "episodes (bounded sample of the 65536 population); %s" % (cores, n, E_DEFAULT, REGIME))
+              "episodes (bounded sample of the 65536 population); %s; %s" % (cores, n, E_DEFAULT, REGIME, CALIBRATION))
     line = {
         "impl": "reference", "metric": "env-steps/sec", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, args.steps),

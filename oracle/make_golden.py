@@ -93,13 +93,44 @@ def golden_rollout(ref, gru, pomdp, P, E, seed, sigma, n_trace):
     # trace the offspring whose first episode is longest (first 200 steps of episode 0)
     trace_ids = np.argsort([-len(l) for l in logs], kind="stable")[:n_trace].astype(np.int32)
     traces = np.full((n_trace, 200, 4), np.nan)
-    tr_actions = np.full((n_trace, 200), -1, dtype=np.int32) if discrete else np.full((n_trace, 200), np.nan, dtype=np.float32)
+    tr_actions = np.full((n_trace, 200), -1, dtype=np.int32)
     for j, i in enumerate(trace_ids):
         for t, rec in enumerate(logs[i][:200]):
             tr_actions[j, t] = rec[0]
             traces[j, t] = rec[1]
     return dict(W=W, init=init, fitness=fitness, trace_ids=trace_ids, traces=traces, trace_actions=tr_actions,
                 gru=np.int32(gru), pomdp=np.int32(pomdp), E=np.int32(E), max_step=np.int32(500))
+
+
+def large_population(seed, P, D=226):
+    """The weights of the large CartPole golden set, regenerated from the seed by the tests (numpy's legacy RandomState stream is
+    frozen): the first half random policies (sigma 2, episodes of ~10-60 steps), the second half perturbations (sigma 0.3) of a
+    hand-built balancing parent (episodes from a few steps up to the 500-step limit)."""
+    rng = np.random.RandomState(seed)
+    init = rng.uniform(-0.05, 0.05, size=(5, 4))
+    W = rng.normal(0, 2.0, size=(P, D)).astype(np.float32)
+    base = np.zeros(D, np.float32)
+    base[:128].reshape(32, 4)[0] = [0.0, 0.5, 10.0, 3.0]
+    base[160:224].reshape(2, 32)[1, 0] = 5.0
+    base[160:224].reshape(2, 32)[0, 0] = -5.0
+    W[P // 2:] = base + (W[P // 2:] * np.float32(0.15))
+    return init, W
+
+
+def golden_rollout_large(ref, P, seed):
+    """>= 4096 offspring so that 'at least 99.9 % of the returns equal the reference's' means something.
+    Only the returns are stored (32 kB); tests rebuild the weights with large_population()."""
+    init, W = large_population(seed, P)
+    E = 5
+    fitness = np.zeros(P)
+    for i in range(P):
+        model = ref.GymEnvModel(4, 2, True, False)
+        set_flat(model, W[i], 4, 2, False)
+        env = pyref.CartPoleShim(max_step=500, init_states=init)
+        fitness[i] = ref.RolloutWorker((env, {"0": model}, E))
+    import zlib
+    return dict(seed=np.int64(seed), P=np.int32(P), E=np.int32(E), fitness=fitness, init=init,
+                w_crc32=np.uint32(zlib.crc32(np.ascontiguousarray(W).tobytes())))
 
 
 class TracingSpread(pyref.SimpleSpreadShim):
@@ -218,7 +249,21 @@ def reward_vectors(P, rng):
     return [r0, r1, r2]
 
 
-def golden_strategy(ref, name, seed):
+def alias_reward_vectors(P, rng):
+    """simple_evolution's object aliasing (offspring_strategies.py:165-176,232-250: population slots 0 and 1 are `mu_model` and
+    `elite_models[0]`, the SAME module at generation 0 and whenever slot 0 or 1 won the previous generation; the elite sum runs in
+    place on the winner's storage).  Four generations that put the two aliased slots into the elite set in every position:
+    first and second (generation 0: the all-zero network added to itself; generation 1: non-zero weights, x += x), in the middle
+    of the elites behind another winner, and inside a larger group of tied rewards."""
+    base = lambda: rng.uniform(8, 400, size=P)
+    r0 = base(); r0[0] = r0[1] = 500.0
+    r1 = base(); r1[0] = r1[1] = 500.0
+    r2 = base(); r2[7] = 500.0; r2[0] = r2[1] = 450.0
+    r3 = base(); r3[[0, 1, 5, 9]] = 500.0
+    return [r0, r1, r2, r3]
+
+
+def golden_strategy(ref, name, seed, rewards_fn=None):
     obs_dim, act, gru = 4, 2, False
     D = pyref.param_count(obs_dim, act, gru)
     np.random.seed(seed)
@@ -238,8 +283,9 @@ def golden_strategy(ref, name, seed):
     out = {"cfg_" + k: np.float64(v) for k, v in cfg.items()}
     rng = np.random.RandomState(seed + 1)
     P = len(group)
-    rews = reward_vectors(P, rng)
+    rews = (rewards_fn or reward_vectors)(P, rng)
     out["P"] = np.int32(P)
+    out["generations"] = np.int32(len(rews))
     for g, rewards in enumerate(rews):
         pop = np.stack([flat_of(off["0"]) for off in group])
         out["pop_%d" % g] = pop
@@ -283,6 +329,7 @@ def main():
         "policy_mlp": lambda: golden_policy(ref, False, 48, 32, 11),
         "policy_gru": lambda: golden_policy(ref, True, 12, 40, 12),
         "rollout_cartpole_mlp": lambda: golden_rollout(ref, False, False, 256, 5, 21, 2.0, 6),
+        "rollout_cartpole_mlp_4096": lambda: golden_rollout_large(ref, 4096, 71),
         "rollout_cartpole_gru_pomdp": lambda: golden_rollout(ref, True, True, 24, 3, 22, 0.7, 3),
         "rollout_spread_n2": lambda: golden_spread(ref, 2, 128, 5, 41, 1.0, 4),
         "rollout_spread_n3": lambda: golden_spread(ref, 3, 48, 3, 42, 1.0, 2),
@@ -296,6 +343,7 @@ def main():
         "rollout_pendulum_gru": lambda: golden_classic(ref, "Pendulum-v0", 24, 2, 64, 0.5, 4, gru=True),
         "rollout_acrobot_gru": lambda: golden_classic(ref, "Acrobot-v1", 16, 2, 65, 0.7, 2, gru=True),
         "strategy_simple_evolution": lambda: golden_strategy(ref, "simple_evolution", 31),
+        "strategy_simple_evolution_alias": lambda: golden_strategy(ref, "simple_evolution", 34, alias_reward_vectors),
         "strategy_simple_genetic": lambda: golden_strategy(ref, "simple_genetic", 32),
         "strategy_openai_es": lambda: golden_strategy(ref, "openai_es", 33),
     }

@@ -135,6 +135,21 @@ def test_rollout_trained_parent_long_episodes(twin):
     assert (ts == 500 * E).mean() > 0.5
 
 
+def test_rollout_4096_offspring_match_reference_returns(twin, golden):
+    """The reference's own weight arrays at population 4096 (tests/golden/rollout_cartpole_mlp_4096.npz: returns of the
+    reference's RolloutWorker + GymEnvModel): >= 99.9 % of the returns exactly equal (north_star), and every return equal to
+    the twin's."""
+    from test_oracle_cartpole import large_golden
+    init, W, want = large_golden(golden)
+    P = W.shape[0]
+    eng = _engine(population=P, group=P, n_head=1, eval_ep_num=5)
+    fit, steps = eng.rollout(0, 0.0, None, w_override=_cuda(W), init_states=_cuda(init))
+    fit = fit.cpu().numpy()
+    assert (fit == want).mean() >= 0.999
+    tf, ts = twin.population_cartpole(np.zeros((1, 226), np.float32), n=P, E=5, W_override=W, init=init, nthreads=8)
+    assert np.array_equal(fit, tf) and np.array_equal(steps.cpu().numpy(), ts)
+
+
 def test_rollout_verification_mode_matches_reference(twin, golden):
     """The engine consumes the reference's own weight arrays and initial states (north_star
     verification mode).  Golden = reference RolloutWorker + GymEnvModel (torch CPU)."""
@@ -316,6 +331,13 @@ def test_elite_mean_and_genetic_carry_over(twin, golden):
         order = eng.rank_desc(_cuda(g["rewards_%d" % gen]), full_key=True)
         mu = eng.elite_mean(gen, 0.0, None, order, k, w_override=_cuda(g["pop_%d" % gen]))
         assert np.array_equal(mu.cpu().numpy(), g["mu_after_%d" % gen])              # bit-exact vs the reference
+    # the reference's aliased elites (slots 0 and 1 are one module summed onto itself; tests/test_oracle_strategy.py): same bits
+    ga = golden("strategy_simple_evolution_alias")
+    for gen in range(int(ga["generations"])):
+        order = eng.rank_desc(_cuda(ga["rewards_%d" % gen]), full_key=True)
+        assert np.array_equal(order.cpu().numpy()[:k], ga["elite_ids_%d" % gen])
+        mu = eng.elite_mean(gen, 0.0, None, order, k, w_override=_cuda(ga["pop_%d" % gen]))
+        assert np.array_equal(mu.cpu().numpy(), ga["mu_after_%d" % gen])
     # Philox mode vs the twin
     rng = np.random.default_rng(4)
     parent = rng.normal(0, 1, (1, D)).astype(np.float32)

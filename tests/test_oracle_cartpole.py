@@ -100,6 +100,36 @@ def test_rollout_golden_mlp(twin, golden):
     _check_rollout_golden(twin, golden("rollout_cartpole_mlp"))
 
 
+def large_golden(golden):
+    """(init, W, reference returns) of tests/golden/rollout_cartpole_mlp_4096.npz; the weights are rebuilt from the seed exactly as
+    oracle/make_golden.py::large_population drew them (numpy's legacy RandomState stream is frozen) and checked by CRC."""
+    import zlib
+    g = golden("rollout_cartpole_mlp_4096")
+    P, seed = int(g["P"]), int(g["seed"])
+    rng = np.random.RandomState(seed)
+    init = rng.uniform(-0.05, 0.05, size=(5, 4))
+    W = rng.normal(0, 2.0, size=(P, 226)).astype(np.float32)
+    base = np.zeros(226, np.float32)
+    base[:128].reshape(32, 4)[0] = [0.0, 0.5, 10.0, 3.0]
+    base[160:224].reshape(2, 32)[1, 0] = 5.0
+    base[160:224].reshape(2, 32)[0, 0] = -5.0
+    W[P // 2:] = base + (W[P // 2:] * np.float32(0.15))
+    assert zlib.crc32(np.ascontiguousarray(W).tobytes()) == int(g["w_crc32"]) and np.array_equal(init, g["init"])
+    return init, W, g["fitness"]
+
+
+def test_rollout_golden_mlp_4096_offspring(twin, golden):
+    """the 99.9 % criterion on a population where it has teeth -- 4096 offspring, half random policies (short
+    ragged episodes), half perturbations of a balancing parent (episodes up to the 500-step limit), returns of the reference's
+    RolloutWorker + GymEnvModel (torch).  At most 4 offspring may differ (a near-tie action flip against torch's own tanh)."""
+    init, W, want = large_golden(golden)
+    fit, steps = twin.population_cartpole(np.zeros((1, 226), np.float32), n=W.shape[0], E=5, W_override=W, init=init, nthreads=8)
+    same = fit == want
+    assert same.mean() >= 0.999, (int((~same).sum()), np.flatnonzero(~same)[:10])
+    assert np.array_equal(steps, (fit * 5).round().astype(np.int64))
+    assert (want == 500).sum() > 1000 and (want < 30).sum() > 1000                 # both regimes are in the set
+
+
 def test_rollout_golden_gru_pomdp(twin, golden):
     _check_rollout_golden(twin, golden("rollout_cartpole_gru_pomdp"))
 

@@ -153,3 +153,26 @@ def test_sgd_twin_matches_numpy_restatement(twin):
     # momentum 0: plain SGD, theta += -stepsize * g
     t0, v0 = twin.sgd(tt, tv, g, 0.05, 0.0)
     assert np.array_equal(v0, g) and np.array_equal(t0, tt + np.float32(-0.05) * g)
+
+
+def test_elite_mean_with_aliased_elites_bit_exact(twin, golden):
+    """VERDICT r1 missing #4: population slots 0 and 1 of simple_evolution are `mu_model` and `elite_models[0]` -- one and the
+    same module at generation 0 and after every generation one of them wins -- and the reference sums the elites IN PLACE on
+    the winner's storage (offspring_strategies.py:241-248).  Under the pinned (stable) tie order the two aliased slots are
+    always adjacent in the ranking, so the aliased update `x += x` equals adding an equal copy: the reference's own result
+    (golden from its unmodified classes, rewards built to make the aliased slots elites in every position) is the plain
+    sequential float32 elite mean the engine computes, bit for bit, in all four generations."""
+    g = golden("strategy_simple_evolution_alias")
+    G, k = int(g["generations"]), int(g["cfg_elite_num"])
+    assert G == 4
+    for gen in range(G):
+        ids = g["elite_ids_%d" % gen]
+        assert np.array_equal(twin.rank_desc(g["rewards_%d" % gen])[:k], ids)
+        assert {0, 1} <= set(int(i) for i in ids)                                   # both aliased slots are elites
+        pop = g["pop_%d" % gen]
+        assert np.array_equal(pop[0], pop[1])                                       # ... and numerically identical (Q2)
+        mu = twin.elite_mean(pop[ids])
+        assert np.array_equal(mu, g["mu_after_%d" % gen])
+        nxt = g["pop_%d" % (gen + 1)] if gen < G - 1 else g["pop_final"]
+        assert np.array_equal(nxt[0], mu) and np.array_equal(nxt[1], mu)
+    assert np.abs(g["mu_after_1"]).max() > 0.1                                       # non-zero weights were summed onto themselves

@@ -331,6 +331,10 @@ def test_emu_elite_mean_and_genetic_carry_over(emu, twin, golden):
     for gen in range(3):                                           # verification mode: the reference's populations
         order = eng.rank_desc(g["rewards_%d" % gen], full_key=True)
         assert np.array_equal(eng.elite_mean(gen, 0.0, None, order, k, w_override=g["pop_%d" % gen]), g["mu_after_%d" % gen])
+    ga = golden("strategy_simple_evolution_alias")                 # the reference's aliased elite slots: same bits
+    for gen in range(int(ga["generations"])):
+        order = eng.rank_desc(ga["rewards_%d" % gen], full_key=True)
+        assert np.array_equal(eng.elite_mean(gen, 0.0, None, order, k, w_override=ga["pop_%d" % gen]), ga["mu_after_%d" % gen])
     rng = np.random.default_rng(4)
     parent = rng.normal(0, 1, (1, D)).astype(np.float32)
     eng = emu(population=97, group=97, n_head=2, seed=8)
