@@ -7,6 +7,9 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 # SES_B200_LIB: an alternative build of the same sources (A/B timing of compile-time choices; tools/ only)
 LIB_PATH = os.environ.get("SES_B200_LIB") or os.path.join(_PKG, "libses_b200.so")
+# the -DSES_BUILD_TESTS build (include/ses_b200_test.h): test hooks + the alternative kernels behind SES_K1_VARIANT,
+# SES_GRU_VARIANT, SES_K2_FUSED, SES_SPREAD_SLOTS8.  Loaded by tests/ and tools/ only (RolloutEngine(test_build=True)).
+TEST_LIB_PATH = os.path.join(_PKG, "libses_b200_tests.so")
 SOURCES = [os.path.join(_PKG, "csrc", f) for f in (
     "ses_abi.cu", "ses_common.cuh", "rollout_slots.cuh", "rollout_cartpole_mlp.cuh", "rollout_cartpole_gru.cuh", "rollout_mpe.cuh",
     "rollout_classic.cuh", "rollout_gru_generic.cuh",
@@ -45,52 +48,74 @@ SYMBOLS = {
     "ses_peer_fitness_ptr": (C.c_int, [_vp, _i32, C.POINTER(_vp)]),
     "ses_peer_barrier": (C.c_int, [_vp, _vp]),
     "ses_peer_check": (C.c_int, [_vp]),
+    "ses_measure_fp32_peak": (C.c_int, [_i32, C.POINTER(C.c_double)]),
+    "ses_measure_fp32x2_peak": (C.c_int, [_i32, C.POINTER(C.c_double)]),
+    "ses_set_step_counter": (C.c_int, [_vp, _vp]),
+    "ses_launch_count": (_i64, [_vp]),
+}
+# include/ses_b200_test.h: only in the test build
+TEST_SYMBOLS = {
     "ses_test_math": (C.c_int, [_i32, _vp, _vp, _i64, _vp]),
     "ses_test_normals": (C.c_int, [_vp, _u32, _i32, _vp, _vp]),
     "ses_test_div_total_mass": (C.c_int, [C.c_uint64, C.POINTER(C.c_uint64)]),
     "ses_test_ddiv_fast": (C.c_int, [C.c_uint64, C.POINTER(C.c_uint64)]),
     "ses_test_tanh_fast_exhaustive": (C.c_int, [_f32, _f32, C.POINTER(C.c_uint64)]),
-    "ses_measure_fp32_peak": (C.c_int, [_i32, C.POINTER(C.c_double)]),
-    "ses_measure_fp32x2_peak": (C.c_int, [_i32, C.POINTER(C.c_double)]),
     "ses_test_tanh_x2_exhaustive": (C.c_int, [_i32, _f32, _f32, C.POINTER(C.c_uint64)]),
-    "ses_set_step_counter": (C.c_int, [_vp, _vp]),
-    "ses_launch_count": (_i64, [_vp]),
 }
 
 
-def build_library(force=False, verbose=False):
-    """Compile the CUDA library for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
-    if not force and os.path.exists(LIB_PATH) and all(
-            os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in SOURCES):
-        return LIB_PATH
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, SOURCES[0]]
-    subprocess.check_call(cmd, cwd=_ROOT)
-    return LIB_PATH
+def _nvcc_cmd(out, tests, verbose=False):
+    return (["nvcc"] + NVCC_FLAGS + (["-DSES_BUILD_TESTS"] if tests else []) + (["-Xptxas", "-v"] if verbose else []) +
+            ["-o", out, SOURCES[0]])
 
 
-_lib = None
+def _stale(path):
+    deps = SOURCES + [os.path.join(_ROOT, "include", "ses_b200.h"), os.path.join(_ROOT, "include", "ses_b200_test.h")]
+    return not os.path.exists(path) or any(os.path.getmtime(path) < os.path.getmtime(d) for d in deps)
 
 
-def load():
-    """Load libses_b200.so; no fallback -- a missing library is an error."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
+def build_library(force=False, verbose=False, tests=False):
+    """Compile the CUDA library for sm_100a in-tree (nvcc cross-compiles without a GPU).  tests=True builds
+    libses_b200_tests.so (-DSES_BUILD_TESTS) instead of the product library."""
+    path = TEST_LIB_PATH if tests else LIB_PATH
+    if force or _stale(path):
+        subprocess.check_call(_nvcc_cmd(path, tests, verbose), cwd=_ROOT)
+    return path
+
+
+def build_all(force=False):
+    """Product and test builds side by side (two nvcc processes)."""
+    jobs = [(p, subprocess.Popen(_nvcc_cmd(p, t), cwd=_ROOT)) for p, t in ((LIB_PATH, False), (TEST_LIB_PATH, True)) if force or _stale(p)]
+    for p, proc in jobs:
+        if proc.wait() != 0:
+            raise RuntimeError("nvcc failed for %s" % p)
+    return LIB_PATH, TEST_LIB_PATH
+
+
+_libs = {}
+
+
+def load(tests=False):
+    """Load libses_b200.so (tests=True: libses_b200_tests.so); no fallback -- a missing library is an error."""
+    if tests in _libs:
+        return _libs[tests]
+    path = TEST_LIB_PATH if tests else LIB_PATH
+    if not os.path.exists(path):
         raise RuntimeError(
             "simple-es_b200: %s is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
-            "(nvcc, sm_100a). The engine has no CPU fallback." % LIB_PATH)
-    lib = C.CDLL(LIB_PATH)
-    for name, (res, args) in SYMBOLS.items():
+            "(nvcc, sm_100a). The engine has no CPU fallback." % path)
+    lib = C.CDLL(path)
+    syms = dict(SYMBOLS, **TEST_SYMBOLS) if tests else SYMBOLS
+    for name, (res, args) in syms.items():
         fn = getattr(lib, name)          # AttributeError if the ABI is incomplete
         fn.restype = res
         fn.argtypes = args
     if lib.ses_abi_version() != 1:
         raise RuntimeError("simple-es_b200: ABI version mismatch")
-    _lib = lib
+    _libs[tests] = lib
     return lib
 
 
-def check(rc):
+def check(rc, lib=None):
     if rc != 0:
-        raise RuntimeError("simple-es_b200: " + load().ses_last_error().decode())
+        raise RuntimeError("simple-es_b200: " + (lib or load()).ses_last_error().decode())

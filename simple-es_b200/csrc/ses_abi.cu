@@ -2,6 +2,9 @@
 // Host side only does argument checking, scratch management and launches; there is no CPU
 // implementation of any entry point (no fallback): without a device every call fails.
 #include "../../include/ses_b200.h"
+#ifdef SES_BUILD_TESTS
+#include "../../include/ses_b200_test.h"
+#endif
 
 #include <cuda_runtime.h>
 
@@ -63,7 +66,7 @@ struct ses_handle {
     int *hist = nullptr;
     int *tot = nullptr;            // [8][256]
     int *hist_fused = nullptr;     // fused K2: [passes][tiles][256] tile histograms, zeroed per call
-    int k2_fused = 0;
+    int k2_fused = 1;
     double *part1 = nullptr;
     int nb0 = 0, nb1 = 0, n_tiles = 0;
     // scratch for the host-buffer generation path
@@ -176,11 +179,14 @@ extern "C" int ses_create(const ses_config *cfg, ses_handle **out)
     h->eff_max_step = cfg->max_step > 0 ? (cfg->max_step < env_cap ? cfg->max_step : env_cap) : env_cap;
     h->lanes_used_override = env_int("SES_ROLLOUT_LANES", 0);
     h->ctas_per_sm = env_int("SES_ROLLOUT_CTAS_PER_SM", 0);
+#ifdef SES_BUILD_TESTS
+    // alternative kernels exist only in the test build (include/ses_b200_test.h)
     h->k1_variant = env_int("SES_K1_VARIANT", 7);
     h->spread_slots8 = env_int("SES_SPREAD_SLOTS8", 0);
+    h->k2_fused = env_int("SES_K2_FUSED", 1);     // 1 + passes launches (default); 0: the separate kernels
+#endif
     h->k1_split = env_int("SES_K1_SPLIT", 1);
     h->k1_sparse = env_int("SES_K1_SPARSE", 1);
-    h->k2_fused = env_int("SES_K2_FUSED", 1);     // 1 + passes launches (default); 0: the separate kernels
     if (h->k1_variant < 0 || h->k1_variant > 7) h->k1_variant = 7;
 
     const int P = cfg->population;
@@ -358,14 +364,16 @@ extern "C" int ses_rollout(ses_handle *h, uint32_t generation, float sigma, cons
     if (c.env == SES_ENV_CARTPOLE && !c.gru) {
         // slots per warp: enough offspring to occupy 32 lanes (E >= 4: 8, E in {2,3}: 16, E = 1: 32)
         if (c.eval_ep_num >= 4) {
+#ifdef SES_BUILD_TESTS
             if (h->k1_variant == 0) return launch_slots<CartpoleMlpEnvT<0>, 8>(h, rp, need_warps, tr, st);
+            if (h->k1_variant == 1) return launch_slots<CartpoleMlpEnvT<1>, 8>(h, rp, need_warps, tr, st);
             if (h->k1_variant == 2) return launch_slots<CartpoleMlpEnvT<2>, 8>(h, rp, need_warps, tr, st);
             if (h->k1_variant == 3) return launch_slots<CartpoleMlpEnvT<3>, 8>(h, rp, need_warps, tr, st);
             if (h->k1_variant == 4) return launch_slots<CartpoleMlpEnvT<4>, 8>(h, rp, need_warps, tr, st);
             if (h->k1_variant == 5) return launch_slots<CartpoleMlpEnvT<5>, 8>(h, rp, need_warps, tr, st);
             if (h->k1_variant == 6) return launch_slots<CartpoleMlpEnvT<6>, 8>(h, rp, need_warps, tr, st);
-            if (h->k1_variant == 7) return launch_slots<CartpoleMlpEnvT<7>, 8>(h, rp, need_warps, tr, st);
-            return launch_slots<CartpoleMlpEnvT<1>, 8>(h, rp, need_warps, tr, st);
+#endif
+            return launch_slots<CartpoleMlpEnvT<7>, 8>(h, rp, need_warps, tr, st);
         }
         if (c.eval_ep_num >= 2) return launch_slots<CartpoleMlpEnvT<7>, 16>(h, rp, need_warps, tr, st);
         return launch_slots<CartpoleMlpEnvT<7>, 32>(h, rp, need_warps, tr, st);
@@ -555,6 +563,9 @@ extern "C" int ses_rank_desc(ses_handle *h, const double *fitness_dev, int32_t n
         CU(cudaGetLastError());
         return 0;
     }
+#ifndef SES_BUILD_TESTS
+    return fail("ses_rank_desc: the separate-kernel K2 path exists only in the test build");
+#else
     CU(cudaMemsetAsync(h->tot, 0, sizeof(int) * 8 * 256, st));
     k_sort_init<<<(n + 255) / 256, 256, 0, st>>>(fitness_dev, n, key_bits, key_scale, h->keys[0], vals[0]);
     h->launches += 1;
@@ -577,6 +588,7 @@ extern "C" int ses_rank_desc(ses_handle *h, const double *fitness_dev, int32_t n
     }
     CU(cudaGetLastError());
     return 0;
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -817,65 +829,6 @@ extern "C" int ses_generation_genetic_host(ses_handle *h, uint32_t generation, f
 }
 
 // ------------------------------------------------------------------------------------------------
-// test hooks
-// ------------------------------------------------------------------------------------------------
-__global__ void k_test_math(int kind, const void *in, void *out, long long n)
-{
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (kind <= 4 || kind == 7) {
-        const float x = static_cast<const float *>(in)[i];
-        float y = 0.0f, s, c;
-        switch (kind) {
-        case 0: y = tanh32(x); break;
-        case 1: y = sigm32(x); break;
-        case 2: y = ln32(x); break;
-        case 3: sincos2pi32(x, s, c); y = s; break;
-        case 7: y = tanh32_fast(x); break;
-        default: sincos2pi32(x, s, c); y = c; break;
-        }
-        static_cast<float *>(out)[i] = y;
-    } else {
-        const double x = static_cast<const double *>(in)[i];
-        double y;
-        if (kind == 5) y = sin64(x);
-        else if (kind == 6) y = cos64(x);
-        else { double s, c; sincos64_full(x, s, c); y = kind == 8 ? s : c; }
-        static_cast<double *>(out)[i] = y;
-    }
-}
-
-extern "C" int ses_test_math(int32_t kind, const void *in_dev, void *out_dev, int64_t n, void *stream)
-{
-    if (kind < 0 || kind > 9) return fail("ses_test_math: unknown kind %d", kind);
-    if (n < 1) return 0;
-    k_test_math<<<(unsigned)((n + 255) / 256), 256, 0, S(stream)>>>(kind, in_dev, out_dev, (long long)n);
-    CU(cudaGetLastError());
-    return 0;
-}
-
-__global__ void k_test_normals(uint32_t seed, uint32_t gen, uint32_t id, int D, float *out)
-{
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (4 * q >= D) return;
-    const float4 n = normal4(seed, (uint32_t)q, id, gen);
-    const int d = 4 * q;
-    out[d] = n.x;
-    if (d + 1 < D) out[d + 1] = n.y;
-    if (d + 2 < D) out[d + 2] = n.z;
-    if (d + 3 < D) out[d + 3] = n.w;
-}
-
-extern "C" int ses_test_normals(ses_handle *h, uint32_t generation, int32_t id, float *out_dev, void *stream)
-{
-    if (!h || !out_dev) return fail("ses_test_normals: null argument");
-    CU(cudaSetDevice(h->cfg.device));
-    k_test_normals<<<(h->NQ + 63) / 64, 64, 0, S(stream)>>>(h->cfg.seed, generation, (uint32_t)id, h->D, out_dev);
-    CU(cudaGetLastError());
-    return 0;
-}
-
-// ------------------------------------------------------------------------------------------------
 // FP32 pipe peak: dependent-free FFMA streams, the denominator of K1's roofline (bench.py)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_ffma_peak(float *out, int iters, float a, float b)
@@ -948,6 +901,66 @@ extern "C" int ses_measure_fp32_peak(int32_t device, double *tflops_out)
 {
     if (!tflops_out) return fail("ses_measure_fp32_peak: null argument");
     return measure_peak(device, tflops_out, false);
+}
+
+#ifdef SES_BUILD_TESTS
+// ------------------------------------------------------------------------------------------------
+// test hooks
+// ------------------------------------------------------------------------------------------------
+__global__ void k_test_math(int kind, const void *in, void *out, long long n)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (kind <= 4 || kind == 7) {
+        const float x = static_cast<const float *>(in)[i];
+        float y = 0.0f, s, c;
+        switch (kind) {
+        case 0: y = tanh32(x); break;
+        case 1: y = sigm32(x); break;
+        case 2: y = ln32(x); break;
+        case 3: sincos2pi32(x, s, c); y = s; break;
+        case 7: y = tanh32_fast(x); break;
+        default: sincos2pi32(x, s, c); y = c; break;
+        }
+        static_cast<float *>(out)[i] = y;
+    } else {
+        const double x = static_cast<const double *>(in)[i];
+        double y;
+        if (kind == 5) y = sin64(x);
+        else if (kind == 6) y = cos64(x);
+        else { double s, c; sincos64_full(x, s, c); y = kind == 8 ? s : c; }
+        static_cast<double *>(out)[i] = y;
+    }
+}
+
+extern "C" int ses_test_math(int32_t kind, const void *in_dev, void *out_dev, int64_t n, void *stream)
+{
+    if (kind < 0 || kind > 9) return fail("ses_test_math: unknown kind %d", kind);
+    if (n < 1) return 0;
+    k_test_math<<<(unsigned)((n + 255) / 256), 256, 0, S(stream)>>>(kind, in_dev, out_dev, (long long)n);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+__global__ void k_test_normals(uint32_t seed, uint32_t gen, uint32_t id, int D, float *out)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (4 * q >= D) return;
+    const float4 n = normal4(seed, (uint32_t)q, id, gen);
+    const int d = 4 * q;
+    out[d] = n.x;
+    if (d + 1 < D) out[d + 1] = n.y;
+    if (d + 2 < D) out[d + 2] = n.z;
+    if (d + 3 < D) out[d + 3] = n.w;
+}
+
+extern "C" int ses_test_normals(ses_handle *h, uint32_t generation, int32_t id, float *out_dev, void *stream)
+{
+    if (!h || !out_dev) return fail("ses_test_normals: null argument");
+    CU(cudaSetDevice(h->cfg.device));
+    k_test_normals<<<(h->NQ + 63) / 64, 64, 0, S(stream)>>>(h->cfg.seed, generation, (uint32_t)id, h->D, out_dev);
+    CU(cudaGetLastError());
+    return 0;
 }
 
 // every float32 bit pattern b in [lo_bits, hi_bits]: tanh32_fast(x) must equal tanh32(x) bit for bit
@@ -1082,3 +1095,4 @@ extern "C" int ses_test_div_total_mass(uint64_t n, uint64_t *mismatches_host)
     *mismatches_host = r;
     return 0;
 }
+#endif  // SES_BUILD_TESTS

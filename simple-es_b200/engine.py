@@ -10,6 +10,7 @@ library's own sm_100a kernels.  Replaces, inside one generation of the reference
 """
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import torch
@@ -84,7 +85,7 @@ class RolloutEngine:
 
     def __init__(self, env_name, obs_dim, act_dim, gru, pomdp, max_step, eval_ep_num, population, group, n_head,
                  n_parents, seed=0, init_mode="shared", n_agents=2, id_begin=0, id_end=None, device=0, antithetic=False,
-                 shard=None, discrete_action=True):
+                 shard=None, discrete_action=True, test_build=None):
         """`shard` = (rank, world, block): block-cyclic slice instead of the contiguous [id_begin, id_end)."""
         if env_name not in ENV_IDS:
             raise ValueError(
@@ -95,7 +96,12 @@ class RolloutEngine:
                              "implemented for %s" % (env_name, env_name not in CONTINUOUS_ENVS, ", ".join(CONTINUOUS_ENVS)))
         if not torch.cuda.is_available():
             raise RuntimeError("simple-es_b200: no CUDA device; the engine has no CPU fallback")
-        self.lib = _lib.load()
+        # test_build: libses_b200_tests.so -- test hooks and the alternative kernels behind SES_K1_VARIANT & co (tests / tools only;
+        # SES_B200_TEST_BUILD=1 makes it the default of a process)
+        if test_build is None:
+            test_build = os.environ.get("SES_B200_TEST_BUILD", "0") not in ("", "0")
+        self.test_build = bool(test_build)
+        self.lib = _lib.load(tests=self.test_build)
         self.device = torch.device("cuda", device)
         self.P = int(population)
         self.id_begin = int(id_begin)
@@ -123,7 +129,7 @@ class RolloutEngine:
             shard_rank=self.shard[0] if self.shard else 0, shard_world=self.shard[1] if self.shard else 0,
             continuous_action=int(not discrete_action))
         h = C.c_void_p()
-        _lib.check(self.lib.ses_create(C.byref(self.cfg), C.byref(h)))
+        self._check(self.lib.ses_create(C.byref(self.cfg), C.byref(h)))
         self._h = h
         # integer-key fast path of K2: CartPole fitness*E is an integer < 2^key_bits
         # (CartPole: +1 per step; MountainCar / Acrobot: -1 or 0 per step => |fitness * E| <= E * max_step)
@@ -132,6 +138,14 @@ class RolloutEngine:
             self.key_scale = float(self.E)
         else:
             self.key_bits, self.key_scale = 0, 1.0
+
+    def _check(self, rc):
+        _lib.check(rc, self.lib)
+
+    def _hooks(self):
+        if not self.test_build:
+            raise RuntimeError("test hooks live in libses_b200_tests.so: construct the engine with test_build=True")
+        return self.lib
 
     def close(self):
         if getattr(self, "_h", None):
@@ -169,7 +183,7 @@ class RolloutEngine:
         """`counter`: 0-d / 1-element int64 CUDA tensor; every rollout() adds the env steps it simulated."""
         self._chk(counter, torch.int64, 1, "counter")
         self._step_counter = counter            # keep alive
-        _lib.check(self.lib.ses_set_step_counter(self._h, _ptr(counter)))
+        self._check(self.lib.ses_set_step_counter(self._h, _ptr(counter)))
 
     # ------------------------------------------------------------------------------ K1
     def rollout(self, generation, sigma, parents, fitness=None, steps=None, w_override=None, init_states=None,
@@ -191,7 +205,7 @@ class RolloutEngine:
             n_trace = min(n_trace, self.n_local)
             trace = torch.full((n_trace, 200, self.state_dim), float("nan"), dtype=torch.float64, device=dev)
             actions = torch.full((n_trace, 200, self.n_agents), -1, dtype=torch.int32, device=dev)
-        _lib.check(self.lib.ses_rollout(self._h, int(generation), float(sigma), _ptr(parents), _ptr(w_override),
+        self._check(self.lib.ses_rollout(self._h, int(generation), float(sigma), _ptr(parents), _ptr(w_override),
                                         _ptr(init_states), _ptr(fitness), _ptr(steps), _ptr(trace), _ptr(actions),
                                         int(n_trace), self._stream()))
         if n_trace > 0:
@@ -208,7 +222,7 @@ class RolloutEngine:
         if shaped and shaped_out is None:
             shaped_out = torch.empty(n, dtype=torch.float64, device=self.device)
         kb, ks = (0, 1.0) if full_key else (self.key_bits, self.key_scale)
-        _lib.check(self.lib.ses_rank_desc(self._h, _ptr(fitness), n, kb, ks, _ptr(order),
+        self._check(self.lib.ses_rank_desc(self._h, _ptr(fitness), n, kb, ks, _ptr(order),
                                           _ptr(shaped_out) if shaped else None, self._stream()))
         return (order, shaped_out) if shaped else order
 
@@ -226,7 +240,7 @@ class RolloutEngine:
         self._chk(shaped, torch.float64, self.P, "shaped")
         eps_override = self._chk(eps_override, torch.float32, self.P * self.D, "eps_override")
         uf = -1.0 * (lr / (self.P * sigma))              # offspring_strategies.py:406-408
-        _lib.check(self.lib.ses_update_openai(self._h, int(generation), _ptr(shaped), _ptr(eps_override), uf,
+        self._check(self.lib.ses_update_openai(self._h, int(generation), _ptr(shaped), _ptr(eps_override), uf,
                                               self.adam_a(lr, t, beta1, beta2), beta1, beta2, eps, _ptr(mu), _ptr(m),
                                               _ptr(v), _ptr(grad_out), self._stream()))
 
@@ -238,7 +252,7 @@ class RolloutEngine:
         self._chk(shaped, torch.float64, self.P, "shaped")
         eps_override = self._chk(eps_override, torch.float32, self.P * self.D, "eps_override")
         uf = -1.0 * (lr / (self.P * sigma))              # offspring_strategies.py:406-408
-        _lib.check(self.lib.ses_update_openai_sgd(self._h, int(generation), _ptr(shaped), _ptr(eps_override), uf, float(lr),
+        self._check(self.lib.ses_update_openai_sgd(self._h, int(generation), _ptr(shaped), _ptr(eps_override), uf, float(lr),
                                                   float(momentum), _ptr(mu), _ptr(v), _ptr(grad_out), self._stream()))
 
     def materialize(self, generation, sigma, parents, ids, w_override=None, out=None):
@@ -246,14 +260,14 @@ class RolloutEngine:
         n = ids.numel()
         if out is None:
             out = torch.empty((n, self.D), dtype=torch.float32, device=self.device)
-        _lib.check(self.lib.ses_materialize(self._h, int(generation), float(sigma), _ptr(parents), _ptr(w_override),
+        self._check(self.lib.ses_materialize(self._h, int(generation), float(sigma), _ptr(parents), _ptr(w_override),
                                             _ptr(ids), n, _ptr(out), self._stream()))
         return out
 
     def elite_mean(self, generation, sigma, parents, order, k, w_override=None, out=None):
         if out is None:
             out = torch.empty(self.D, dtype=torch.float32, device=self.device)
-        _lib.check(self.lib.ses_update_elite_mean(self._h, int(generation), float(sigma), _ptr(parents),
+        self._check(self.lib.ses_update_elite_mean(self._h, int(generation), float(sigma), _ptr(parents),
                                                   _ptr(w_override), _ptr(order), int(k), _ptr(out), self._stream()))
         return out
 
@@ -263,23 +277,23 @@ class RolloutEngine:
         channel (torch.distributed.all_gather_object).  Returns the two [P] float64 exchange tensors (double
         buffered by generation parity) that rollout() must be given as `fitness`."""
         mine = C.create_string_buffer(64)
-        _lib.check(self.lib.ses_peer_export(self._h, mine))
+        self._check(self.lib.ses_peer_export(self._h, mine))
         handles = all_gather_bytes(mine.raw)
         assert len(handles) == world and all(len(b) == 64 for b in handles)
         blob = C.create_string_buffer(b"".join(handles), 64 * world)
-        _lib.check(self.lib.ses_peer_attach(self._h, blob, int(rank), int(world)))
+        self._check(self.lib.ses_peer_attach(self._h, blob, int(rank), int(world)))
         bufs = []
         for parity in (0, 1):
             ptr = C.c_void_p()
-            _lib.check(self.lib.ses_peer_fitness_ptr(self._h, parity, C.byref(ptr)))
+            self._check(self.lib.ses_peer_fitness_ptr(self._h, parity, C.byref(ptr)))
             bufs.append(torch.as_tensor(_DeviceArray(ptr.value, self.P, "<f8"), device=self.device))
         return bufs
 
     def peer_barrier(self):
-        _lib.check(self.lib.ses_peer_barrier(self._h, self._stream()))
+        self._check(self.lib.ses_peer_barrier(self._h, self._stream()))
 
     def peer_check(self):
-        _lib.check(self.lib.ses_peer_check(self._h))
+        self._check(self.lib.ses_peer_check(self._h))
 
     # ------------------------------------------------------------------------------ host-buffer generation
     def generation_openai_host(self, generation, sigma, lr, t, mu, m, v, fitness):
@@ -288,7 +302,7 @@ class RolloutEngine:
         total = np.zeros(1, dtype=np.int64)
         for a, dt in ((mu, np.float32), (m, np.float32), (v, np.float32), (fitness, np.float64)):
             assert isinstance(a, np.ndarray) and a.dtype == dt and a.flags.c_contiguous
-        _lib.check(self.lib.ses_generation_openai_host(
+        self._check(self.lib.ses_generation_openai_host(
             self._h, int(generation), float(sigma), float(lr), int(t), C.c_void_p(mu.ctypes.data),
             C.c_void_p(m.ctypes.data), C.c_void_p(v.ctypes.data), C.c_void_p(fitness.ctypes.data),
             C.c_void_p(total.ctypes.data), self._stream()))
@@ -309,7 +323,7 @@ class RolloutEngine:
         total = np.zeros(1, dtype=np.int64)
         assert isinstance(parents, np.ndarray) and parents.dtype == np.float32 and parents.flags.c_contiguous and parents.size == numel
         assert isinstance(fitness, np.ndarray) and fitness.dtype == np.float64 and fitness.flags.c_contiguous and fitness.size == self.P
-        _lib.check(fn(self._h, *head, C.c_void_p(parents.ctypes.data), C.c_void_p(fitness.ctypes.data),
+        self._check(fn(self._h, *head, C.c_void_p(parents.ctypes.data), C.c_void_p(fitness.ctypes.data),
                       C.c_void_p(total.ctypes.data), self._stream()))
         return int(total[0])
 
@@ -318,34 +332,34 @@ class RolloutEngine:
         kinds = {"tanh": 0, "sigmoid": 1, "ln": 2, "sin2pi": 3, "cos2pi": 4, "sin64": 5, "cos64": 6, "tanh_fast": 7,
                  "sin64_full": 8, "cos64_full": 9}
         out = torch.empty_like(x)
-        _lib.check(self.lib.ses_test_math(kinds[kind], _ptr(x), _ptr(out), x.numel(), self._stream()))
+        self._check(self._hooks().ses_test_math(kinds[kind], _ptr(x), _ptr(out), x.numel(), self._stream()))
         return out
 
     def test_tanh_fast_exhaustive(self, lo=0.0, hi=10.0):
         """Number of float32 inputs in [lo, hi] (and their negatives) where K1's fast-path tanh != the contract's."""
         bad = C.c_uint64(0)
-        _lib.check(self.lib.ses_test_tanh_fast_exhaustive(float(lo), float(hi), C.byref(bad)))
+        self._check(self._hooks().ses_test_tanh_fast_exhaustive(float(lo), float(hi), C.byref(bad)))
         return int(bad.value)
 
     def test_tanh_x2_exhaustive(self, newton, lo=0.0, hi=10.0):
         """The same for the packed (FFMA2) tanh of K1's hidden-unit pairs; newton=False is K1 variant 2."""
         bad = C.c_uint64(0)
-        _lib.check(self.lib.ses_test_tanh_x2_exhaustive(int(bool(newton)), float(lo), float(hi), C.byref(bad)))
+        self._check(self._hooks().ses_test_tanh_x2_exhaustive(int(bool(newton)), float(lo), float(hi), C.byref(bad)))
         return int(bad.value)
 
     def test_div_total_mass(self, n=1 << 33):
         """Mismatches between K1's multiply+2fma division by total_mass (1.1) and IEEE division on n random doubles."""
         bad = C.c_uint64(0)
-        _lib.check(self.lib.ses_test_div_total_mass(int(n), C.byref(bad)))
+        self._check(self._hooks().ses_test_div_total_mass(int(n), C.byref(bad)))
         return int(bad.value)
 
     def test_ddiv_fast(self, n=1 << 30):
         """Mismatches between K1 variant 6's branch-free double division and IEEE division on n random in-range operand pairs."""
         bad = C.c_uint64(0)
-        _lib.check(self.lib.ses_test_ddiv_fast(int(n), C.byref(bad)))
+        self._check(self._hooks().ses_test_ddiv_fast(int(n), C.byref(bad)))
         return int(bad.value)
 
     def test_normals(self, generation, idx):
         out = torch.empty(self.D, dtype=torch.float32, device=self.device)
-        _lib.check(self.lib.ses_test_normals(self._h, int(generation), int(idx), _ptr(out), self._stream()))
+        self._check(self._hooks().ses_test_normals(self._h, int(generation), int(idx), _ptr(out), self._stream()))
         return out

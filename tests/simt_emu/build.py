@@ -16,7 +16,8 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "simple-es_b200", "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(BUILD, "libses_simt_emu.so")
-CXXFLAGS = ["-std=c++17", "-O2", "-g", "-ffp-contract=off", "-mfma", "-fPIC", "-shared", "-fno-strict-aliasing",
+# -DSES_BUILD_TESTS: the emulated library is test infrastructure -- it carries the test hooks and every alternative kernel
+CXXFLAGS = ["-DSES_BUILD_TESTS", "-std=c++17", "-O2", "-g", "-ffp-contract=off", "-mfma", "-fPIC", "-shared", "-fno-strict-aliasing",
             "-Wno-unknown-pragmas", "-Wno-attributes", "-Wno-unused-value"]
 
 
@@ -110,6 +111,7 @@ def transform(text):
     for rx, rep in ASM:
         text = rx.sub(rep, text)
     text = text.replace('#include "../../include/ses_b200.h"', '#include "%s"' % os.path.join(ROOT, "include", "ses_b200.h"))
+    text = text.replace('#include "../../include/ses_b200_test.h"', '#include "%s"' % os.path.join(ROOT, "include", "ses_b200_test.h"))
     if re.search(r"\basm\b", text) or "<<<" in text:
         raise RuntimeError("simt_emu: an inline-asm statement or a kernel launch was not rewritten")
     return text

@@ -25,7 +25,7 @@ def load():
     global _lib
     if _lib is None:
         lib = C.CDLL(emu_build.build())
-        for name, (res, args) in product_lib.SYMBOLS.items():
+        for name, (res, args) in dict(product_lib.SYMBOLS, **product_lib.TEST_SYMBOLS).items():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args

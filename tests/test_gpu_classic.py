@@ -28,7 +28,7 @@ def _cuda(a):
 
 
 def test_sincos_full_bit_exact(twin):
-    eng = _engine("Acrobot-v1")
+    eng = _engine("Acrobot-v1", test_build=True)
     rng = np.random.default_rng(0)
     x = np.concatenate([rng.uniform(-100, 100, 2_000_000), rng.uniform(-4, 4, 1_000_000), np.arange(-80, 81) * (np.pi / 4), [0.0, -0.0]])
     s, c = twin.sincos_full(x)

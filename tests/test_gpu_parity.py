@@ -27,7 +27,7 @@ def _cuda(a):
 
 # ------------------------------------------------------------------------------------- contract
 def test_math_contract_bit_exact(twin):
-    eng = _engine()
+    eng = _engine(test_build=True)            # the contract functions are reachable through the test build's hooks only
     rng = np.random.default_rng(0)
     x = np.concatenate([rng.uniform(-10, 10, 1_000_000), rng.normal(0, 1, 1_000_000), [0.0, -0.0, 50, -50]]).astype(np.float32)
     assert np.array_equal(eng.test_math("tanh", _cuda(x)).cpu().numpy(), twin.tanhf(x))
@@ -54,7 +54,7 @@ def test_math_contract_bit_exact(twin):
 
 
 def test_philox_normals_bit_exact(twin):
-    eng = _engine(seed=1234)
+    eng = _engine(seed=1234, test_build=True)
     for gen, idx in [(0, 0), (0, 1), (3, 77), (1000, 65535), (2 ** 31, 2 ** 20 - 1)]:
         got = eng.test_normals(gen, idx).cpu().numpy()
         assert np.array_equal(got, twin.normals(1234, gen, idx, D))
@@ -98,6 +98,7 @@ def test_rollout_k1_variants_bit_exact(twin, knobs, E, monkeypatch):
     with W2+b2 / W2+b2+b1 / b1 of the lane's slot held in registers; 4 is the default)
     must all reproduce the oracle bit for bit: Philox and verification (w_override) paths, ragged and 500-step
     episodes, 8 / 16 / 32 slots per warp (E = 5 / 3 / 1)."""
+    monkeypatch.setenv("SES_B200_TEST_BUILD", "1")        # the alternative kernels live in libses_b200_tests.so
     for k, v in knobs.items():
         monkeypatch.setenv(k, v)
     P = 2048
@@ -227,6 +228,7 @@ def test_rollout_full_size_properties():
 @pytest.mark.parametrize("n", [2, 97, 4097, 65536, 1 << 20])
 def test_rank_desc_bit_exact(n, fused, monkeypatch):
     """Both K2 builds: separate init / histogram / scatter / shape kernels, and SES_K2_FUSED=1 (1 + passes launches)."""
+    monkeypatch.setenv("SES_B200_TEST_BUILD", "1")
     monkeypatch.setenv("SES_K2_FUSED", str(fused))
     eng = _engine(population=max(n, 2), group=max(n, 2))
     rng = np.random.default_rng(n)

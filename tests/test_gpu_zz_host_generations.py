@@ -59,6 +59,7 @@ def test_k1_variants_6_7_branch_free_division_bit_exact(twin, monkeypatch, varia
     action-dependent tail evaluated for both actions as well (6).  Same bits as the twin; the division equals IEEE division
     on 2^30 random in-range operand pairs."""
     from simple_es_b200.engine import RolloutEngine
+    monkeypatch.setenv("SES_B200_TEST_BUILD", "1")
     monkeypatch.setenv("SES_K1_VARIANT", str(variant))
     eng = RolloutEngine("CartPole-v1", 4, 2, False, False, 500, 5, 3000, 3000, 1, 1, seed=11)
     assert eng.test_ddiv_fast(1 << 30) == 0
@@ -73,11 +74,13 @@ def test_k1_variants_6_7_branch_free_division_bit_exact(twin, monkeypatch, varia
     assert np.array_equal(steps.cpu().numpy(), ts) and (ts == 2500).mean() > 0.5
 
 
-def test_gru_variant1_speculative_lanes_bit_exact(twin, monkeypatch):
-    """SES_GRU_VARIANT=1 (opt-in): the GRU rollout with the cart-pole step evaluated for both actions on otherwise idle
-    lanes at the start of the step.  Same bits as the twin (E = 5 and a chunked E = 7, POMDP on / off)."""
+def test_gru_variant0_plain_kernel_bit_exact(twin, monkeypatch):
+    """SES_GRU_VARIANT=0 (test build): the plain GRU rollout, physics after the argmax -- the default since round 2 is the
+    speculative kernel (the cart-pole step evaluated for both actions on otherwise idle lanes at the start of the step), which
+    every other GRU test runs.  Same bits as the twin (E = 5 and a chunked E = 7, POMDP on / off)."""
     from simple_es_b200.engine import RolloutEngine
-    monkeypatch.setenv("SES_GRU_VARIANT", "1")
+    monkeypatch.setenv("SES_B200_TEST_BUILD", "1")
+    monkeypatch.setenv("SES_GRU_VARIANT", "0")
     rng = np.random.default_rng(7)
     mu = rng.normal(0, 0.3, (1, 6562)).astype(np.float32)
     for pomdp, E in [(True, 5), (False, 7)]:

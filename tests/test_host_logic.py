@@ -2,8 +2,9 @@
 switch, the CLI flags and the checkpoint format."""
 import ctypes as C
 import os
-import sys
 import re
+import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -14,14 +15,28 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_library_exports_every_declared_symbol():
+    """The product library exports exactly what include/ses_b200.h declares -- and none of the test hooks; the test build
+    (-DSES_BUILD_TESTS, include/ses_b200_test.h) exports both."""
     from simple_es_b200 import _lib
-    _lib.build_library()
+    _lib.build_all()
     header = open(os.path.join(ROOT, "include", "ses_b200.h")).read()
     declared = set(re.findall(r"\b(ses_[a-z0-9_]+)\s*\(", header))
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    theader = open(os.path.join(ROOT, "include", "ses_b200_test.h")).read()
+    tdeclared = set(re.findall(r"\b(ses_test_[a-z0-9_]+)\s*\(", theader))
+    assert tdeclared == set(_lib.TEST_SYMBOLS), tdeclared ^ set(_lib.TEST_SYMBOLS)
     lib = C.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
+    for name in tdeclared:
+        assert not hasattr(lib, name), "test hook %s leaked into the product library" % name
+    tlib = C.CDLL(_lib.TEST_LIB_PATH)
+    for name in declared | tdeclared:
+        assert hasattr(tlib, name), name
+    # one rollout kernel per (environment, policy, slots per warp) in the product: no alternative CartPole-MLP variants
+    names = subprocess.run(["cuobjdump", "-res-usage", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    variants = set(re.findall(r"CartpoleMlpEnvTILi(\d)E", names))
+    assert variants == {"7"}, variants
     lib = _lib.load()
     assert lib.ses_abi_version() == 1
     assert lib.ses_param_count(4, 2, 0) == 226 and lib.ses_param_count(4, 2, 1) == 6562
