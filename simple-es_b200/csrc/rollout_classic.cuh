@@ -123,7 +123,7 @@ struct MountainCarEnv {
     static constexpr int D = param_count(OBS, ACT, 0), NQ = (D + 3) / 4;     // 195, 49
     static constexpr int STATE_DIM = 2, N_AGENTS = 1;
     static constexpr bool UNIT_REWARD = false;
-    static constexpr bool LANES32_OK = true;     // the launcher may give all 32 lanes episodes (rollout_slots.cuh scheduler)
+    static constexpr bool LANES32_OK = false;     // the launcher may give all 32 lanes episodes (rollout_slots.cuh scheduler)
     struct State { double pos, vel, ret; };
 
     __device__ static __forceinline__ void init(State &s, const RolloutParams &p, int id, int ep)
@@ -182,7 +182,7 @@ struct PendulumEnv {
     static constexpr int D = param_count(OBS, ACT, 0), NQ = (D + 3) / 4;     // 161, 41
     static constexpr int STATE_DIM = 2, N_AGENTS = 1;
     static constexpr bool UNIT_REWARD = false;
-    static constexpr bool LANES32_OK = true;
+    static constexpr bool LANES32_OK = false;
     static constexpr double PI = 3.141592653589793;
     struct State { double th, thd, ret; };
 
@@ -253,7 +253,7 @@ struct AcrobotEnv {
     static constexpr int D = param_count(OBS, ACT, 0), NQ = (D + 3) / 4;     // 323, 81
     static constexpr int STATE_DIM = 4, N_AGENTS = 1;
     static constexpr bool UNIT_REWARD = false;
-    static constexpr bool LANES32_OK = true;     // the launcher may give all 32 lanes episodes (rollout_slots.cuh scheduler)
+    static constexpr bool LANES32_OK = false;     // the launcher may give all 32 lanes episodes (rollout_slots.cuh scheduler)
     static constexpr double PI = 3.141592653589793;
     // sc = { sin th1, cos th1, sin th2, cos th2 } of the current state: computed once per step (terminal test) and reused
     // by the next step's observation and first RK4 stage (same function, same argument: same bits as recomputing)

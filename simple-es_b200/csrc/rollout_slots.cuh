@@ -36,6 +36,9 @@
 namespace ses {
 
 constexpr int MAX_PEERS = 8;     // ranks of one NVSwitch box
+constexpr int WORK_COUNTER_TAIL = 1 + 256;   // work_counter: [0] queue A, [1 + smid] CTA arrivals per SM, [WORK_COUNTER_TAIL] queue B
+constexpr int WORK_COUNTER_STEPS = WORK_COUNTER_TAIL + 1;   // (8-byte aligned) env steps of this launch: the launcher's episode-length estimate
+constexpr int WORK_COUNTER_INTS = WORK_COUNTER_STEPS + 2;
 
 struct RolloutParams {
     const float *parents;        // [n_parents][D]
@@ -45,7 +48,9 @@ struct RolloutParams {
     long long *steps;            // [P]
     double *trace;               // optional [n_trace][200][state_dim]
     int *trace_actions;          // optional [n_trace][200][n_agents]
-    int *work_counter;           // zeroed before launch
+    int *work_counter;           // zeroed before launch; counts EPISODES handed out (local offspring index * E + episode)
+    int *ep_acc;                 // [n_local][2] {steps, episodes done} of offspring whose episodes ran in more than one warp
+                                 // (EPISODE_UNITS envs; all zero between launches: the last part to finish resets its pair)
     unsigned long long *total_steps;   // optional: += env steps simulated by this launch
     float sigma;
     uint32_t seed;
@@ -65,8 +70,8 @@ struct RolloutParams {
     int sparse_rank;             // >= 0: warps of the CTAs that arrive on their SM as number sparse_rank or later take at most
     int sparse_quota;            //       sparse_quota offspring in total ("fractional" warps of a launch that does not fill the SMs)
     int split_ok;                // Envs with step_split(): a warp left with few episodes and nothing to refill spreads each over 2 / 4 lanes
-    int strict_tail;             // > 0: once fewer than this many offspring are left in the queue, a warp takes a new offspring
-                                 // only if ALL its E episodes get a lane at once (see the scheduler)
+    int tail_start;              // episodes [0, tail_start) are handed out in whole offspring (queue A = work_counter[0]), the rest --
+                                 // EPISODE_UNITS envs: the last round's worth -- in exact numbers (queue B = work_counter[WORK_COUNTER_TAIL])
 };
 
 constexpr int MAX_E = 32;
@@ -91,20 +96,67 @@ template <class Env, int S>
 struct __align__(16) SlotSmem<Env, S, false> {
     float4 w[Env::NQ][S];
     int off_id[S];
-    int ep_next[S];
+    int ep_first[S];             // the slot runs episodes [ep_first, ep_first + ep_cnt) of its offspring (all E of them unless the
+    int ep_cnt[S];               // env is EPISODE_UNITS and the queue handed this warp a part)
+    int ep_next[S];              // ... of which ep_next have been handed to lanes and ep_done have ended
     int ep_done[S];
     int steps[S];
-};
+    int more, in_tail, quota, pad_;   // the warp's scheduler state: kept here, not in registers, so that the throughput loop's
+};                                    // register allocation does not depend on the scheduler's bookkeeping
 
 template <class Env, int S>
 struct __align__(16) SlotSmem<Env, S, true> {
     float4 w[Env::NQ][S];
     double ret[S][MAX_E];        // per-episode returns, summed in episode order when the slot retires
     int off_id[S];
+    int ep_first[S];
+    int ep_cnt[S];
     int ep_next[S];
     int ep_done[S];
     int steps[S];
+    int more, in_tail, quota, pad_;
 };
+
+template <class Env, class = void> struct EnvEpisodeUnits { static constexpr bool value = false; };
+template <class Env> struct EnvEpisodeUnits<Env, decltype((void)Env::EPISODE_UNITS)> { static constexpr bool value = Env::EPISODE_UNITS; };
+
+// A slot's episodes have all ended: emit the offspring's fitness (loop.py:124).  An offspring whose E episodes ran in ONE warp
+// is emitted directly.  EPISODE_UNITS envs (reward 1 per step: the return is an integer step count) may have run parts of an
+// offspring in different warps: each part adds its steps, then its episode count, to the offspring's pair in ep_acc; the part
+// that completes the count emits the sum (integer addition: exact in any order) and clears the pair for the next launch.
+template <class Env, class Smem>
+__device__ __forceinline__ void retire_slot(Smem &sm, const RolloutParams &p, int s, unsigned long long &warp_steps)
+{
+    const int id = sm.off_id[s];
+    const int stp = sm.steps[s];
+    warp_steps += (unsigned long long)stp;
+    bool whole = true;
+    if constexpr (EnvEpisodeUnits<Env>::value) whole = sm.ep_cnt[s] == p.E;
+    if (whole) {
+        p.steps[id] = (long long)stp;
+        double total;
+        if constexpr (Env::UNIT_REWARD) {
+            total = (double)stp;                                    // reward 1.0 per step
+        } else {
+            total = 0.0;
+            for (int e = 0; e < p.E; ++e) total = __dadd_rn(total, sm.ret[s][e]);
+        }
+        publish_fitness(p, id, __ddiv_rn(total, (double)p.E));
+    } else {
+        int *a = p.ep_acc + 2 * (size_t)p.shard.id_to_local(id);
+        const int cnt = sm.ep_cnt[s];
+        atomicAdd(a, stp);
+        __threadfence();                                            // the steps are visible before the count that announces them
+        if (atomicAdd(a + 1, cnt) + cnt == p.E) {
+            __threadfence();
+            const int tot = atomicExch(a, 0);
+            atomicExch(a + 1, 0);
+            p.steps[id] = (long long)tot;
+            publish_fitness(p, id, __ddiv_rn((double)tot, (double)p.E));
+        }
+    }
+    sm.off_id[s] = -1;
+}
 
 template <class Env, class = void> struct EnvSplit { static constexpr bool value = false; };
 template <class Env> struct EnvSplit<Env, decltype((void)Env::SPLIT)> { static constexpr bool value = Env::SPLIT; };
@@ -181,14 +233,14 @@ __global__ void __launch_bounds__(WARPS * 32) k_rollout_slots(const RolloutParam
     const unsigned lt = lanemask_lt();
     const bool usable = lane < p.lanes_used;
 
-    if (lane < S) { sm.off_id[lane] = -1; sm.ep_next[lane] = 0; sm.ep_done[lane] = 0; sm.steps[lane] = 0; }
+    if (lane < S) { sm.off_id[lane] = -1; sm.ep_first[lane] = 0; sm.ep_cnt[lane] = 0; sm.ep_next[lane] = 0; sm.ep_done[lane] = 0; sm.steps[lane] = 0; }
     __syncwarp();
     // Sparse warps.  A launch whose episodes do not fill every resident warp (one rank's share of an 8-GPU run: 2.3 warps
     // per SM sub-partition) would leave some sub-partitions with three full warps and others with two; the former set the
     // time.  Instead every SM gets the same CTAs: those that arrive first take full loads, the CTA that arrives as number
     // sparse_rank shares what is left -- a few episodes per warp, which the straggler phase then runs on 2 or 4 lanes each,
     // at a fraction of a full warp's cost per step.  work_counter[1 + smid] counts the CTAs arriving on an SM.
-    int quota = 0x7fffffff;
+    int quota0 = 0x7fffffff;
     if (p.sparse_rank >= 0) {
         __shared__ int cta_rank_s;
         if (threadIdx.x == 0) {
@@ -197,15 +249,16 @@ __global__ void __launch_bounds__(WARPS * 32) k_rollout_slots(const RolloutParam
             cta_rank_s = atomicAdd(p.work_counter + 1 + (smid & 255u), 1);
         }
         __syncthreads();
-        if (cta_rank_s >= p.sparse_rank) quota = p.sparse_quota;
+        if (cta_rank_s >= p.sparse_rank) quota0 = p.sparse_quota;
     }
+    if (lane == 0) { sm.more = 1; sm.in_tail = p.tail_start <= 0; sm.quota = quota0; }
+    __syncwarp();
 
     // per-lane episode state
     int slot = -1, nstep = 0;
     [[maybe_unused]] int ep = 0;
     typename Env::State st;
     unsigned long long warp_steps = 0;   // lanes < S: steps of the offspring they retired
-    bool more = true;          // warp-uniform: the global offspring queue may still hold work
     bool sched = true;         // warp-uniform: something changed that the scheduler must look at
     [[maybe_unused]] bool to_split = false;
 
@@ -213,60 +266,92 @@ __global__ void __launch_bounds__(WARPS * 32) k_rollout_slots(const RolloutParam
         if (sched) {
             // ------------------------------------------------------------------ scheduler
             __syncwarp();
+            // warp-uniform scheduler state (SlotSmem): more = the episode queues may still hold work; in_tail = queue A (whole
+            // offspring) is exhausted, requests go to queue B; quota = what a sparse warp may still take
+            bool more = sm.more != 0, in_tail = sm.in_tail != 0;
+            int quota = sm.quota;
             int my_id = -1;
             if (lane < S) {
                 my_id = sm.off_id[lane];
-                if (my_id >= 0 && sm.ep_done[lane] == p.E) {       // offspring finished: emit fitness
-                    const int stp = sm.steps[lane];
-                    p.steps[my_id] = (long long)stp;
-                    warp_steps += (unsigned long long)stp;
-                    double total;
-                    if constexpr (Env::UNIT_REWARD) {
-                        total = (double)stp;                        // reward 1.0 per step
-                    } else {
-                        total = 0.0;
-                        for (int e = 0; e < p.E; ++e) total = __dadd_rn(total, sm.ret[lane][e]);
-                    }
-                    publish_fitness(p, my_id, __ddiv_rn(total, (double)p.E));   // loop.py:124
-                    sm.off_id[lane] = -1;
+                if (my_id >= 0 && sm.ep_done[lane] == sm.ep_cnt[lane]) {   // every episode of the slot has ended
+                    retire_slot<Env>(sm, p, lane, warp_steps);
                     my_id = -1;
                 }
             }
             const unsigned empty_mask = __ballot_sync(FULL, lane < p.slots_cap && my_id < 0);
-            const int pend_mine = (lane < S && my_id >= 0) ? (p.E - sm.ep_next[lane]) : 0;
+            const int n_empty = __popc(empty_mask);
+            const int pend_mine = (lane < S && my_id >= 0) ? (sm.ep_cnt[lane] - sm.ep_next[lane]) : 0;
             int pending = pend_mine;
 #pragma unroll
             for (int o = 16; o; o >>= 1) pending += __shfl_xor_sync(FULL, pending, o);
             const unsigned idle_mask = __ballot_sync(FULL, usable && slot < 0);
             const int n_idle = __popc(idle_mask);
-            // demand-driven refill: just enough new offspring to occupy the idle lanes.  When lanes_used is not a multiple
-            // of E (32 lanes, E = 5) the last offspring taken is split over two rounds of the warp, which keeps every lane
-            // busy -- except at the end of the queue, where the left-over episodes would cost each warp one more, nearly
-            // empty, round: there (fewer than strict_tail offspring left) an offspring is taken only if it fits entirely.
-            int want = (n_idle - pending + p.E - 1) / p.E;
-            if (p.strict_tail > 0 && more && want > 0) {
-                int taken = 0;                                     // one lane reads: the value must be warp-uniform
-                if (lane == 0) taken = *reinterpret_cast<volatile int *>(p.work_counter);
-                taken = __shfl_sync(FULL, taken, 0);
-                if (p.shard.n_local - taken <= p.strict_tail) {
-                    const int whole = (n_idle - pending) / p.E;
-                    // (a warp with fewer lanes than E, nothing running and nothing pending must still take one)
-                    if (whole > 0 || pending > 0 || __ballot_sync(FULL, slot >= 0) != 0) want = whole;
+            // Demand-driven refill: just enough episodes to occupy the idle lanes (episode index = local offspring * E + episode).
+            // The bulk of a launch, [0, tail_start), is handed out in WHOLE offspring from queue A: the request is rounded up to a
+            // multiple of E and the episodes that find no lane wait in the slot for the warp's next round, so an offspring's
+            // weights are derived once.  Envs whose returns are integer step counts (EPISODE_UNITS) hand out the last round's worth,
+            // [tail_start, n_total), from queue B in EXACT numbers: a warp whose lanes came free together takes precisely that many
+            // episodes (rounding up there would leave every warp a few episodes for one more, nearly empty, round), and a sparse
+            // warp takes its small share.  An exact range may leave an offspring's episodes to two warps (retire_slot adds them up).
+            const int n_total = p.shard.n_local * p.E;
+            int want = n_idle - pending;
+            bool exact = false;
+            int cap = n_empty * p.E;                               // queue A is aligned: n E episodes are n offspring
+            bool realign = false;
+            if constexpr (EnvEpisodeUnits<Env>::value) {
+                if (in_tail) {
+                    // a lane or two coming free at a time (ragged episode lengths) still take whole offspring
+                    exact = quota != 0x7fffffff || want >= 2 * p.E || n_empty == 1;
+                    cap = n_empty > 0 ? (n_empty - 1) * p.E + 1 : 0;   // whatever the range's alignment it spans <= n_empty offspring
+                    realign = !exact && want > 0 && more;
                 }
             }
-            want = min(min(max(want, 0), __popc(empty_mask)), quota);
-            if (quota == 0) more = false;                          // a sparse warp that has taken its share
+            if (realign) {
+                // Queue B may stand in the middle of an offspring (an exact request left it there).  A whole-offspring request then
+                // takes that offspring's remaining episodes first, so that its range ENDS on an offspring boundary and the queue is
+                // aligned again for everybody: k E - m episodes, m = episodes of the front offspring already gone (read, not
+                // reserved: if another warp gets in between, the next request of this kind repairs the alignment).
+                int c = 0;
+                if (lane == 0) c = *reinterpret_cast<volatile int *>(p.work_counter + WORK_COUNTER_TAIL);
+                c = __shfl_sync(FULL, c, 0);
+                const int m = c % p.E;
+                const int k = min((want + m + p.E - 1) / p.E, n_empty - 1);
+                want = k > 0 ? k * p.E - m : 0;
+            } else if (!exact) {
+                want = ((want + p.E - 1) / p.E) * p.E;
+            }
+            want = min(min(max(want, 0), cap), quota);
+            if (quota == 0) more = false;                          // a sparse warp that has taken its share (the launcher sizes the
+                                                                   // shares so that together they cover the launch)
+            bool rerun = false;
             if (want > 0 && more) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(p.work_counter, want);
-                base = __shfl_sync(FULL, base, 0);                 // local index of the first new offspring
-                if (base + want >= p.shard.n_local) more = false;
-                const int got = max(0, min(want, p.shard.n_local - base));
-                if (quota != 0x7fffffff) { quota -= want; if (quota == 0) more = false; }
+                int base = 0, got;
+                if (!in_tail) {
+                    if (lane == 0) base = atomicAdd(p.work_counter, want);
+                    base = __shfl_sync(FULL, base, 0);             // first episode of the range this warp was given
+                    got = max(0, min(want, p.tail_start - base));
+                    if (base + want >= p.tail_start) {             // queue A is exhausted: go on with queue B
+                        in_tail = true;
+                        if (p.tail_start >= n_total) more = false;
+                        rerun = got < want && more;                // ... at once if this request came up short
+                    }
+                } else {
+                    if (lane == 0) base = atomicAdd(p.work_counter + WORK_COUNTER_TAIL, want);
+                    base = p.tail_start + __shfl_sync(FULL, base, 0);
+                    got = max(0, min(want, n_total - base));
+                    if (base + want >= n_total) more = false;
+                    if (quota != 0x7fffffff) { quota -= want; if (quota == 0) more = false; }
+                }
+                const int off0 = base / p.E;                       // local index of the first offspring the range touches
+                const int n_off = got > 0 ? (base + got - 1) / p.E - off0 + 1 : 0;
                 const int my_rank = __popc(empty_mask & lt);       // rank of this lane's slot among the empty ones
-                const bool fill = ((empty_mask >> lane) & 1u) && my_rank < got;
+                const bool fill = ((empty_mask >> lane) & 1u) && my_rank < n_off;
                 if (fill) {
-                    sm.off_id[lane] = p.shard.local_to_id(base + my_rank);
+                    const int ol = off0 + my_rank;
+                    const int lo = max(base, ol * p.E) - ol * p.E, hi = min(base + got, (ol + 1) * p.E) - ol * p.E;
+                    sm.off_id[lane] = p.shard.local_to_id(ol);
+                    sm.ep_first[lane] = lo;
+                    sm.ep_cnt[lane] = hi - lo;
                     sm.ep_next[lane] = 0;
                     sm.ep_done[lane] = 0;
                     sm.steps[lane] = 0;
@@ -274,7 +359,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_rollout_slots(const RolloutParam
                 const unsigned fill_mask = __ballot_sync(FULL, fill);
                 __syncwarp();
                 // regenerate the weights of the newly filled slots: (slot, quad) tasks over 32 lanes
-                const int ntask = got * NQ;
+                const int ntask = n_off * NQ;
                 for (int t = lane; t < ntask; t += 32) {
                     const int k = t / NQ, q = t - k * NQ;
                     const int s = __fns(fill_mask, 0, k + 1);      // k-th filled slot
@@ -305,8 +390,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_rollout_slots(const RolloutParam
 #pragma unroll
             for (int s = 0; s < S; ++s) {
                 const int nx = sm.ep_next[s];
-                const int av = (sm.off_id[s] >= 0) ? (p.E - nx) : 0;
-                if (usable && slot < 0 && my_slot < 0 && r < acc + av) { my_slot = s; my_ep = nx + (r - acc); }
+                const int av = (sm.off_id[s] >= 0) ? (sm.ep_cnt[s] - nx) : 0;
+                if (usable && slot < 0 && my_slot < 0 && r < acc + av) { my_slot = s; my_ep = sm.ep_first[s] + nx + (r - acc); }
                 if (lane == s) { my_prefix = acc; my_avail = av; }
                 acc += av;
             }
@@ -318,6 +403,9 @@ __global__ void __launch_bounds__(WARPS * 32) k_rollout_slots(const RolloutParam
                 Env::init(st, p, sm.off_id[my_slot], my_ep);
                 Env::template bind<S>(st, sm.w, my_slot);
             }
+            __syncwarp();
+            if (lane == 0) { sm.more = more; sm.in_tail = in_tail; sm.quota = quota; }
+            if (rerun) continue;                                   // queue A ran dry under this request: ask queue B for the rest
             const unsigned act_mask = __ballot_sync(FULL, slot >= 0);
             if (act_mask == 0) break;                              // queue empty and every lane idle
             if constexpr (EnvSplit<Env>::value && !TRACE) {
@@ -360,22 +448,14 @@ __global__ void __launch_bounds__(WARPS * 32) k_rollout_slots(const RolloutParam
         if (to_split) {
             split_phase<Env, S, Smem>(&sm, p.pomdp, p.max_step, slot, nstep, st.x, st.xd, st.th, st.thd);
             __syncwarp();
-            if (lane < S) {                                        // retire every slot the warp still holds
-                const int my_id = sm.off_id[lane];
-                if (my_id >= 0) {
-                    const int stp = sm.steps[lane];
-                    p.steps[my_id] = (long long)stp;
-                    warp_steps += (unsigned long long)stp;
-                    publish_fitness(p, my_id, __ddiv_rn((double)stp, (double)p.E));
-                    sm.off_id[lane] = -1;
-                }
-            }
+            if (lane < S && sm.off_id[lane] >= 0) retire_slot<Env>(sm, p, lane, warp_steps);   // every slot the warp still holds
         }
     }
-    if (p.total_steps) {
 #pragma unroll
-        for (int o = 16; o; o >>= 1) warp_steps += __shfl_xor_sync(FULL, warp_steps, o);
-        if (lane == 0 && warp_steps) atomicAdd(p.total_steps, warp_steps);
+    for (int o = 16; o; o >>= 1) warp_steps += __shfl_xor_sync(FULL, warp_steps, o);
+    if (lane == 0 && warp_steps) {
+        if (p.total_steps) atomicAdd(p.total_steps, warp_steps);
+        atomicAdd(reinterpret_cast<unsigned long long *>(p.work_counter + WORK_COUNTER_STEPS), warp_steps);
     }
 }
 

@@ -61,6 +61,13 @@ struct ses_handle {
     int eff_max_step;
     // scratch (device)
     int *work_counter = nullptr;
+    // episode-length estimate of the slot kernels' last launch (read back asynchronously; never waited for)
+    unsigned long long *k1_steps_host = nullptr;   // pinned
+    cudaEvent_t k1_ev = nullptr;
+    bool k1_ev_pending = false;
+    long long k1_last_episodes = 0;
+    double k1_mean_len = -1.0;     // < 0: unknown
+    int *ep_acc = nullptr;         // [n_local][2]: steps / episodes of offspring split over warps (rollout_slots.cuh retire_slot)
     unsigned long long *keys[2] = {nullptr, nullptr};
     int *vals_scratch = nullptr;
     int *hist = nullptr;
@@ -100,8 +107,6 @@ struct ses_handle {
 
     int64_t launches = 0;
 };
-
-constexpr int WORK_COUNTER_INTS = 1 + 256;    // [0] the offspring queue, [1 + smid] CTAs that have arrived on an SM (sparse warps)
 
 static cudaStream_t S(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -194,6 +199,10 @@ extern "C" int ses_create(const ses_config *cfg, ses_handle **out)
     h->nb0 = (P + GB0 - 1) / GB0;
     h->nb1 = (h->nb0 + GB1 - 1) / GB1;
     CU(cudaMalloc(&h->work_counter, sizeof(int) * WORK_COUNTER_INTS));
+    CU(cudaMallocHost(reinterpret_cast<void **>(&h->k1_steps_host), sizeof(unsigned long long)));
+    CU(cudaEventCreateWithFlags(&h->k1_ev, cudaEventDisableTiming));
+    CU(cudaMalloc(&h->ep_acc, sizeof(int) * 2 * (size_t)(h->shard.n_local > 0 ? h->shard.n_local : 1)));
+    CU(cudaMemset(h->ep_acc, 0, sizeof(int) * 2 * (size_t)(h->shard.n_local > 0 ? h->shard.n_local : 1)));
     CU(cudaMalloc(&h->keys[0], sizeof(unsigned long long) * P));
     CU(cudaMalloc(&h->keys[1], sizeof(unsigned long long) * P));
     CU(cudaMalloc(&h->vals_scratch, sizeof(int) * P));
@@ -210,6 +219,9 @@ extern "C" int ses_destroy(ses_handle *h)
     if (!h) return 0;
     cudaSetDevice(h->cfg.device);
     cudaFree(h->work_counter);
+    if (h->k1_steps_host) cudaFreeHost(h->k1_steps_host);
+    if (h->k1_ev) cudaEventDestroy(h->k1_ev);
+    cudaFree(h->ep_acc);
     cudaFree(h->keys[0]); cudaFree(h->keys[1]);
     cudaFree(h->vals_scratch); cudaFree(h->hist); cudaFree(h->tot); cudaFree(h->hist_fused);
     cudaFree(h->part1);
@@ -248,50 +260,49 @@ static int launch_slots(ses_handle *h, RolloutParams &rp, int need_warps, bool t
     if (per_sm < 1) return fail("rollout kernel does not fit on an SM (smem %zu B)", smem);
     if (h->ctas_per_sm > 0 && h->ctas_per_sm < per_sm) per_sm = h->ctas_per_sm;
     const int resident_warps = per_sm * h->num_sms * WARPS;
-    // lanes of a warp that take episodes.  E * floor(32 / E) (30 for E = 5) lets slots start and finish together; all 32
-    // with the last offspring of a refill carried into the warp's next round (and a strict end of the queue) holds more
-    // episodes per round.  Episodes of a launch run in rounds of resident_warps * lanes; a converged population (equal
-    // episode lengths) pays for every started round, so take 32 lanes exactly when that saves a round
-    // (profiles/r02_k1_rounds.jsonl: 0.76 ms per 500-step round of 3 warps per sub-partition, whatever the lanes).
+    // Lanes of a warp that take episodes.  E * floor(32 / E) (30 for E = 5) lets slots start and finish together.  Envs whose
+    // queue can hand out single episodes (EPISODE_UNITS: CartPole) use all 32: in the bulk of a launch the last offspring of a
+    // refill waits for the warp's next round, and once at most one round of episodes is left every warp takes exactly as many
+    // episodes as it has idle lanes, so no left-over episodes cost an extra, nearly empty round (profiles/r02_k1_experiments.md).
     const int E = h->cfg.eval_ep_num;
     const long long n_ep = (long long)h->shard.n_local * E;
     const int lanes_even = E >= 32 ? 32 : E * (32 / E);
-    int lanes = lanes_even;
-    if (h->lanes_used_override > 0) {
-        lanes = h->lanes_used_override < 32 ? h->lanes_used_override : 32;
-    } else if (lanes_even < 32 && Env::LANES32_OK && SL >= (32 + E - 1) / E + 1) {
-        const long long cap_even = (long long)resident_warps * lanes_even;
-        const long long rounds_even = (n_ep + cap_even - 1) / cap_even;
-        // 32 lanes: a warp's rounds hold 32 episodes each (the refill takes ceil((32 - pending) / E) offspring and carries the
-        // rest), its last, strict, round `pending` + whole offspring only
-        long long rounds_32 = rounds_even;
-        for (long long R = 1; R < rounds_even; ++R) {
-            long long pend = 0, held = 0;
-            for (long long r = 1; r < R; ++r) { const long long nw = (32 - pend + E - 1) / E; held += 32; pend += nw * E - 32; }
-            held += pend + ((32 - pend) / E) * E;
-            if (held * resident_warps >= n_ep) { rounds_32 = R; break; }
-        }
-        if (rounds_32 < rounds_even) lanes = 32;
-    }
+    constexpr bool EP_UNITS = EnvEpisodeUnits<Env>::value;
+    int lanes = (EP_UNITS && SL >= (32 + E - 1) / E + 1) ? 32 : lanes_even;
+    if (h->lanes_used_override > 0) lanes = h->lanes_used_override < 32 ? h->lanes_used_override : 32;
     rp.lanes_used = lanes;
-    rp.strict_tail = (lanes > E && lanes % E) ? resident_warps * ((32 + E - 1) / E) : 0;
+    {   // Queue B (exact requests) holds the last two rounds' worth of episodes -- when episodes are long.  With short, ragged
+        // episodes (a generation-0 population) lanes come free one or two at a time, every refill is a small whole-offspring
+        // request, and those are cheapest on the aligned queue A (one atomic, no offspring shared between warps): no queue B.
+        // Which regime a launch is in is read off the PREVIOUS launch's mean episode length (k1_mean_len: copied back
+        // asynchronously, never waited for; unknown = long).  None of this can change a result.
+        if (h->k1_ev_pending && cudaEventQuery(h->k1_ev) == cudaSuccess) {
+            h->k1_ev_pending = false;
+            if (h->k1_last_episodes > 0) h->k1_mean_len = (double)*h->k1_steps_host / (double)h->k1_last_episodes;
+        }
+        const bool ragged = h->k1_mean_len >= 0.0 && h->k1_mean_len < 0.25 * (double)h->eff_max_step;
+        const int tail_rounds = env_int("SES_K1_TAIL", ragged ? 0 : 2);
+        const long long tail = EP_UNITS ? (long long)resident_warps * 32 * tail_rounds : 0;
+        long long t0 = n_ep > tail ? ((n_ep - tail) / E) * E : 0;
+        if (EP_UNITS && n_ep <= (long long)resident_warps * 32) t0 = 0;      // a single round: exact from the start (sparse warps need it)
+        rp.tail_start = EP_UNITS ? (int)t0 : (int)n_ep;
+    }
     need_warps = (int)((n_ep + lanes - 1) / lanes);
     int grid = per_sm * h->num_sms;
     const int need = (need_warps + WARPS - 1) / WARPS;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     // A launch that does not fill the SMs (need < resident CTAs): give every SM the same CTAs -- `full` CTAs with full warps
-    // plus one whose warps share the rest, a few episodes each, which the straggler phase runs on 2 / 4 lanes per episode
+    // plus one whose warps share the rest, a few episodes each, which the straggler phase runs on 4 / 2 lanes per episode
     // (see the kernel).  Only where the sparse warps end up with at most 16 episodes, i.e. where they can split.
-    if constexpr (EnvSplit<Env>::value) {
-        const int per_warp = lanes / E;                                   // offspring of a full warp
+    if constexpr (EnvSplit<Env>::value && EP_UNITS) {
         const int full = need / h->num_sms;                               // full CTAs per SM
-        const long long rest = (long long)h->shard.n_local - (long long)full * h->num_sms * WARPS * per_warp;
-        if (h->k1_sparse && h->k1_split && !trace && lanes % E == 0 && need < per_sm * h->num_sms && full >= 1 && full < per_sm && rest > 0) {
+        const long long rest = n_ep - (long long)full * h->num_sms * WARPS * lanes;
+        if (h->k1_sparse && h->k1_split && !trace && h->lanes_used_override == 0 && need < per_sm * h->num_sms && full >= 1 && full < per_sm && rest > 0) {
             const int quota = (int)((rest + (long long)h->num_sms * WARPS - 1) / ((long long)h->num_sms * WARPS));
-            if (quota * E <= 16) {
+            if (quota <= 16) {
                 rp.sparse_rank = full;
-                rp.sparse_quota = quota;
+                rp.sparse_quota = quota;                                  // episodes per sparse warp
                 grid = (full + 1) * h->num_sms;
             }
         }
@@ -299,11 +310,24 @@ static int launch_slots(ses_handle *h, RolloutParams &rp, int need_warps, bool t
             rp.sparse_rank = env_int("SES_K1_SPARSE_RANK", 0);
             rp.sparse_quota = env_int("SES_K1_SPARSE_QUOTA", 0);
             grid = (h->ctas_per_sm > 0 ? h->ctas_per_sm : per_sm) * h->num_sms;
+            if (rp.sparse_rank <= 0) {                                    // no full CTAs: the shares alone must cover the launch
+                const long long warps = (long long)grid * WARPS;
+                const long long min_quota = (n_ep + warps - 1) / warps;
+                if (rp.sparse_quota < min_quota) rp.sparse_quota = (int)min_quota;
+                rp.sparse_rank = 0;
+            }
         }
+        if (rp.sparse_rank >= 0) rp.tail_start = 0;                       // shares are counted in episodes: the exact queue only
     }
     kernel<<<grid, WARPS * 32, smem, st>>>(rp);
     CU(cudaGetLastError());
     h->launches += 1;
+    if (!h->k1_ev_pending) {                                               // this launch's env-step count, for the next launches' geometry
+        CU(cudaMemcpyAsync(h->k1_steps_host, h->work_counter + WORK_COUNTER_STEPS, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CU(cudaEventRecord(h->k1_ev, st));
+        h->k1_ev_pending = true;
+        h->k1_last_episodes = n_ep;
+    }
     return 0;
 }
 
@@ -336,7 +360,7 @@ extern "C" int ses_rollout(ses_handle *h, uint32_t generation, float sigma, cons
     RolloutParams rp;
     rp.parents = parents_dev; rp.w_override = w_override_dev; rp.init_states = init_states_dev;
     rp.fitness = fitness_dev; rp.steps = reinterpret_cast<long long *>(steps_dev);
-    rp.trace = trace_dev; rp.trace_actions = trace_actions_dev; rp.work_counter = h->work_counter;
+    rp.trace = trace_dev; rp.trace_actions = trace_actions_dev; rp.work_counter = h->work_counter; rp.ep_acc = h->ep_acc;
     rp.sigma = sigma; rp.seed = c.seed; rp.gen = generation;
     rp.layout.group = c.group; rp.layout.n_head = c.n_head; rp.layout.antithetic = c.antithetic;
     rp.shard = h->shard;
@@ -356,7 +380,7 @@ extern "C" int ses_rollout(ses_handle *h, uint32_t generation, float sigma, cons
 
     // lanes per warp and the grid are chosen per kernel in launch_slots(); the GRU kernel maps a warp to one offspring
     rp.lanes_used = c.eval_ep_num >= 32 ? 32 : c.eval_ep_num * (32 / c.eval_ep_num);
-    rp.strict_tail = 0;
+    rp.tail_start = 0;
     rp.split_ok = h->k1_split;
     rp.sparse_rank = -1; rp.sparse_quota = 0;
     const int need_warps = 0;

@@ -480,6 +480,11 @@ inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) { memset(
 inline cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, h.reserved, sizeof(*p)); return cudaSuccess; }
 inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
 inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new simt_event{0.0}; return cudaSuccess; }
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { return cudaEventCreate(e); }
+constexpr unsigned cudaEventDisableTiming = 2;
+inline cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; }          // emulated launches are synchronous
+inline cudaError_t cudaMallocHost(void **p, size_t n) { *p = calloc(1, n); return *p ? cudaSuccess : cudaErrorNotSupported; }
+inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
 inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
 inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) { e->t = (double)clock64() * 1e-6; return cudaSuccess; }
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }

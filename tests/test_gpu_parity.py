@@ -136,6 +136,30 @@ def test_rollout_trained_parent_long_episodes(twin):
     assert (ts == 500 * E).mean() > 0.5
 
 
+@pytest.mark.parametrize("knobs", [{}, {"SES_K1_TAIL": "0"}, {"SES_K1_TAIL": "1"}, {"SES_K1_TAIL": "100"}, {"SES_K1_SPLIT": "0"},
+                                   {"SES_K1_SPARSE": "0"}, {"SES_ROLLOUT_LANES": "30"}, {"SES_ROLLOUT_LANES": "7"},
+                                   {"SES_K1_SPARSE_RANK": "0", "SES_K1_SPARSE_QUOTA": "3"}, {"SES_ROLLOUT_CTAS_PER_SM": "1"}])
+def test_rollout_launch_geometry_never_changes_a_bit(twin, knobs, monkeypatch):
+    """Round 2 scheduler of the CartPole-MLP kernel: all 32 lanes with the exact-request queue for the last rounds (an offspring's
+    episodes may run in two warps and are added up with integer atomics), the straggler phase (one episode on 2 / 4 lanes with
+    mirrored speculative physics), sparse warps (a launch that does not fill the SMs) -- whatever the geometry, fitness and
+    env-step counts are the twin's, for ragged and for 500-step populations, several population sizes around the round
+    boundaries, twice in a row (the cross-warp accumulators must come back to zero)."""
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    w1 = np.zeros((1, D), np.float32)
+    w1[0, :4] = [0.0, 0.5, 10.0, 3.0]; w1[0, 160 + 32] = 5.0; w1[0, 160] = -5.0
+    for P, E, sigma, parent in [(8192, 5, 0.05, w1), (13000, 5, 0.05, w1), (3000, 5, 2.0, np.zeros((1, D), np.float32)),
+                                (4097, 3, 0.05, w1), (2500, 7, 0.3, w1)]:
+        eng = _engine(population=P, group=P, n_head=1, eval_ep_num=E, seed=31)
+        tf = ts = None
+        for gen in (0, 1):
+            fit, steps = eng.rollout(gen, sigma, _cuda(parent))
+            tf, ts = twin.population_cartpole(parent, sigma=sigma, seed=31, gen=gen, group=P, n_head=1, n=P, E=E, nthreads=8)
+            assert np.array_equal(steps.cpu().numpy(), ts) and np.array_equal(fit.cpu().numpy(), tf)
+        eng.close()
+
+
 def test_rollout_4096_offspring_match_reference_returns(twin, golden):
     """The reference's own weight arrays at population 4096 (tests/golden/rollout_cartpole_mlp_4096.npz: returns of the
     reference's RolloutWorker + GymEnvModel): >= 99.9 % of the returns exactly equal (north_star), and every return equal to

@@ -95,6 +95,22 @@ def test_emu_rollout_philox_bit_exact(emu, twin, init_mode, pomdp, E):
     assert ts.max() > 3 * ts.min()                          # ragged episode lengths: the warp scheduler re-arms lanes
 
 
+@pytest.mark.parametrize("knobs", [{}, {"SES_K1_TAIL": "0"}, {"SES_K1_TAIL": "1"}, {"SES_K1_TAIL": "100"}, {"SES_K1_SPLIT": "0"},
+                                   {"SES_K1_SPARSE_RANK": "0", "SES_K1_SPARSE_QUOTA": "3"}, {"SES_K1_SPARSE_RANK": "1", "SES_K1_SPARSE_QUOTA": "7"}])
+def test_emu_rollout_launch_geometry_never_changes_a_bit(emu, twin, knobs, monkeypatch):
+    """The round-2 scheduler (exact-request queue with offspring shared between warps, straggler phase, sparse warps): fitness
+    and step counts do not depend on the launch geometry -- 500-step and ragged populations, twice in a row (the cross-warp
+    accumulators return to zero)."""
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    for P, E, sigma, mu in [(90, 5, 0.02, _trained_mu()), (150, 5, 2.0, np.zeros((1, D), np.float32)), (61, 3, 0.02, _trained_mu())]:
+        eng = emu(population=P, group=P, n_head=1, eval_ep_num=E, seed=31, max_step=120)
+        for gen in (0, 1):
+            fit, steps = eng.rollout(gen, sigma, mu)
+            tf, ts = twin.population_cartpole(mu, sigma=sigma, seed=31, gen=gen, group=P, n_head=1, n=P, E=E, max_step=120, nthreads=4)
+            assert np.array_equal(steps, ts) and np.array_equal(fit, tf)
+
+
 @pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7])
 def test_emu_rollout_k1_variants_bit_exact(emu, twin, variant, monkeypatch):
     """Every K1 code path (scalar / packed FFMA2, permuted slot table, weights of the lane's slot in registers) is the
