@@ -97,6 +97,7 @@ ASM = [
      r"\1 = simt::min_xorsign_abs(\2, \3);"),
     (re.compile(r'asm volatile\("mov\.u32 %0, %%lanemask_lt;"\s*:\s*"=r"\((.+?)\)\);'), r"\1 = simt::lanemask_lt();"),
     (re.compile(r'asm volatile\("mov\.u32 %0, %%smid;"\s*:\s*"=r"\((.+?)\)\);'), r"\1 = simt::smid();"),
+    (re.compile(r'asm volatile\("bar\.sync %0, (\d+);"\s*::\s*"r"\((.+?)\)\s*:\s*"memory"\);'), r"simt::named_barrier(\2, \1);"),
     (re.compile(r'asm volatile\("st\.release\.sys\.global\.u64 \[%0\], %1;"\s*::\s*"l"\((.+?)\),\s*"l"\((.+?)\)\s*:\s*"memory"\);'),
      r"__atomic_store_n((unsigned long long *)(\1), (unsigned long long)(\2), __ATOMIC_RELEASE);"),
     (re.compile(r'asm volatile\("ld\.acquire\.sys\.global\.u64 %0, \[%1\];"\s*:\s*"=l"\((.+?)\)\s*:\s*"l"\((.+?)\)\s*:\s*"memory"\);'),

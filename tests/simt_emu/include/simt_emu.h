@@ -77,7 +77,7 @@ inline unsigned long long g_counts[C_COUNT] = {0};          // global on purpose
 // ------------------------------------------------------------------------------------------------ fibers
 namespace simt {
 
-enum { READY = 0, WAIT_WARP = 1, WAIT_CTA = 2, DONE = 3 };
+enum { READY = 0, WAIT_WARP = 1, WAIT_CTA = 2, DONE = 3, WAIT_NAMED = 4 };
 enum { K_SYNCWARP = 1, K_BALLOT, K_SHFL, K_MATCH };
 
 struct Warp {
@@ -92,6 +92,7 @@ struct Fiber {
     uint3 tid;
     int state, lane;
     unsigned wseq;          // number of warp collectives this lane has completed
+    int nbar;               // named barrier this thread waits at (WAIT_NAMED)
     Warp *warp;
 };
 
@@ -101,6 +102,7 @@ inline thread_local uint3 g_blockIdx = {0, 0, 0};
 inline thread_local dim3 g_blockDim, g_gridDim;
 inline thread_local unsigned char *g_dyn_smem = nullptr;
 inline thread_local int g_cta_waiting = 0;
+inline thread_local int g_named_waiting[16], g_named_count[16];     // bar.sync id, count (ids 1..15)
 inline thread_local unsigned long long g_switches = 0, g_launches = 0;
 
 inline unsigned char *dyn_smem() { return g_dyn_smem; }
@@ -207,6 +209,7 @@ void run_cta(unsigned nthreads, F &body)
     }
     int alive = (int)nthreads;
     g_cta_waiting = 0;
+    memset(g_named_waiting, 0, sizeof(g_named_waiting));
     while (alive > 0) {
         bool progress = false;
         for (unsigned w = 0; w < nwarps; ++w) {
@@ -242,6 +245,13 @@ void run_cta(unsigned nthreads, F &body)
             g_cta_waiting = 0;
             progress = true;
         }
+        for (int b = 1; b < 16; ++b)
+            if (g_named_waiting[b] && g_named_waiting[b] == g_named_count[b]) {     // exited threads never arrive, as on the hardware
+                for (unsigned t = 0; t < nthreads; ++t)
+                    if (fibers[t].state == WAIT_NAMED && fibers[t].nbar == b) fibers[t].state = READY;
+                g_named_waiting[b] = 0;
+                progress = true;
+            }
         if (!progress) die("deadlock: no thread of the CTA can run (divergent barrier?)");
     }
 }
@@ -305,6 +315,22 @@ inline void __syncthreads()
     f->state = simt::WAIT_CTA;
     simt::yield();
 }
+namespace simt {
+// bar.sync id, count: `count` threads of the CTA meet at barrier `id` (1..15)
+inline void named_barrier(int id, int count)
+{
+    SIMT_CNT(C_SYNCTHREADS);
+    if (id < 1 || id > 15 || count < 1) die("named barrier id out of range");
+    Fiber *f = g_cur;
+    if (g_named_waiting[id] && g_named_count[id] != count) die("threads disagree on the count of a named barrier");
+    g_named_count[id] = count;
+    g_named_waiting[id] += 1;
+    if (g_named_waiting[id] > count) die("more threads than its count arrived at a named barrier");
+    f->nbar = id;
+    f->state = WAIT_NAMED;
+    yield();
+}
+}  // namespace simt
 inline void __syncwarp(unsigned = 0xffffffffu) { SIMT_CNT(C_SYNCWARP); simt::warp_collective(simt::K_SYNCWARP, 0); }
 inline void __threadfence_system() {}
 inline void __threadfence() {}

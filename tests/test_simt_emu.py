@@ -477,10 +477,12 @@ def test_emu_antithetic_sampling_bit_exact_and_mirrored(emu, twin, strategy, n, 
 
 
 # ------------------------------------------------------------------------------------- K1: GRU policy (warp per offspring)
-@pytest.mark.parametrize("variant", [0, 1])
-@pytest.mark.parametrize("pomdp,E,sigma", [(True, 5, 0.7), (False, 3, 0.3), (True, 7, 0.7), (False, 1, 0.5)])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("pomdp,E,sigma", [(True, 5, 0.7), (False, 3, 0.3), (True, 7, 0.7), (False, 1, 0.5), (False, 2, 0.5), (True, 4, 0.6),
+                                           (False, 11, 0.4)])
 def test_emu_rollout_gru_philox_bit_exact(emu, twin, pomdp, E, sigma, variant, monkeypatch):
-    """variant 1 (SES_GRU_VARIANT=1): the physics evaluated for both actions on otherwise idle lanes at the start of the step."""
+    """SES_GRU_VARIANT (test build) 0: plain single-warp kernel; 1: the physics evaluated for both actions on otherwise idle lanes
+    at the start of the step; 2 (the product's kernel): a warp PAIR per offspring, episodes split 3 + 2 (E = 1 falls back to 1)."""
     monkeypatch.setenv("SES_GRU_VARIANT", str(variant))
     P = 40
     eng = emu(population=P, group=P, n_head=2, eval_ep_num=E, gru=True, pomdp=pomdp, seed=13)
@@ -491,7 +493,7 @@ def test_emu_rollout_gru_philox_bit_exact(emu, twin, pomdp, E, sigma, variant, m
     assert ts[0] == ts[1]                                   # simple_evolution layout: offspring 0 and 1 are both mu
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 def test_emu_rollout_gru_verification_mode_matches_reference(emu, golden, variant, monkeypatch):
     monkeypatch.setenv("SES_GRU_VARIANT", str(variant))
     g = golden("rollout_cartpole_gru_pomdp")

@@ -48,7 +48,10 @@ def main():
     rng = np.random.default_rng(0)
     if len(sys.argv) > 1 and sys.argv[1] == "gru_converged":
         eng = RolloutEngine("CartPole-v1", 4, 2, True, False, 500, 5, 4097, 4097, 2, 1, seed=0)
-        print(json.dumps({"gru_converged": timed(eng, 0, 0.02, torch.from_numpy(gru_balancing_parent()).cuda(), reps=2)}))
+        print(json.dumps({"gru_converged": timed(eng, 0, 0.02, torch.from_numpy(gru_balancing_parent()).cuda(), reps=3)}))
+        eng.close()
+        eng = RolloutEngine("CartPole-v1", 4, 2, True, True, 500, 5, 4097, 4097, 2, 1, seed=0)
+        print(json.dumps({"gru_gen0": timed(eng, 0, 1.0, torch.zeros(1, 6562, dtype=torch.float32, device="cuda"), reps=3)}))
         return
     if len(sys.argv) > 1 and sys.argv[1] == "classic":
         for env, obs, act in (("MountainCar-v0", 2, 3), ("Acrobot-v1", 6, 3)):
