@@ -31,19 +31,35 @@ for env, obs, act, gru, E, N, cont in CASES:
     torch.cuda.synchronize()
     print(env, "gru" if gru else "mlp", "E", E, "steps", int(steps.sum()), "best", float(fit.max()))
     eng.close()
-# round 2: the CartPole-MLP scheduler paths -- 32 lanes with the strict tail, the straggler phase (ragged generation-0 episodes and a
-# converged population whose last warps run sparse), sparse warps (a launch that does not fill the SMs), integer-key K2
+# round 2: the CartPole-MLP scheduler paths -- episode-granular queues (aligned queue A, exact queue B with re-alignment: the second
+# launch of a case takes its tail length from the first one's mean episode length), the straggler phase (ragged generation-0
+# episodes and a converged population whose last warps run sparse), sparse warps (a launch that does not fill the SMs, forced
+# shares), integer-key K2
 w1 = np.zeros((1, 226), np.float32)
 w1[0, :4] = [0.0, 0.5, 10.0, 3.0]; w1[0, 160 + 32] = 5.0; w1[0, 160] = -5.0
-for P, sigma, parent, knobs in [(3000, 2.0, np.zeros((1, 226), np.float32), {}), (9000, 0.05, w1, {"SES_ROLLOUT_LANES": "32"}),
-                                (8192, 0.05, w1, {}), (600, 0.05, w1, {"SES_K1_SPARSE_RANK": "0", "SES_K1_SPARSE_QUOTA": "1"})]:
-    for k in ("SES_ROLLOUT_LANES", "SES_K1_SPARSE_RANK", "SES_K1_SPARSE_QUOTA"):
+KNOBS = ("SES_ROLLOUT_LANES", "SES_K1_SPARSE_RANK", "SES_K1_SPARSE_QUOTA", "SES_K1_TAIL")
+for P, sigma, parent, knobs in [(3000, 2.0, np.zeros((1, 226), np.float32), {}), (9000, 0.05, w1, {}), (9000, 2.0, w1, {"SES_K1_TAIL": "1"}),
+                                (8192, 0.05, w1, {}), (600, 0.05, w1, {"SES_K1_SPARSE_RANK": "0", "SES_K1_SPARSE_QUOTA": "1"}),
+                                (2500, 2.0, w1, {"SES_K1_SPARSE_RANK": "1", "SES_K1_SPARSE_QUOTA": "3"})]:
+    for k in KNOBS:
         os.environ.pop(k, None)
     os.environ.update(knobs)
     eng = RolloutEngine("CartPole-v1", 4, 2, False, False, 500, 5, P, P, 1, 1, seed=3)
-    fit, steps = eng.rollout(1, sigma, torch.from_numpy(parent).cuda())
-    order, shaped = eng.rank_desc(fit, shaped=True)
-    torch.cuda.synchronize()
+    for gen in (1, 2):
+        fit, steps = eng.rollout(gen, sigma, torch.from_numpy(parent).cuda())
+        order, shaped = eng.rank_desc(fit, shaped=True)
+        torch.cuda.synchronize()
     print("CartPole-v1 scheduler case P", P, knobs, "steps", int(steps.sum()), "best", float(fit.max()))
     eng.close()
+for k in KNOBS:
+    os.environ.pop(k, None)
+# the test build's alternative GRU kernels (2: a warp pair per offspring over named barriers)
+for variant in ("0", "1", "2", "4"):
+    os.environ["SES_GRU_VARIANT"] = variant
+    eng = RolloutEngine("CartPole-v1", 4, 2, True, False, None, 5, 120, 120, 1, 1, seed=1, test_build=True)
+    fit, steps = eng.rollout(0, 1.0, torch.zeros(1, eng.D, dtype=torch.float32, device="cuda"))
+    torch.cuda.synchronize()
+    print("CartPole-v1 gru variant", variant, "steps", int(steps.sum()))
+    eng.close()
+os.environ.pop("SES_GRU_VARIANT", None)
 print("sanitize run complete")
