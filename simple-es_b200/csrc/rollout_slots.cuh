@@ -35,10 +35,26 @@
 
 namespace ses {
 
-constexpr int MAX_PEERS = 8;     // ranks of one NVSwitch box
 constexpr int WORK_COUNTER_TAIL = 1 + 256;   // work_counter: [0] queue A, [1 + smid] CTA arrivals per SM, [WORK_COUNTER_TAIL] queue B
 constexpr int WORK_COUNTER_STEPS = WORK_COUNTER_TAIL + 1;   // (8-byte aligned) env steps of this launch: the launcher's episode-length estimate
-constexpr int WORK_COUNTER_INTS = WORK_COUNTER_STEPS + 2;
+constexpr int WORK_COUNTER_DONE = WORK_COUNTER_STEPS + 2;   // warps of this launch that have finished (folded peer barrier)
+constexpr int WORK_COUNTER_INTS = WORK_COUNTER_DONE + 1;
+
+// The barrier of a rollout launch runs in a SENTINEL CTA (one CTA more than the launch needs, the last block index): it waits
+// until every worker warp of the launch has counted itself out (WORK_COUNTER_DONE; the workers' peer stores are fenced before
+// that), then raises and awaits the flags.  The worker code gains one atomic at its very end and nothing else: a call at the
+// workers' tail instead (last-arriving warp runs the barrier) cost the throughput loop 3.6-9 % through a different register
+// allocation (profiles/r02_k1_experiments.md section 11).
+__device__ __noinline__ void peer_sync_sentinel(const PeerSync s)
+{
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x >= 32) return;
+    if (lane == 0)
+        while (*reinterpret_cast<volatile int *>(s.done) < s.expected) __nanosleep(200);
+    __syncwarp();
+    __threadfence();
+    peer_flag_barrier(s, lane);
+}
 
 struct RolloutParams {
     const float *parents;        // [n_parents][D]
@@ -72,13 +88,15 @@ struct RolloutParams {
     int split_ok;                // Envs with step_split(): a warp left with few episodes and nothing to refill spreads each over 2 / 4 lanes
     int tail_start;              // episodes [0, tail_start) are handed out in whole offspring (queue A = work_counter[0]), the rest --
                                  // EPISODE_UNITS envs: the last round's worth -- in exact numbers (queue B = work_counter[WORK_COUNTER_TAIL])
+    PeerSync sync;               // sync.world > 1: the launch ends with the peer flag barrier (slot kernels)
 };
 
 constexpr int MAX_E = 32;
 
 // Fitness all-gather fused into the rollout: the lane that retires an offspring stores its fitness into the
 // exchange buffer of every peer GPU (plain st.global on NVLink-mapped peer pointers), so no collective has
-// to move the vector afterwards; ses_peer_barrier() publishes the stores.
+// to move the vector afterwards; the flag barrier at the end of the launch (PeerSync) or ses_peer_barrier() publishes the
+// stores.
 __device__ __forceinline__ void publish_fitness(const RolloutParams &p, int id, double f)
 {
     p.fitness[id] = f;
@@ -221,7 +239,9 @@ __device__ __noinline__ void split_phase(Smem *smp, int pomdp, int max_step, int
         run_split<Env, S, 4>(sm, pomdp, max_step, lane, active, slot, nstep, x, xd, th, thd);      // runs them to their end
 }
 
-template <class Env, int S, int WARPS, bool TRACE>
+// PEER: the instance launched when the launch ends with the peer flag barrier (sentinel CTA + one atomic at the workers' end); a
+// separate instance so that single-GPU launches keep the exact code they have without it.
+template <class Env, int S, int WARPS, bool TRACE, bool PEER = false>
 __global__ void __launch_bounds__(WARPS * 32) k_rollout_slots(const RolloutParams p)
 {
     using Smem = SlotSmem<Env, S, !Env::UNIT_REWARD>;
@@ -233,6 +253,12 @@ __global__ void __launch_bounds__(WARPS * 32) k_rollout_slots(const RolloutParam
     const unsigned lt = lanemask_lt();
     const bool usable = lane < p.lanes_used;
 
+    if constexpr (PEER) {
+        if (blockIdx.x == gridDim.x - 1) {                             // the sentinel CTA of a launch that ends with the peer barrier
+            peer_sync_sentinel(p.sync);
+            return;
+        }
+    }
     if (lane < S) { sm.off_id[lane] = -1; sm.ep_first[lane] = 0; sm.ep_cnt[lane] = 0; sm.ep_next[lane] = 0; sm.ep_done[lane] = 0; sm.steps[lane] = 0; }
     __syncwarp();
     // Sparse warps.  A launch whose episodes do not fill every resident warp (one rank's share of an 8-GPU run: 2.3 warps
@@ -456,6 +482,12 @@ __global__ void __launch_bounds__(WARPS * 32) k_rollout_slots(const RolloutParam
     if (lane == 0 && warp_steps) {
         if (p.total_steps) atomicAdd(p.total_steps, warp_steps);
         atomicAdd(reinterpret_cast<unsigned long long *>(p.work_counter + WORK_COUNTER_STEPS), warp_steps);
+    }
+    if constexpr (PEER) {
+        if (lane == 0) {                                               // folded peer barrier: count this warp out (its peer
+            __threadfence_system();                                    // stores first) for the sentinel CTA
+            atomicAdd(p.work_counter + WORK_COUNTER_DONE, 1);
+        }
     }
 }
 

@@ -96,6 +96,9 @@ struct ses_handle {
     int *peer_error = nullptr;
     long long peer_timeout_cycles = 20000000000ll;
     double *last_rollout_fitness = nullptr;       // exchange buffer the last fused-exchange rollout wrote (poisoned on a barrier timeout)
+    int *grad_done = nullptr;                     // arrival counter of k_grad_partial's CTAs (self-resetting)
+    bool peer_fold = false;                       // test build, SES_PEER_FOLD=1: the barriers run inside K1 / k_grad_partial (PeerSync)
+    bool barrier_folded = false;                  // that rollout's launch ended with the flag barrier: the next ses_peer_barrier() is a no-op
     unsigned long long *step_counter = nullptr;   // caller-owned, optional (ses_set_step_counter)
     // rollout launch configuration
     int lanes_used_override = 0;
@@ -227,7 +230,7 @@ extern "C" int ses_destroy(ses_handle *h)
     cudaFree(h->part1);
     for (int r = 0; r < h->peer_world; ++r)
         if (r != h->peer_rank && h->peer_x[r]) cudaIpcCloseMemHandle(h->peer_x[r]);
-    cudaFree(h->xbuf); cudaFree(h->peer_error);
+    cudaFree(h->xbuf); cudaFree(h->peer_error); cudaFree(h->grad_done);
     cudaFree(h->h_parents); cudaFree(h->h_m); cudaFree(h->h_v);
     cudaFree(h->h_fitness); cudaFree(h->h_shaped); cudaFree(h->h_steps); cudaFree(h->h_order); cudaFree(h->h_total);
     cudaFree(h->e_parents); cudaFree(h->e_out); cudaFree(h->e_fitness); cudaFree(h->e_steps); cudaFree(h->e_order); cudaFree(h->e_total);
@@ -247,11 +250,21 @@ extern "C" int ses_set_step_counter(ses_handle *h, uint64_t *counter_dev)
 // ------------------------------------------------------------------------------------------------
 // K1
 // ------------------------------------------------------------------------------------------------
+static ses::PeerSync peer_sync_next(ses_handle *h, double *poison_fitness);
+
 template <class Env, int SL, int WARPS = 4>
 static int launch_slots(ses_handle *h, RolloutParams &rp, int need_warps, bool trace, cudaStream_t st)
 {
     using Smem = SlotSmem<Env, SL, !Env::UNIT_REWARD>;
+#ifdef SES_BUILD_TESTS
+    // SES_PEER_FOLD=1 (test build): the launch ends with the peer flag barrier (PeerSync, sentinel CTA).  Measured and not
+    // adopted: two launches fewer per generation but 0.782 instead of 0.772 ms at N = 8 (profiles/r02_k1_experiments.md section 11)
+    const bool fold = rp.n_peers > 0 && h->peer_fold && !trace;
+    auto kernel = trace ? k_rollout_slots<Env, SL, WARPS, true> : fold ? k_rollout_slots<Env, SL, WARPS, false, true> : k_rollout_slots<Env, SL, WARPS, false>;
+#else
+    const bool fold = false;
     auto kernel = trace ? k_rollout_slots<Env, SL, WARPS, true> : k_rollout_slots<Env, SL, WARPS, false>;
+#endif
     const size_t smem = WARPS * sizeof(Smem);
     rp.slots_cap = SL;
     CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -319,6 +332,13 @@ static int launch_slots(ses_handle *h, RolloutParams &rp, int need_warps, bool t
         }
         if (rp.sparse_rank >= 0) rp.tail_start = 0;                       // shares are counted in episodes: the exact queue only
     }
+    if (fold) {
+        rp.sync = peer_sync_next(h, rp.fitness);
+        rp.sync.done = h->work_counter + WORK_COUNTER_DONE;
+        rp.sync.expected = grid * WARPS;
+        h->barrier_folded = true;
+        grid += 1;                                                         // the sentinel CTA (rollout_slots.cuh)
+    }
     kernel<<<grid, WARPS * 32, smem, st>>>(rp);
     CU(cudaGetLastError());
     h->launches += 1;
@@ -377,6 +397,8 @@ extern "C" int ses_rollout(ses_handle *h, uint32_t generation, float sigma, cons
                     if (r != h->peer_rank) rp.peer_fitness[rp.n_peers++] = h->peer_x[r] + (size_t)parity * c.population;
         h->last_rollout_fitness = rp.n_peers > 0 ? fitness_dev : nullptr;
     }
+    rp.sync.world = 0;
+    h->barrier_folded = false;
 
     // lanes per warp and the grid are chosen per kernel in launch_slots(); the GRU kernel maps a warp to one offspring
     rp.lanes_used = c.eval_ep_num >= 32 ? 32 : c.eval_ep_num * (32 / c.eval_ep_num);
@@ -444,6 +466,8 @@ extern "C" int ses_peer_export(ses_handle *h, void *ipc_handle_out)
         CU(cudaMemset(h->xbuf, 0, sizeof(double) * xbuf_doubles(h)));
         CU(cudaMalloc(&h->peer_error, sizeof(int)));
         CU(cudaMemset(h->peer_error, 0, sizeof(int)));
+        CU(cudaMalloc(&h->grad_done, sizeof(int)));
+        CU(cudaMemset(h->grad_done, 0, sizeof(int)));
         CU(cudaDeviceSynchronize());
     }
     cudaIpcMemHandle_t mh;
@@ -473,6 +497,9 @@ extern "C" int ses_peer_attach(ses_handle *h, const void *ipc_handles, int32_t r
         CU(cudaGetDeviceProperties(&prop, h->cfg.device));
         const long long ms = env_int("SES_PEER_TIMEOUT_MS", 10000);
         h->peer_timeout_cycles = (ms > 0 ? ms : 10000) * (long long)prop.clockRate;      // clockRate is in kHz = cycles per ms
+#ifdef SES_BUILD_TESTS
+        h->peer_fold = env_int("SES_PEER_FOLD", 0) != 0;
+#endif
     }
     return 0;
 }
@@ -488,39 +515,27 @@ extern "C" int ses_peer_fitness_ptr(ses_handle *h, int32_t parity, double **out)
 // within `timeout_cycles` SM cycles (SES_PEER_TIMEOUT_MS, default 10 s at the nominal SM clock; a throttled clock only makes
 // the wait longer) sets the sticky error flag AND poisons this generation's fitness vector with a NaN, so that nothing
 // downstream can silently consume a partially filled vector; B200Loop calls ses_peer_check() every generation and raises.
-__global__ void k_peer_barrier(unsigned long long *my_flags, unsigned long long *p0,
-                               unsigned long long *p1, unsigned long long *p2, unsigned long long *p3, unsigned long long *p4,
-                               unsigned long long *p5, unsigned long long *p6, unsigned long long *p7, int rank, int world,
-                               unsigned long long epoch, long long timeout_cycles, int *error, double *poison)
-{
-    unsigned long long *peers[MAX_PEERS] = {p0, p1, p2, p3, p4, p5, p6, p7};
-    const int r = threadIdx.x;
-    if (r >= world || r == rank) return;
-    __threadfence_system();
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peers[r] + rank), "l"(epoch) : "memory");
-    unsigned long long seen = 0;
-    const long long t0 = clock64();
-    for (;;) {
-        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(my_flags + r) : "memory");
-        if (seen >= epoch) break;
-        if (clock64() - t0 > timeout_cycles) {                                   // a peer died or stalled
-            atomicExch(error, 1);
-            if (poison) poison[0] = __longlong_as_double(0x7ff8000000000000ll);
-            break;
-        }
-    }
-}
+__global__ void k_peer_barrier(const ses::PeerSync s) { ses::peer_flag_barrier(s, threadIdx.x); }
 
 // `poison_fitness`: the exchange buffer of the generation this barrier publishes (nullptr for the gradient-row barrier)
+// the next barrier of this rank (every rank runs the same sequence of barriers, so the epochs agree)
+static ses::PeerSync peer_sync_next(ses_handle *h, double *poison_fitness)
+{
+    ses::PeerSync s;
+    h->peer_epoch += 1;
+    s.my_flags = xbuf_flags(h->xbuf, h);
+    for (int r = 0; r < MAX_PEERS; ++r) s.peer_flags[r] = r < h->peer_world ? xbuf_flags(h->peer_x[r], h) : nullptr;
+    s.rank = h->peer_rank; s.world = h->peer_world; s.epoch = h->peer_epoch; s.timeout_cycles = h->peer_timeout_cycles;
+    s.error = h->peer_error; s.poison = poison_fitness; s.done = nullptr; s.expected = 0;
+    return s;
+}
+
 static int peer_barrier_launch(ses_handle *h, void *stream, double *poison_fitness)
 {
     if (!h || h->peer_world < 2) return fail("ses_peer_barrier: peers not attached");
     CU(cudaSetDevice(h->cfg.device));
-    h->peer_epoch += 1;
-    unsigned long long *f[MAX_PEERS] = {nullptr};
-    for (int r = 0; r < h->peer_world; ++r) f[r] = xbuf_flags(h->peer_x[r], h);
-    k_peer_barrier<<<1, 32, 0, S(stream)>>>(xbuf_flags(h->xbuf, h), f[0], f[1], f[2], f[3], f[4], f[5], f[6], f[7], h->peer_rank,
-                                            h->peer_world, h->peer_epoch, h->peer_timeout_cycles, h->peer_error, poison_fitness);
+    const PeerSync ps = peer_sync_next(h, poison_fitness);
+    k_peer_barrier<<<1, 32, 0, S(stream)>>>(ps);
     h->launches += 1;
     CU(cudaGetLastError());
     return 0;
@@ -529,6 +544,10 @@ static int peer_barrier_launch(ses_handle *h, void *stream, double *poison_fitne
 extern "C" int ses_peer_barrier(ses_handle *h, void *stream)
 {
     if (!h) return fail("ses_peer_barrier: null handle");
+    if (h->barrier_folded) {                 // the rollout that filled the exchange buffer ended with this barrier (PeerSync)
+        h->barrier_folded = false;
+        return 0;
+    }
     return peer_barrier_launch(h, stream, h->last_rollout_fitness);
 }
 
@@ -641,12 +660,20 @@ static int grad_levels01(ses_handle *h, uint32_t generation, const double *shape
             if (r != h->peer_rank) peers.p[n_peers++] = xbuf_part1(h->peer_x[r], h);
     }
     const int n_chunks = (h->NQ + GQC - 1) / GQC;
+    PeerSync sync;
+    sync.world = 0;
+    const bool fold = shard && h->peer_fold && g1 > g0;                  // the launch ends with the flag barrier
+    if (fold) {
+        sync = peer_sync_next(h, nullptr);
+        sync.done = h->grad_done;
+        sync.expected = (g1 - g0) * n_chunks;
+    }
     if (g1 > g0) {
         k_grad_partial<<<(g1 - g0) * n_chunks, GB1 * GQC, 0, st>>>(shaped_dev, P, h->D, h->NQ, h->cfg.seed, generation, lay, eps_override_dev,
-                                                                  part1, h->nb0, g0, n_chunks, n_peers, peers);
+                                                                  part1, h->nb0, g0, n_chunks, n_peers, peers, sync);
         h->launches += 1;
     }
-    if (shard && peer_barrier_launch(h, stream, nullptr)) return -1;
+    if (shard && !fold && peer_barrier_launch(h, stream, nullptr)) return -1;
     *part1_out = part1;
     return 0;
 }

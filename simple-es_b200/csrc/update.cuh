@@ -29,7 +29,7 @@ constexpr int GQC = 4;     // quads per CTA of k_grad_partial (CTA = 64 blocks x
 __global__ void __launch_bounds__(GB1 * GQC) k_grad_partial(const double *__restrict__ shaped, int P, int D, int NQ, uint32_t seed,
                                                             uint32_t gen, Layout layout, const float *__restrict__ eps_override,
                                                             double *__restrict__ part1, int nb0, int g_begin, int n_chunks,
-                                                            int n_peers, PeerRows peers)
+                                                            int n_peers, PeerRows peers, const PeerSync sync)
 {
     __shared__ double sp[GB1][GQC * 4];
     const int g = g_begin + blockIdx.x / n_chunks;
@@ -74,6 +74,20 @@ __global__ void __launch_bounds__(GB1 * GQC) k_grad_partial(const double *__rest
             part1[o] = t;
             for (int r = 0; r < n_peers; ++r) peers.p[r][o] = t;
         }
+        if (n_peers > 0) __threadfence_system();                   // the rows before this CTA's arrival below
+    }
+    // sharded over ranks: the last CTA of the launch runs the flag barrier, so the launch's completion publishes every rank's
+    // rows (PeerSync, ses_common.cuh).  The arrival counter resets itself.
+    if (sync.world > 1) {
+        __shared__ int last_s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            last_s = atomicAdd(sync.done, 1) == sync.expected - 1;
+            if (last_s) atomicExch(sync.done, 0);
+        }
+        __syncthreads();
+        if (last_s && threadIdx.x < 32) { __threadfence(); peer_flag_barrier(sync, threadIdx.x); }
     }
 }
 

@@ -387,6 +387,7 @@ inline T atomicExch(T *p, U v) { const T o = *p; *p = (T)v; return o; }
 template <class T, class U>
 inline T atomicMax(T *p, U v) { const T o = *p; if ((T)v > o) *p = (T)v; return o; }
 
+inline void __nanosleep(unsigned) {}
 inline long long clock64()
 {
     timespec ts;

@@ -652,12 +652,16 @@ def _openai_rank(emu, rank, world, P, gens, seed, barrier, handles, out, shard_m
         raise
 
 
-@pytest.mark.parametrize("world,shard_mode,P", [(2, "cyclic", 301), (3, "contiguous", 200), (8, "cyclic", 2200)])
-def test_emu_peer_exchange_ranks_equal_single_rank(emu, world, shard_mode, P):
+@pytest.mark.parametrize("world,shard_mode,P,fold", [(2, "cyclic", 301, 1), (2, "cyclic", 301, 0), (3, "contiguous", 200, 1), (8, "cyclic", 2200, 1)])
+def test_emu_peer_exchange_ranks_equal_single_rank(emu, world, shard_mode, P, fold, monkeypatch):
     """SURVEY 8e on the emulator: W ranks (threads), each rolling out its shard with the fitness exchange fused into K1
     (stores into every peer's buffer + flag barrier, double buffered by generation parity) and its share of the gradient's
-    level-1 rows, finish every generation with the SAME fitness vector, rank order and (mu, m, v) as one rank doing it all."""
+    level-1 rows, finish every generation with the SAME fitness vector, rank order and (mu, m, v) as one rank doing it all.
+    fold = 0 (the product): separate barrier kernels; fold = 1 (SES_PEER_FOLD=1, test build: measured on 8 B200s and not adopted):
+    the flag barriers run in a sentinel CTA of K1 and in the last CTA of k_grad_partial (PeerSync).  P = 301 at W = 2 leaves
+    rank 0 without gradient rows: it meets the folded barrier of rank 1 with a separate one."""
     import threading
+    monkeypatch.setenv("SES_PEER_FOLD", str(fold))
     gens, seed = 3, 29
     ref = {}
     _openai_rank(emu, 0, 1, P, gens, seed, None, None, ref, None)
