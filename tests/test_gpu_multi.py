@@ -16,6 +16,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _worker(rank, world, port, strategy, exchange, q, shard="cyclic"):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    if exchange == "peer_fold":      # test build: the flag barriers inside K1 (sentinel CTA) and k_grad_partial (last CTA)
+        os.environ.update(SES_B200_TEST_BUILD="1", SES_PEER_FOLD="1")
+        exchange = "peer"
     import yaml
     from simple_es_b200.loop import B200Loop
     cfg = yaml.load(open(os.path.join(ROOT, "conf", {"openai_es": "cartpole_openai.yaml", "simple_evolution": "cartpole.yaml"}[strategy])),
@@ -50,12 +53,13 @@ def _single(strategy):
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 @pytest.mark.parametrize("strategy,exchange,shard", [("openai_es", "nccl", "cyclic"), ("simple_evolution", "nccl", "cyclic"),
                                                      ("openai_es", "peer", "cyclic"), ("simple_evolution", "peer", "cyclic"),
-                                                     ("openai_es", "nccl", "contiguous"), ("simple_evolution", "peer", "contiguous")])
+                                                     ("openai_es", "nccl", "contiguous"), ("simple_evolution", "peer", "contiguous"),
+                                                     ("openai_es", "peer_fold", "cyclic")])
 def test_two_rank_run_equals_single_gpu(strategy, exchange, shard):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29700 + (os.getpid() % 200) + (7 if exchange == "peer" else 0) + (13 if strategy == "openai_es" else 0) + (29 if shard == "cyclic" else 0)
+    port = 29700 + (os.getpid() % 200) + (7 if exchange == "peer" else 3 if exchange == "peer_fold" else 0) + (13 if strategy == "openai_es" else 0) + (29 if shard == "cyclic" else 0)
     procs = [ctx.Process(target=_worker, args=(r, 2, port, strategy, exchange, q, shard)) for r in range(2)]
     for p in procs:
         p.start()

@@ -74,13 +74,15 @@ def test_k1_variants_6_7_branch_free_division_bit_exact(twin, monkeypatch, varia
     assert np.array_equal(steps.cpu().numpy(), ts) and (ts == 2500).mean() > 0.5
 
 
-def test_gru_variant0_plain_kernel_bit_exact(twin, monkeypatch):
-    """SES_GRU_VARIANT=0 (test build): the plain GRU rollout, physics after the argmax -- the default since round 2 is the
-    speculative kernel (the cart-pole step evaluated for both actions on otherwise idle lanes at the start of the step), which
-    every other GRU test runs.  Same bits as the twin (E = 5 and a chunked E = 7, POMDP on / off)."""
+@pytest.mark.parametrize("variant", [0, 1, 2, 4])
+def test_gru_test_build_variants_bit_exact(twin, monkeypatch, variant):
+    """SES_GRU_VARIANT (test build): 0 the plain GRU rollout (physics after the argmax), 1 speculative physics with every table in
+    shared memory, 2 a warp pair per offspring over named barriers (3 + 2 episodes), 4 two tables in registers -- the product's
+    kernel (3: speculative physics, n-gate table in registers) is what every other GRU test runs.  Same bits as the twin
+    (E = 5 and a chunked E = 7, POMDP on / off)."""
     from simple_es_b200.engine import RolloutEngine
     monkeypatch.setenv("SES_B200_TEST_BUILD", "1")
-    monkeypatch.setenv("SES_GRU_VARIANT", "0")
+    monkeypatch.setenv("SES_GRU_VARIANT", str(variant))
     rng = np.random.default_rng(7)
     mu = rng.normal(0, 0.3, (1, 6562)).astype(np.float32)
     for pomdp, E in [(True, 5), (False, 7)]:
