@@ -18,6 +18,9 @@ extern "C" {
  *       5 sin64, 6 cos64 (in/out f64); 7 tanh32 with the division fast path written out (what K1 runs). */
 int ses_test_math(int32_t kind, const void *in_dev, void *out_dev, int64_t n, void *stream);
 int ses_test_normals(ses_handle *h, uint32_t generation, int32_t id, float *out_dev /* [D] */, void *stream);
+/* launch geometry of the handle's last slot-kernel rollout: out[8] = { grid, lanes, tail_start, sparse_rank,
+ * sparse_quota, resident CTAs per SM, resident warps, 0 } -- lets the tests assert which scheduler path a launch took */
+int ses_test_k1_geometry(ses_handle *h, int32_t *out_host /* [8] */);
 /* counts mismatches between K1's 3-instruction x/1.1 and IEEE division over n pseudo-random doubles */
 int ses_test_div_total_mass(uint64_t n, uint64_t *mismatches_host);
 /* counts mismatches between the branch-free double division of K1 variant 6 (ddiv_fast) and IEEE division over n pseudo-random

@@ -57,6 +57,7 @@ SYMBOLS = {
 TEST_SYMBOLS = {
     "ses_test_math": (C.c_int, [_i32, _vp, _vp, _i64, _vp]),
     "ses_test_normals": (C.c_int, [_vp, _u32, _i32, _vp, _vp]),
+    "ses_test_k1_geometry": (C.c_int, [_vp, C.POINTER(C.c_int32)]),
     "ses_test_div_total_mass": (C.c_int, [C.c_uint64, C.POINTER(C.c_uint64)]),
     "ses_test_ddiv_fast": (C.c_int, [C.c_uint64, C.POINTER(C.c_uint64)]),
     "ses_test_tanh_fast_exhaustive": (C.c_int, [_f32, _f32, C.POINTER(C.c_uint64)]),

@@ -97,6 +97,7 @@ struct ses_handle {
     long long peer_timeout_cycles = 20000000000ll;
     double *last_rollout_fitness = nullptr;       // exchange buffer the last fused-exchange rollout wrote (poisoned on a barrier timeout)
     int *grad_done = nullptr;                     // arrival counter of k_grad_partial's CTAs (self-resetting)
+    int k1_geometry[8] = {0};                     // the last slot-kernel launch (ses_test_k1_geometry)
     bool peer_fold = false;                       // test build, SES_PEER_FOLD=1: the barriers run inside K1 / k_grad_partial (PeerSync)
     bool barrier_folded = false;                  // that rollout's launch ended with the flag barrier: the next ses_peer_barrier() is a no-op
     unsigned long long *step_counter = nullptr;   // caller-owned, optional (ses_set_step_counter)
@@ -332,12 +333,9 @@ static int launch_slots(ses_handle *h, RolloutParams &rp, int need_warps, bool t
         }
         if (rp.sparse_rank >= 0) rp.tail_start = 0;                       // shares are counted in episodes: the exact queue only
     }
-    if (fold) {
-        rp.sync = peer_sync_next(h, rp.fitness);
-        rp.sync.done = h->work_counter + WORK_COUNTER_DONE;
-        rp.sync.expected = grid * WARPS;
-        h->barrier_folded = true;
-        grid += 1;                                                         // the sentinel CTA (rollout_slots.cuh)
+    {
+        const int g[8] = {grid, rp.lanes_used, rp.tail_start, rp.sparse_rank, rp.sparse_quota, per_sm, resident_warps, 0};
+        memcpy(h->k1_geometry, g, sizeof(g));
     }
     kernel<<<grid, WARPS * 32, smem, st>>>(rp);
     CU(cudaGetLastError());
@@ -1003,6 +1001,13 @@ __global__ void k_test_normals(uint32_t seed, uint32_t gen, uint32_t id, int D, 
     if (d + 1 < D) out[d + 1] = n.y;
     if (d + 2 < D) out[d + 2] = n.z;
     if (d + 3 < D) out[d + 3] = n.w;
+}
+
+extern "C" int ses_test_k1_geometry(ses_handle *h, int32_t *out_host)
+{
+    if (!h || !out_host) return fail("ses_test_k1_geometry: null argument");
+    for (int i = 0; i < 8; ++i) out_host[i] = h->k1_geometry[i];
+    return 0;
 }
 
 extern "C" int ses_test_normals(ses_handle *h, uint32_t generation, int32_t id, float *out_dev, void *stream)

@@ -359,6 +359,13 @@ class RolloutEngine:
         self._check(self._hooks().ses_test_ddiv_fast(int(n), C.byref(bad)))
         return int(bad.value)
 
+    def test_k1_geometry(self):
+        """Launch geometry of the last slot-kernel rollout (test build): dict of grid, lanes, tail_start, sparse_rank, sparse_quota,
+        ctas_per_sm, resident_warps."""
+        out = (C.c_int32 * 8)()
+        self._check(self._hooks().ses_test_k1_geometry(self._h, out))
+        return dict(zip(("grid", "lanes", "tail_start", "sparse_rank", "sparse_quota", "ctas_per_sm", "resident_warps", "reserved"), list(out)))
+
     def test_normals(self, generation, idx):
         out = torch.empty(self.D, dtype=torch.float32, device=self.device)
         self._check(self._hooks().ses_test_normals(self._h, int(generation), int(idx), _ptr(out), self._stream()))

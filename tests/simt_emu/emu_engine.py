@@ -198,6 +198,11 @@ class EmuEngine:
         self._check(self.lib.ses_test_math(kinds[kind], _p(x), _p(out), x.size, None))
         return out
 
+    def test_k1_geometry(self):
+        out = (C.c_int32 * 8)()
+        self._check(self.lib.ses_test_k1_geometry(self._h, out))
+        return dict(zip(("grid", "lanes", "tail_start", "sparse_rank", "sparse_quota", "ctas_per_sm", "resident_warps", "reserved"), list(out)))
+
     def test_normals(self, generation, idx):
         out = np.full(self.D, np.nan, dtype=np.float32)
         self._check(self.lib.ses_test_normals(self._h, int(generation), int(idx), _p(out), None))

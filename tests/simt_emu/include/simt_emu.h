@@ -500,7 +500,12 @@ inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 template <class K>
 inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return cudaSuccess; }
 template <class K>
-inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, K, int, size_t) { *n = 2; return cudaSuccess; }
+inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, K, int, size_t)
+{
+    const char *v = getenv("SES_SIMT_EMU_CTAS_PER_SM");            // resident CTAs per emulated SM (default 2)
+    *n = v && *v && atoi(v) > 0 ? atoi(v) : 2;
+    return cudaSuccess;
+}
 // "IPC": the emulated ranks of a multi-GPU test live in ONE process (one OS thread per rank), so a memory handle is just
 // the pointer and a peer mapping is the buffer itself
 inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) { memset(h, 0, sizeof(*h)); memcpy(h->reserved, &p, sizeof(p)); return cudaSuccess; }

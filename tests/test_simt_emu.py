@@ -111,6 +111,26 @@ def test_emu_rollout_launch_geometry_never_changes_a_bit(emu, twin, knobs, monke
             assert np.array_equal(steps, ts) and np.array_equal(fit, tf)
 
 
+@pytest.mark.parametrize("sms,ctas", [(2, 3), (3, 2)])
+def test_emu_rollout_multi_round_converged_launches(emu, twin, sms, ctas, monkeypatch):
+    """Multi-round launches of full-length episodes (queue A, then the exact queue B for the last two rounds' worth), three
+    generations each so that the adaptive tail sees a converged previous launch; 2 / 3 resident CTAs per emulated SM.  The
+    launcher's choice is read back through the geometry hook; same bits as the twin."""
+    monkeypatch.setenv("SES_SIMT_EMU_SMS", str(sms))
+    monkeypatch.setenv("SES_SIMT_EMU_CTAS_PER_SM", str(ctas))
+    for P in (230, 270, 420):
+        eng = emu(population=P, group=P, n_head=1, eval_ep_num=5, seed=37, max_step=60)
+        for gen in (0, 1, 2):
+            fit, steps = eng.rollout(gen, 0.02, _trained_mu())
+            g = eng.test_k1_geometry()
+            assert g["ctas_per_sm"] == ctas and g["resident_warps"] == sms * ctas * 4 and g["lanes"] == 32 and g["sparse_rank"] < 0
+            assert g["tail_start"] == max(0, (P * 5 - 2 * 32 * g["resident_warps"]) // 5 * 5)       # two rounds of exact requests
+            tf, ts = twin.population_cartpole(_trained_mu(), sigma=0.02, seed=37, gen=gen, group=P, n_head=1, n=P, E=5, max_step=60, nthreads=4)
+            assert np.array_equal(steps, ts) and np.array_equal(fit, tf)
+            assert (ts == 300).mean() > 0.9                 # converged: (nearly) every episode runs to the truncation
+        eng.close()
+
+
 @pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7])
 def test_emu_rollout_k1_variants_bit_exact(emu, twin, variant, monkeypatch):
     """Every K1 code path (scalar / packed FFMA2, permuted slot table, weights of the lane's slot in registers) is the
