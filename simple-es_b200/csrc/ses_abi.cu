@@ -263,7 +263,7 @@ static int launch_slots(ses_handle *h, RolloutParams &rp, int need_warps, bool t
     const bool fold = rp.n_peers > 0 && h->peer_fold && !trace;
     auto kernel = trace ? k_rollout_slots<Env, SL, WARPS, true> : fold ? k_rollout_slots<Env, SL, WARPS, false, true> : k_rollout_slots<Env, SL, WARPS, false>;
 #else
-    const bool fold = false;
+    [[maybe_unused]] const bool fold = false;
     auto kernel = trace ? k_rollout_slots<Env, SL, WARPS, true> : k_rollout_slots<Env, SL, WARPS, false>;
 #endif
     const size_t smem = WARPS * sizeof(Smem);
@@ -336,6 +336,13 @@ static int launch_slots(ses_handle *h, RolloutParams &rp, int need_warps, bool t
     {
         const int g[8] = {grid, rp.lanes_used, rp.tail_start, rp.sparse_rank, rp.sparse_quota, per_sm, resident_warps, 0};
         memcpy(h->k1_geometry, g, sizeof(g));
+    }
+    if (fold) {
+        rp.sync = peer_sync_next(h, rp.fitness);
+        rp.sync.done = h->work_counter + WORK_COUNTER_DONE;
+        rp.sync.expected = grid * WARPS;
+        h->barrier_folded = true;
+        grid += 1;                                                         // the sentinel CTA (rollout_slots.cuh)
     }
     kernel<<<grid, WARPS * 32, smem, st>>>(rp);
     CU(cudaGetLastError());
