@@ -19,7 +19,9 @@ constexpr int GB1 = 64;
 
 struct PeerRows { double *p[8]; };
 
-constexpr int GQC = 4;     // quads per CTA of k_grad_partial (CTA = 64 blocks x 4 quads = 256 threads)
+// quads per CTA of k_grad_partial (CTA = 64 blocks x GQC quads).  A pure launch-shape parameter: 2 (928 CTAs of 128 threads at
+// P = 65536, 6.3 per SM) balances the 148 SMs better than 4 (480 CTAs, 3.2 per SM): 59 -> 54 us per update on a B200.
+constexpr int GQC = 2;
 
 // levels 0 and 1 fused: CTA <-> (group g, chunk of GQC quads); thread <-> (block b of the group, quad q).
 // Level 0 runs in registers (32 sequential fma per parameter), the 64 block partials of the group meet in
