@@ -173,10 +173,9 @@ __device__ __forceinline__ unsigned long long sort_key(const double *__restrict_
     return ((2ull << key_bits) - 1ull) - (unsigned long long)v;
 }
 
-// pass-0 histogram straight from the fitness vector
+// pass-0 histogram straight from the fitness vector (one tile = one CTA)
 template <int SORT_ITEMS>
-__global__ void __launch_bounds__(SORT_THREADS) k_sort_hist_first(const double *__restrict__ fitness, int n, int key_bits, double key_scale,
-                                                                  int *__restrict__ hist)
+__device__ __forceinline__ void sort_hist_first_tile(const double *__restrict__ fitness, int n, int key_bits, double key_scale, int *hist)
 {
     constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
     __shared__ int h[256];
@@ -195,16 +194,25 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_hist_first(const double *
     hist[blockIdx.x * 256 + threadIdx.x] = h[threadIdx.x];
 }
 
+template <int SORT_ITEMS>
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_hist_first(const double *__restrict__ fitness, int n, int key_bits, double key_scale,
+                                                                  int *__restrict__ hist)
+{
+    sort_hist_first_tile<SORT_ITEMS>(fitness, n, key_bits, key_scale, hist);
+}
+
+// loads of data other CTAs of the SAME launch wrote (the persistent kernel below): L2 only, an SM's L1 may hold a stale line
+template <bool COHERENT, class T>
+__device__ __forceinline__ T sort_ld(const T *p) { if constexpr (COHERENT) return __ldcg(p); else return *p; }
+
 // one stable scatter pass; `first`: keys come from the fitness vector; `last`: no next pass -- write the permutation
 // (vals_out) and, if shaped != nullptr, the centered ranks; otherwise also accumulate hist_next (zeroed by the host) for
 // the digit at shift + 8.  Digit totals are the column sums of the tile histograms (no separate table).
-template <int SORT_ITEMS>
-__global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter_fused(const double *__restrict__ fitness, int key_bits, double key_scale,
-                                                                     const unsigned long long *__restrict__ keys_in,
-                                                                     const int *__restrict__ vals_in, int n, int shift, int first, int last,
-                                                                     const int *__restrict__ hist, int *__restrict__ hist_next,
-                                                                     unsigned long long *__restrict__ keys_out, int *__restrict__ vals_out,
-                                                                     double stdv, double *__restrict__ shaped)
+template <int SORT_ITEMS, bool COHERENT>
+__device__ __forceinline__ void sort_scatter_fused_tile(const double *__restrict__ fitness, int key_bits, double key_scale,
+                                                        const unsigned long long *keys_in, const int *vals_in, int n, int shift, int first, int last,
+                                                        const int *hist, int *hist_next, unsigned long long *keys_out, int *vals_out,
+                                                        double stdv, double *shaped)
 {
     constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS, SORT_WSEG = 32 * SORT_ITEMS;
     __shared__ int digit_base[256];
@@ -217,7 +225,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter_fused(const doubl
     {   // (a) global base of digit d for this CTA: sum_{d'<d} tot[d'] + sum_{c<cta} hist[c][d], tot[d] = sum_c hist[c][d]
         int t = 0, below = 0;
         for (int c = 0; c < (int)gridDim.x; ++c) {
-            const int v = hist[c * 256 + tid];
+            const int v = sort_ld<COHERENT>(hist + c * 256 + tid);
             t += v;
             if (c < (int)blockIdx.x) below += v;
         }
@@ -246,8 +254,8 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter_fused(const doubl
             key[it] = ok ? sort_key(fitness, n, p, key_bits, key_scale) : 0ull;
             val[it] = ok ? n - 1 - p : -1;
         } else {
-            key[it] = ok ? keys_in[p] : 0ull;
-            val[it] = ok ? vals_in[p] : -1;
+            key[it] = ok ? sort_ld<COHERENT>(keys_in + p) : 0ull;
+            val[it] = ok ? sort_ld<COHERENT>(vals_in + p) : -1;
         }
         const int d = ok ? (int)((key[it] >> shift) & 255ull) : (256 + lane);
         const unsigned peers = __match_any_sync(FULL, d);
@@ -290,6 +298,58 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter_fused(const doubl
             shaped[val[it]] = __ddiv_rn(v, stdv);
         }
         __syncwarp();
+    }
+}
+
+template <int SORT_ITEMS>
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter_fused(const double *__restrict__ fitness, int key_bits, double key_scale,
+                                                                     const unsigned long long *__restrict__ keys_in,
+                                                                     const int *__restrict__ vals_in, int n, int shift, int first, int last,
+                                                                     const int *__restrict__ hist, int *__restrict__ hist_next,
+                                                                     unsigned long long *__restrict__ keys_out, int *__restrict__ vals_out,
+                                                                     double stdv, double *__restrict__ shaped)
+{
+    sort_scatter_fused_tile<SORT_ITEMS, false>(fitness, key_bits, key_scale, keys_in, vals_in, n, shift, first, last, hist, hist_next, keys_out, vals_out,
+                                               stdv, shaped);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent variant: the whole sort in ONE cooperative launch.  Every CTA keeps its tile through the pass-0 histogram and all
+// scatter passes; the launch boundaries of the fused build (each worth ~3.6 us of a kernel that does a few microseconds of
+// work) become grid barriers (an arrival counter in global memory, zeroed with the histograms; all CTAs are co-resident:
+// cudaLaunchCooperativeKernel refuses the launch otherwise and the caller falls back to the fused build).  Data written by
+// other CTAs earlier in the launch is read through L2 (sort_ld<true>).  Same tile code, same positions, same permutation.
+// Used for float64 keys (8 passes: 82 -> 72 us at P = 16384); for integer keys (2 passes) the fused build is as fast.
+// ---------------------------------------------------------------------------------------------
+struct SortBuffers {
+    unsigned long long *keys[2];
+    int *vals[2];            // ping-pong, arranged by the host so that the last pass writes the caller's order array
+};
+
+__device__ __forceinline__ void sort_grid_barrier(unsigned *bar, unsigned target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        while (*reinterpret_cast<volatile unsigned *>(bar) < target) __nanosleep(64);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+template <int SORT_ITEMS>
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_persistent(const double *__restrict__ fitness, int n, int key_bits, double key_scale, int passes,
+                                                                  SortBuffers buf, int *hist_all, int per_pass, unsigned *bar, double stdv,
+                                                                  double *shaped)
+{
+    sort_hist_first_tile<SORT_ITEMS>(fitness, n, key_bits, key_scale, hist_all);
+    sort_grid_barrier(bar, gridDim.x);
+    for (int ps = 0; ps < passes; ++ps) {
+        const int a = ps & 1, b = a ^ 1, last = ps == passes - 1;
+        sort_scatter_fused_tile<SORT_ITEMS, true>(fitness, key_bits, key_scale, buf.keys[a], buf.vals[a], n, 8 * ps, ps == 0, last, hist_all + (size_t)per_pass * ps,
+                                                  last ? nullptr : hist_all + (size_t)per_pass * (ps + 1), buf.keys[b], buf.vals[b], stdv, shaped);
+        if (!last) sort_grid_barrier(bar, (unsigned)(ps + 2) * gridDim.x);
     }
 }
 

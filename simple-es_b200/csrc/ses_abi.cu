@@ -74,6 +74,7 @@ struct ses_handle {
     int *tot = nullptr;            // [8][256]
     int *hist_fused = nullptr;     // fused K2: [passes][tiles][256] tile histograms, zeroed per call
     int k2_fused = 1;
+    int k2_persistent = 1;         // the whole sort in one cooperative launch (falls back to the fused build if the launch is refused)
     double *part1 = nullptr;
     int nb0 = 0, nb1 = 0, n_tiles = 0;
     // scratch for the host-buffer generation path
@@ -194,6 +195,7 @@ extern "C" int ses_create(const ses_config *cfg, ses_handle **out)
     h->spread_slots8 = env_int("SES_SPREAD_SLOTS8", 0);
     h->k2_fused = env_int("SES_K2_FUSED", 1);     // 1 + passes launches (default); 0: the separate kernels
 #endif
+    h->k2_persistent = env_int("SES_K2_PERSISTENT", 1);   // 1: one cooperative launch for the whole sort (default); 0: the fused build
     h->k1_split = env_int("SES_K1_SPLIT", 1);
     h->k1_sparse = env_int("SES_K1_SPARSE", 1);
     if (h->k1_variant < 0 || h->k1_variant > 7) h->k1_variant = 7;
@@ -212,7 +214,7 @@ extern "C" int ses_create(const ses_config *cfg, ses_handle **out)
     CU(cudaMalloc(&h->vals_scratch, sizeof(int) * P));
     CU(cudaMalloc(&h->hist, sizeof(int) * h->n_tiles * 256));
     CU(cudaMalloc(&h->tot, sizeof(int) * 8 * 256));
-    CU(cudaMalloc(&h->hist_fused, sizeof(int) * 8 * (size_t)h->n_tiles * 256));
+    CU(cudaMalloc(&h->hist_fused, sizeof(int) * (8 * (size_t)h->n_tiles * 256 + 1)));   // + the persistent kernel's grid-barrier counter
     CU(cudaMalloc(&h->part1, sizeof(double) * (size_t)h->nb1 * h->DP));
     *out = h;
     return 0;
@@ -591,7 +593,28 @@ extern "C" int ses_rank_desc(ses_handle *h, const double *fitness_dev, int32_t n
         if (shaped_dev && n < 2) return fail("ses_rank_desc: centered ranks need n >= 2");
         const double stdv = n >= 2 ? sqrt((double)(n + 1) / (12.0 * (double)(n - 1))) : 1.0;
         const size_t per_pass = (size_t)tiles * 256;                      // [tiles][256] tile histograms of one pass
-        CU(cudaMemsetAsync(h->hist_fused, 0, sizeof(int) * per_pass * passes, st));
+        CU(cudaMemsetAsync(h->hist_fused, 0, sizeof(int) * (per_pass * passes + 1), st));
+#ifndef SES_SIMT_EMU
+        // float64 keys (8 passes) only: 82 -> 72 us at P = 16384; with the 2 passes of integer keys the grid barriers, the
+        // L2-only loads and the cooperative launch cost what the two launch boundaries did (26.0 -> 27.3 us at P = 65536)
+        if (h->k2_persistent && passes >= 4) {
+            SortBuffers buf;
+            buf.keys[0] = h->keys[0]; buf.keys[1] = h->keys[1]; buf.vals[0] = vals[0]; buf.vals[1] = vals[1];
+            int *hist_all = h->hist_fused;
+            unsigned *bar = reinterpret_cast<unsigned *>(h->hist_fused + per_pass * passes);
+            int n_arg = n, kb = key_bits, passes_arg = passes, pp = (int)per_pass;
+            double ks = key_scale, stdv_arg = stdv;
+            void *args[] = {(void *)&fitness_dev, &n_arg, &kb, &ks, &passes_arg, &buf, &hist_all, &pp, &bar, &stdv_arg, (void *)&shaped_dev};
+            const void *fn = small ? (const void *)k_sort_persistent<SORT_ITEMS_SMALL> : (const void *)k_sort_persistent<SORT_ITEMS_LARGE>;
+            const cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(tiles), dim3(SORT_THREADS), args, 0, st);
+            if (e == cudaSuccess) {
+                h->launches += 1;
+                return 0;
+            }
+            (void)cudaGetLastError();                              // refused (not co-resident, no cooperative launch): the fused build from now on
+            h->k2_persistent = 0;
+        }
+#endif
         if (small) k_sort_hist_first<SORT_ITEMS_SMALL><<<tiles, SORT_THREADS, 0, st>>>(fitness_dev, n, key_bits, key_scale, h->hist_fused);
         else k_sort_hist_first<SORT_ITEMS_LARGE><<<tiles, SORT_THREADS, 0, st>>>(fitness_dev, n, key_bits, key_scale, h->hist_fused);
         h->launches += 1;

@@ -388,6 +388,8 @@ template <class T, class U>
 inline T atomicMax(T *p, U v) { const T o = *p; if ((T)v > o) *p = (T)v; return o; }
 
 inline void __nanosleep(unsigned) {}
+template <class T>
+inline T __ldcg(const T *p) { return *p; }
 inline long long clock64()
 {
     timespec ts;

@@ -248,12 +248,14 @@ def test_rollout_full_size_properties():
 
 
 # ------------------------------------------------------------------------------------- K2
-@pytest.mark.parametrize("fused", [0, 1])
+@pytest.mark.parametrize("fused", [0, 1, 2])
 @pytest.mark.parametrize("n", [2, 97, 4097, 65536, 1 << 20])
 def test_rank_desc_bit_exact(n, fused, monkeypatch):
-    """Both K2 builds: separate init / histogram / scatter / shape kernels, and SES_K2_FUSED=1 (1 + passes launches)."""
+    """All K2 builds: separate init / histogram / scatter / shape kernels (0, test build), the fused build (1: 1 + passes launches)
+    and the product's persistent kernel (2: the whole sort in one cooperative launch, grid barriers between the passes)."""
     monkeypatch.setenv("SES_B200_TEST_BUILD", "1")
-    monkeypatch.setenv("SES_K2_FUSED", str(fused))
+    monkeypatch.setenv("SES_K2_FUSED", str(min(fused, 1)))
+    monkeypatch.setenv("SES_K2_PERSISTENT", "1" if fused == 2 else "0")
     eng = _engine(population=max(n, 2), group=max(n, 2))
     rng = np.random.default_rng(n)
     for kind in ("float", "ties", "cartpole"):
@@ -264,8 +266,10 @@ def test_rank_desc_bit_exact(n, fused, monkeypatch):
         else:
             r = rng.integers(40, 2501, n) / 5.0
         want = np.flip(np.argsort(r, kind="stable")).astype(np.int32)
+        l0 = eng.launches
         got = eng.rank_desc(_cuda(r), full_key=True).cpu().numpy()
         assert np.array_equal(got, want), kind
+        assert eng.launches - l0 == {0: 18, 1: 9, 2: 1}[fused] - (1 if fused == 0 else 0)      # float64 keys: 8 passes (no shaping kernel here)
         if kind == "cartpole":                                     # integer-key fast path
             got, shaped = eng.rank_desc(_cuda(r), shaped=True)
             assert np.array_equal(got.cpu().numpy(), want)

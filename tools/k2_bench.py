@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""K2 A/B on one GPU: ses_rank_desc (rank + centered ranks) with the separate kernels (2 + 2*passes launches) and the
-fused build (SES_K2_FUSED=1: 1 + passes launches).  CUDA events, 5 warm-up + 50 timed calls, microseconds per call.
+"""K2 A/B on one GPU: ses_rank_desc (rank + centered ranks) with the fused build (SES_K2_PERSISTENT=0: 1 + passes launches) and
+the persistent kernel (one cooperative launch, grid barriers between the passes).  CUDA events, 5 warm-up + 50 timed calls,
+microseconds per call.
 
     python tools/k2_bench.py            (writes gpurun_out/k2_ab.jsonl)
 """
@@ -32,7 +33,7 @@ def main():
             fit = torch.from_numpy(rng.integers(40, 2501, P) / 5.0).cuda()
         res = {}
         for fused in (0, 1):
-            os.environ["SES_K2_FUSED"] = str(fused)
+            os.environ["SES_K2_PERSISTENT"] = str(fused)
             eng = RolloutEngine("CartPole-v1", 4, 2, False, False, 500, 5, P, P, 1, 1, seed=0)
             order = torch.empty(P, dtype=torch.int32, device="cuda"); shaped = torch.empty(P, dtype=torch.float64, device="cuda")
             full = kind == "float"
@@ -47,8 +48,8 @@ def main():
             res[fused] = (e0.elapsed_time(e1) * 1e3 / 50, (eng.launches - l0) // 50, order.clone(), shaped.clone())
             eng.close()
         same = bool(torch.equal(res[0][2], res[1][2]) and torch.equal(res[0][3], res[1][3]))
-        line = {"case": name, "P": P, "unfused_us": res[0][0], "unfused_launches": res[0][1], "fused_us": res[1][0],
-                "fused_launches": res[1][1], "identical_outputs": same}
+        line = {"case": name, "P": P, "fused_us": res[0][0], "fused_launches": res[0][1], "persistent_us": res[1][0],
+                "persistent_launches": res[1][1], "identical_outputs": same}
         print(json.dumps(line)); out.write(json.dumps(line) + "\n")
     out.close()
 
