@@ -150,6 +150,9 @@ extern "C" int ses_create(const ses_config *cfg, ses_handle **out)
     }
     if (cfg->eval_ep_num < 1 || cfg->eval_ep_num > 32) return fail("ses_create: eval_ep_num must be in [1, 32] (got %d)", cfg->eval_ep_num);
     if (cfg->population < 2) return fail("ses_create: population must be >= 2");
+    // the work queue counts episodes in 32-bit integers (headroom for the requests that overshoot the end of the queue)
+    if ((long long)cfg->population * cfg->eval_ep_num > (1ll << 30))
+        return fail("ses_create: population x eval_ep_num = %lld exceeds 2^30 episodes per generation", (long long)cfg->population * cfg->eval_ep_num);
     if (cfg->group < 1 || cfg->n_head < 0 || cfg->n_parents < 1) return fail("ses_create: bad population layout");
     if (cfg->antithetic != 0 && cfg->antithetic != 1) return fail("ses_create: antithetic must be 0 or 1");
     if (cfg->id_begin < 0 || cfg->id_end > cfg->population || cfg->id_begin > cfg->id_end) return fail("ses_create: bad slice [%d, %d)", cfg->id_begin, cfg->id_end);

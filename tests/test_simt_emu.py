@@ -622,6 +622,17 @@ def test_emu_rollout_pendulum_traces_equal_the_twin(emu, twin, golden):
     np.testing.assert_allclose(fit, g["fitness"][:10], rtol=1e-4)            # vs the reference path (north_star tolerance)
 
 
+def test_emu_create_rejects_more_than_2_30_episodes(emu):
+    """The episode queue is 32-bit: population x eval_ep_num is bounded at create time (the reference has no such scale)."""
+    from simple_es_b200 import _lib as product_lib
+    import ctypes as C
+    eng = emu()
+    P = (1 << 26) + 8
+    cfg = product_lib.ses_config(env=0, obs_dim=4, act_dim=2, eval_ep_num=32, population=P, group=P, n_head=1, n_parents=1, id_end=P)
+    h = C.c_void_p()
+    assert eng.lib.ses_create(C.byref(cfg), C.byref(h)) != 0 and b"2^30 episodes" in eng.lib.ses_last_error()
+
+
 def test_emu_continuous_head_needs_pendulum(emu):
     from simple_es_b200 import _lib as product_lib
     import ctypes as C

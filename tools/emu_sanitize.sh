@@ -20,6 +20,6 @@ subprocess.check_call(["g++"] + base + ["-fsanitize=address", "-fno-omit-frame-p
                                         "-o", os.path.join(b.BUILD, "libses_simt_emu_asan.so"), src])
 PY
 B=$PWD/tests/simt_emu/_build
-echo "== UBSan"; SES_SIMT_EMU_LIB=$B/libses_simt_emu_ubsan.so UBSAN_OPTIONS=print_stacktrace=1 python -m pytest tests/test_simt_emu.py -x -q -p no:cacheprovider | tail -2
+echo "== UBSan"; SES_SIMT_EMU_LIB=$B/libses_simt_emu_ubsan.so UBSAN_OPTIONS=print_stacktrace=1 python -m pytest tests/test_simt_emu.py tests/test_gru_generic.py -m "not gpu" -x -q -p no:cacheprovider | tail -2
 echo "== ASan";  LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0 \
-    SES_SIMT_EMU_LIB=$B/libses_simt_emu_asan.so python -m pytest tests/test_simt_emu.py -x -q -p no:cacheprovider | tail -2
+    SES_SIMT_EMU_LIB=$B/libses_simt_emu_asan.so python -m pytest tests/test_simt_emu.py tests/test_gru_generic.py -m "not gpu" -x -q -p no:cacheprovider | tail -2
