@@ -36,6 +36,7 @@ FLOP_PER_STEP = 418          # 192 FMA + 34 bias adds per 
 FMA_LANE_OPS_PER_STEP = 640  # executed on the FP32 FMA pipe per env step: fc1 128 + fc2 64 + 32 tanh x 14
 K1_DRAM_BYTES_PER_LAUNCH = 168192       # dram__bytes_read.sum + dram__bytes_write.sum of K1 in profiles/r02_k1_conv.txt (one converged launch, P = 65536)
 K1_PROFILE = "profiles/r02_k1_conv.txt"
+GRU_WAVEFRONTS_PER_OFFSPRING_STEP = 288   # see run_extra_config: algorithmic shared-memory wavefronts of the CartPole-GRU kernel
 K1_SYMBOL = "ses::k_rollout_slots<ses::CartpoleMlpEnvT<7>, 8, 4, false, false>"   # the kernel ses_rollout launches for this workload
 STRATEGY = dict(name="openai_es", init_sigma=0.2, sigma_decay=0.9999, learning_rate=0.1)
 
@@ -392,6 +393,27 @@ def run_extra_config(key, path, overrides, note, local, world, steps, warmup, fl
            "steps": steps, "warmup": warmup, "ms_per_generation": ms / steps, "generations_per_sec": steps / (ms * 1e-3),
            "env_steps_per_sec": n / (ms * 1e-3), "env_steps": n, "mean_episode_len": n / float(steps * s.P * E_DEFAULT),
            "best_reward_last_gen": best, "n_gpus": world, "regime": "generations %d..%d of a run started from %s" % (warmup, warmup + steps - 1, "mu = 0" if init is None else init)}
+    if key == "c2_converged_gru_pop4096" and world == 1:
+        # The GRU rollout kernel is bound by the shared-memory crossbar (one wavefront per cycle per SM), not by the FMA pipe
+        # (profiles/r02_gru_variants_ncu.txt).  Algorithmic wavefronts per offspring-step (E = 5 episodes in lockstep):
+        # two weight tables x 16 conflict-free LDS.128 x 4 wavefronts + 80 broadcast LDS.128 x 2 = 288 (the n-gate table lives in
+        # registers); ncu counts 365 with the staging stores and the logit reads.  One offspring-step = E env steps.
+        sms = torch.cuda.get_device_properties(s.engine.device).multi_processor_count
+        mhz = 1965.0                                                    # B200 max SM clock (B200_PROFILING.md); NVML's value if it answers
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(pynvml.nvmlDeviceGetHandleByIndex(local), pynvml.NVML_CLOCK_SM))
+        except Exception:
+            pass
+        peak = sms * mhz * 1e6 / 1e9
+        achieved = GRU_WAVEFRONTS_PER_OFFSPRING_STEP * (n / float(E_DEFAULT)) / (ms * 1e-3) / 1e9
+        out["roofline"] = {"bound": "shared_memory", "kernel": "ses::k_rollout_cartpole_gru<5, 4, false, true, 1>", "achieved": achieved, "peak": peak,
+                           "unit": "Gwavefronts/s", "frac": achieved / peak,
+                           "algorithmic": "%d shared-memory wavefronts per offspring-step x %d offspring-steps / %.3f ms of whole generations (K1 is 97 %% of them)"
+                                          % (GRU_WAVEFRONTS_PER_OFFSPRING_STEP, n // E_DEFAULT, ms),
+                           "peak_source": "%d SMs x 1 wavefront per cycle x %.0f MHz (the max SM clock; ncu of the kernel alone: 62 %% of the wavefront peak, "
+                                          "profiles/r02_gru_variants_ncu.txt)" % (sms, mhz)}
     if s.exchange == "peer":
         s.engine.peer_check()
     del loop, s
