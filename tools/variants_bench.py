@@ -53,6 +53,10 @@ def main():
         eng = RolloutEngine("CartPole-v1", 4, 2, True, True, 500, 5, 4097, 4097, 2, 1, seed=0)
         print(json.dumps({"gru_gen0": timed(eng, 0, 1.0, torch.zeros(1, 6562, dtype=torch.float32, device="cuda"), reps=3)}))
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "spread3":
+        eng = RolloutEngine("simple_spread", 18, 5, False, False, "None", 5, 16384, 16384, 1, 1, seed=0, n_agents=3, init_mode="fresh")
+        print(json.dumps({"spread_n3": timed(eng, 0, 0.2, torch.zeros(1, 6 * 3 * 32 + 32 + 165, dtype=torch.float32, device="cuda"), reps=2)}))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "classic":
         for env, obs, act in (("MountainCar-v0", 2, 3), ("Acrobot-v1", 6, 3)):
             eng = RolloutEngine(env, obs, act, False, False, None, 5, 16384, 16384, 1, 1, seed=0, init_mode="fresh")
