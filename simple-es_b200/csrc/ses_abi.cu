@@ -205,6 +205,7 @@ extern "C" int ses_create(const ses_config *cfg, ses_handle **out)
 
     const int P = cfg->population;
     h->n_tiles = (P + sort_tile(SORT_ITEMS_SMALL) - 1) / sort_tile(SORT_ITEMS_SMALL);
+    if (P <= (1 << 15)) h->n_tiles = (P + sort_tile(1) - 1) / sort_tile(1);    // the persistent kernel's 256-key tiles (ses_rank_desc)
     h->nb0 = (P + GB0 - 1) / GB0;
     h->nb1 = (h->nb0 + GB1 - 1) / GB1;
     CU(cudaMalloc(&h->work_counter, sizeof(int) * WORK_COUNTER_INTS));
@@ -596,20 +597,27 @@ extern "C" int ses_rank_desc(ses_handle *h, const double *fitness_dev, int32_t n
         if (shaped_dev && n < 2) return fail("ses_rank_desc: centered ranks need n >= 2");
         const double stdv = n >= 2 ? sqrt((double)(n + 1) / (12.0 * (double)(n - 1))) : 1.0;
         const size_t per_pass = (size_t)tiles * 256;                      // [tiles][256] tile histograms of one pass
-        CU(cudaMemsetAsync(h->hist_fused, 0, sizeof(int) * (per_pass * passes + 1), st));
 #ifndef SES_SIMT_EMU
-        // float64 keys (8 passes) only: 82 -> 72 us at P = 16384; with the 2 passes of integer keys the grid barriers, the
+        // float64 keys (8 passes) only: 82 -> 64 us at P = 16384; with the 2 passes of integer keys the grid barriers, the
         // L2-only loads and the cooperative launch cost what the two launch boundaries did (26.0 -> 27.3 us at P = 65536)
-        if (h->k2_persistent && passes >= 4) {
+        const bool persistent = h->k2_persistent && passes >= 4;
+        // small populations: 512-key tiles put twice the CTAs on the latency-bound passes (P = 16384: 71.7 -> 63.6 us; 256-key tiles
+        // 76.4 us: the per-tile histogram walk and the barrier grow with the CTA count); SES_K2_TILE_ITEMS = 1 | 2 | 4 for experiments
+        const int items = persistent && h->cfg.population <= (1 << 15) ? env_int("SES_K2_TILE_ITEMS", 2) : 0;
+        const int ptiles = items == 1 ? (n + sort_tile(1) - 1) / sort_tile(1) : items == 2 ? (n + sort_tile(2) - 1) / sort_tile(2) : tiles;
+        const size_t ppass = (size_t)ptiles * 256;
+        CU(cudaMemsetAsync(h->hist_fused, 0, sizeof(int) * (ppass * passes + 1), st));      // ppass >= per_pass: covers the fused build too
+        if (persistent) {
             SortBuffers buf;
             buf.keys[0] = h->keys[0]; buf.keys[1] = h->keys[1]; buf.vals[0] = vals[0]; buf.vals[1] = vals[1];
             int *hist_all = h->hist_fused;
-            unsigned *bar = reinterpret_cast<unsigned *>(h->hist_fused + per_pass * passes);
-            int n_arg = n, kb = key_bits, passes_arg = passes, pp = (int)per_pass;
+            unsigned *bar = reinterpret_cast<unsigned *>(h->hist_fused + ppass * passes);
+            int n_arg = n, kb = key_bits, passes_arg = passes, pp = (int)ppass;
             double ks = key_scale, stdv_arg = stdv;
             void *args[] = {(void *)&fitness_dev, &n_arg, &kb, &ks, &passes_arg, &buf, &hist_all, &pp, &bar, &stdv_arg, (void *)&shaped_dev};
-            const void *fn = small ? (const void *)k_sort_persistent<SORT_ITEMS_SMALL> : (const void *)k_sort_persistent<SORT_ITEMS_LARGE>;
-            const cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(tiles), dim3(SORT_THREADS), args, 0, st);
+            const void *fn = items == 1 ? (const void *)k_sort_persistent<1> : items == 2 ? (const void *)k_sort_persistent<2>
+                           : small ? (const void *)k_sort_persistent<SORT_ITEMS_SMALL> : (const void *)k_sort_persistent<SORT_ITEMS_LARGE>;
+            const cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(ptiles), dim3(SORT_THREADS), args, 0, st);
             if (e == cudaSuccess) {
                 h->launches += 1;
                 return 0;
@@ -617,6 +625,8 @@ extern "C" int ses_rank_desc(ses_handle *h, const double *fitness_dev, int32_t n
             (void)cudaGetLastError();                              // refused (not co-resident, no cooperative launch): the fused build from now on
             h->k2_persistent = 0;
         }
+#else
+        CU(cudaMemsetAsync(h->hist_fused, 0, sizeof(int) * (per_pass * passes + 1), st));
 #endif
         if (small) k_sort_hist_first<SORT_ITEMS_SMALL><<<tiles, SORT_THREADS, 0, st>>>(fitness_dev, n, key_bits, key_scale, h->hist_fused);
         else k_sort_hist_first<SORT_ITEMS_LARGE><<<tiles, SORT_THREADS, 0, st>>>(fitness_dev, n, key_bits, key_scale, h->hist_fused);
