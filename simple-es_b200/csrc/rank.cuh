@@ -173,6 +173,26 @@ __device__ __forceinline__ unsigned long long sort_key(const double *__restrict_
     return ((2ull << key_bits) - 1ull) - (unsigned long long)v;
 }
 
+// inclusive prefix sum over the 256 threads of a sort CTA: warp shuffles + one pass over the 8 warp totals (two barriers instead
+// of the sixteen of a shared-memory Hillis-Steele scan); tmp: >= SORT_WARPS ints of shared memory
+__device__ __forceinline__ int sort_scan256(int v, int *tmp)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, off);
+        if (lane >= off) x += y;
+    }
+    __syncthreads();                                               // tmp may still be read by a previous use
+    if (lane == 31) tmp[w] = x;
+    __syncthreads();
+    int add = 0;
+#pragma unroll
+    for (int ww = 0; ww < SORT_WARPS; ++ww) add += ww < w ? tmp[ww] : 0;
+    return x + add;
+}
+
 // pass-0 histogram straight from the fitness vector (one tile = one CTA)
 template <int SORT_ITEMS>
 __device__ __forceinline__ void sort_hist_first_tile(const double *__restrict__ fitness, int n, int key_bits, double key_scale, int *hist)
@@ -229,15 +249,7 @@ __device__ __forceinline__ void sort_scatter_fused_tile(const double *__restrict
             t += v;
             if (c < (int)blockIdx.x) below += v;
         }
-        scan_tmp[tid] = t;
-        __syncthreads();
-        for (int off = 1; off < 256; off <<= 1) {
-            int v = tid >= off ? scan_tmp[tid - off] : 0;
-            __syncthreads();
-            scan_tmp[tid] += v;
-            __syncthreads();
-        }
-        digit_base[tid] = scan_tmp[tid] - t + below;
+        digit_base[tid] = sort_scan256(t, scan_tmp) - t + below;
     }
     for (int i = tid; i < SORT_WARPS * 256; i += SORT_THREADS) (&whist[0][0])[i] = 0;
     __syncthreads();

@@ -11,7 +11,7 @@
 //
 // What is emulated: __global__ functions called through simt::launch (the build script rewrites <<< >>>), threadIdx /
 // blockIdx / blockDim / gridDim (x only), static and dynamic __shared__, __syncthreads, __syncwarp, __ballot_sync,
-// __shfl_sync, __shfl_xor_sync, __match_any_sync, atomicAdd / atomicExch, the *_rn arithmetic intrinsics (plain IEEE
+// __shfl_sync, __shfl_xor_sync, __shfl_up_sync, __match_any_sync, atomicAdd / atomicExch, the *_rn arithmetic intrinsics (plain IEEE
 // operations: the translation unit is compiled with -ffp-contract=off), packed float2 intrinsics, bit casts, and the part
 // of the runtime API ses_abi.cu uses (device memory == host memory, one synchronous stream).
 #pragma once
@@ -365,6 +365,17 @@ inline T __shfl_xor_sync(unsigned, T v, int lanemask, int width = 32)
     const int lane = simt::g_cur->lane;
     const int s = lane ^ lanemask;
     if ((s & ~(width - 1)) != (lane & ~(width - 1)) || !((w.arrived[par] >> s) & 1u)) return v;
+    return simt::from_bits<T>(w.opnd[par][s]);
+}
+template <class T>
+inline T __shfl_up_sync(unsigned, T v, unsigned delta, int width = 32)
+{
+    SIMT_CNT(C_SHFL);
+    const int par = simt::warp_collective(simt::K_SHFL, simt::to_bits(v));
+    const simt::Warp &w = *simt::g_cur->warp;
+    const int lane = simt::g_cur->lane;
+    const int s = lane - (int)delta;
+    if (s < (lane & ~(width - 1)) || !((w.arrived[par] >> s) & 1u)) return v;      // below the segment: the lane keeps its own value
     return simt::from_bits<T>(w.opnd[par][s]);
 }
 template <class T>
